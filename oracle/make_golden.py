@@ -1,0 +1,142 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own functions (imported from
+/root/reference, build container only) on seeded synthetic inputs.  TEST INFRASTRUCTURE ONLY.
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+
+The fixtures pin the oracle (oracle/deepsir_oracle.py) — tests/test_oracle_golden.py replays them
+without the reference being present (the GPU box has no /root/reference).
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("DEEPSIR_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from network import matchnet as R_match  # noqa: E402  (reference)
+from network import model as R_model  # noqa: E402
+from network import tools as R_tools  # noqa: E402
+from common.math import se3_torch as R_se3  # noqa: E402
+
+from deepsir_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+torch.set_num_threads(1)  # single-thread MKL: the fixtures do not depend on the host's core count
+
+
+def sha(t):
+    return hashlib.sha256(np.ascontiguousarray(t.numpy()).tobytes()).hexdigest()[:16]
+
+
+def save(name, **kw):
+    arrs = {k: (v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in kw.items()}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print(name, {k: v.shape for k, v in arrs.items()})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    g = torch.Generator().manual_seed(7)
+
+    # ---- feature distance (matchnet.py:49-192) -------------------------------------------------
+    fs = torch.nn.functional.normalize(torch.randn(2, 64, 150, generator=g), dim=1)
+    fr = torch.nn.functional.normalize(torch.randn(2, 64, 170, generator=g), dim=1)
+    save("match_dense",
+         feat_src=fs, feat_ref=fr,
+         l2=R_match.match_features_V2(fs, fr, "l2"),
+         euclidean=R_match.match_features_V2(fs, fr, "euclidean"),
+         angle=R_match.match_features_V2(fs, fr, "angle"),
+         nc_l2=R_match.match_features(fs.permute(0, 2, 1).contiguous(), fr.permute(0, 2, 1).contiguous(), "l2"),
+         fd_sq=R_match.feat_dist(fs, fr, "sqeuclidean"),
+         fd_city=R_match.feat_dist(fs, fr, "cityblock"),
+         fd_euc=R_match.feat_dist(fs, fr, "euclidean"))
+
+    # ---- chunked argmin (model.py:558-569) on planted features, N=1500 with stride forced to 600 and
+    #      at the shipped stride 6000 on N=7000 (two chunks) -----------------------------------------
+    def ref_argmin(fs_, fr_, stride):
+        out = []
+        for n in range(int(np.ceil(fs_.shape[2] / stride))):
+            mm = R_match.match_features_V2(fs_[:, :, n * stride:(n + 1) * stride], fr_)
+            out.append(mm.min(dim=2, keepdim=False)[1])
+        return torch.cat(out, dim=1)
+
+    b = synth.make_batch(2, 1500, 64, "kitti", config=1)
+    save("match_argmin_1500", seed_config=1, n=1500, d=64, batch=2, sha_src=sha(b["feat_src"]), sha_ref=sha(b["feat_ref"]),
+         idx=ref_argmin(b["feat_src"], b["feat_ref"], 600), idx_full=ref_argmin(b["feat_src"], b["feat_ref"], 6000))
+    b = synth.make_batch(1, 7000, 32, "3dmatch", config=3)
+    save("match_argmin_7000", seed_config=3, n=7000, d=32, batch=1, sha_src=sha(b["feat_src"]), sha_ref=sha(b["feat_ref"]),
+         idx=ref_argmin(b["feat_src"], b["feat_ref"], 6000))
+    # ties: duplicated reference columns -> torch.min returns the first index
+    fr_dup = torch.cat([fr[:, :, :40], fr[:, :, :40], fr[:, :, 40:]], dim=2)
+    save("match_argmin_ties", feat_src=fs, feat_ref=fr_dup, idx=ref_argmin(fs, fr_dup, 6000))
+
+    # ---- gather (tools.py:211-221) -----------------------------------------------------------------
+    xyz = torch.randn(2, 3, 170, generator=g)
+    gi = torch.randint(0, 170, (2, 150), generator=g)
+    save("gather_v3", inputs=xyz, idx=gi, out=R_tools.gather_neighbour_V3(xyz, gi))
+
+    # ---- affinity + sinkhorn (matchnet.py:195-271) ----------------------------------------------
+    d = R_match.match_features_V2(fs[:, :, :40], fr[:, :, :50])
+    beta = torch.tensor([10.0, 4.0])
+    alpha = torch.tensor([0.5, 0.3])
+    aff = R_match.compute_affinity(beta, d, alpha)
+    save("affinity_sinkhorn", dist=d, beta=beta, alpha=alpha, affinity=aff,
+         affinity_scalar_alpha=R_match.compute_affinity(beta, d),
+         sinkhorn_slack=R_match.sinkhorn(aff, n_iters=5, slack=True),
+         sinkhorn_noslack=R_match.sinkhorn(aff, n_iters=5, slack=False),
+         sinkhorn_1row=aff - torch.logsumexp(aff, dim=2, keepdim=True))
+
+    # ---- weighted Kabsch (model.py:22-66) ---------------------------------------------------------
+    cases = {}
+    b = synth.make_batch(3, 400, 64, "kitti", config=1, first_pair=10)
+    src = b["points_src"][:, :, :3].contiguous()
+    tgt_full = torch.stack([b["points_ref"][i, b["perm"][i], :3] for i in range(3)])
+    cases["planted"] = (src, tgt_full, b["weights"])
+    cases["uniform_w"] = (src, tgt_full, torch.ones(3, 400, 1))
+    planar = src.clone(); planar[:, :, 2] = 0.0
+    Rz = synth._rot_zyx(0.3, 0.0, 0.0).float()
+    cases["planar"] = (planar, planar @ Rz.t() + torch.tensor([1.0, -2.0, 0.5]), torch.ones(3, 400, 1))
+    refl = src[:, :50].clone()
+    cases["reflection"] = (refl, refl * torch.tensor([1.0, 1.0, -1.0]), torch.ones(3, 50, 1))
+    cases["neg_w"] = (src, tgt_full, b["weights"] - 0.2)
+    cases["single_heavy"] = (src, tgt_full, torch.cat([torch.full((3, 1, 1), 1e3), torch.ones(3, 399, 1)], 1))
+    kw = {}
+    for name, (s, t, w) in cases.items():
+        T, inv = R_model.compute_rigid_transform_2(s, t, w)
+        assert inv is False
+        kw[name + "_src"], kw[name + "_tgt"], kw[name + "_w"], kw[name + "_T"] = s, t, w, T
+    save("kabsch2", **kw)
+
+    # ---- SE(3) (se3_torch.py) ------------------------------------------------------------------
+    Ta = torch.stack([synth.random_pose(g) for _ in range(4)])
+    Tb = torch.stack([synth.random_pose(g, any_axis=True, yaw_deg=90, tilt_scale=1.0) for _ in range(4)])
+    pts = torch.randn(4, 33, 3, generator=g) * 20
+    save("se3", Ta=Ta, Tb=Tb, pts=pts, identity=R_se3.identity(4), inverse=R_se3.inverse(Ta),
+         concat=R_se3.concatenate(Ta, Tb), transform=R_se3.transform(Ta, pts),
+         transform_v2=R_se3.transform_V2(Ta, pts.permute(0, 2, 1).contiguous()))
+
+    # ---- one full loop of model.py:551-601 with fixed features/weights (NN stages removed) -------------
+    b = synth.make_batch(2, 1200, 64, "oxford", config=5)
+    xyz_src = b["points_src"][:, :, :3].permute(0, 2, 1).contiguous()
+    xyz_ref = b["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
+    transforms, preds = [], []
+    for it in range(3):
+        idx = ref_argmin(b["feat_src"], b["feat_ref"], 6000)
+        ref_new = R_tools.gather_neighbour_V3(xyz_ref, idx)
+        sp = xyz_src.permute(0, 2, 1).contiguous()
+        T, _ = R_model.compute_rigid_transform_2(sp, ref_new.permute(0, 2, 1).contiguous(), b["weights"])
+        xyz_src = R_se3.transform(T, sp).permute(0, 2, 1).contiguous()
+        transforms.append(T if it == 0 else R_se3.concatenate(T, transforms[-1]))
+        preds.append(idx)
+    save("loop_oxford_1200", seed_config=5, n=1200, d=64, batch=2, sha_src=sha(b["feat_src"]),
+         transforms=torch.stack(transforms), pred=torch.stack(preds), xyz_src_final=xyz_src,
+         transform_gt=b["transform_gt"])
+
+
+if __name__ == "__main__":
+    main()
