@@ -1,0 +1,348 @@
+// C-ABI entry points (include/deepsir_b200.h).  Each function validates its arguments, carves the
+// caller's workspace, and enqueues kernels on the caller's stream.  No host synchronisation, no
+// allocation, no global state besides a thread-local "last CUDA error" string.
+#include <atomic>
+
+#include "common.cuh"
+#include "kabsch.cuh"
+#include "knn.cuh"
+#include "match.cuh"
+#include "match_tc.cuh"
+
+namespace dsir {
+static thread_local cudaError_t g_last_err = cudaSuccess;
+void set_last_cuda_error(cudaError_t e) { g_last_err = e; }
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace dsir
+
+using namespace dsir;
+
+extern "C" {
+
+int dsir_version(void) { return 100; }
+
+const char *dsir_strerror(int code) {
+    switch (code) {
+        case DSIR_OK: return "ok";
+        case DSIR_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size or unknown enum)";
+        case DSIR_ERR_UNSUPPORTED: return "shape not supported by the sm_100a kernels";
+        case DSIR_ERR_WORKSPACE: return "workspace missing or too small";
+        case DSIR_ERR_CUDA: return "CUDA call failed (see dsir_last_cuda_error)";
+        case DSIR_ERR_KNN_TOO_FEW: return "knn: fewer support points than k";
+        case DSIR_ERR_NO_DEVICE: return "no sm_100 (B200) device: deepsir_b200 has no other code path";
+        default: return "unknown error";
+    }
+}
+
+const char *dsir_last_cuda_error(void) { return cudaGetErrorString(g_last_err); }
+
+uint64_t dsir_launch_count(void) { return (uint64_t)g_launches.load(std::memory_order_relaxed); }
+
+int dsir_device_check(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return DSIR_ERR_NO_DEVICE; }
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return DSIR_ERR_NO_DEVICE;
+    }
+    return major == 10 ? DSIR_OK : DSIR_ERR_NO_DEVICE;
+}
+
+/* ------------------------------------------------------------------ KNN ------------------------ */
+size_t dsir_knn_workspace_bytes(int B, int Ns, int Nq, int k, int algo) {
+    (void)Nq; (void)k; (void)algo;
+    if (B <= 0 || Ns <= 0) return 256;
+    return ws_block((size_t)B * Ns * sizeof(float4)) + 256;
+}
+
+int dsir_knn_xyz(const float *support, int sup_stride, const float *query, int qry_stride, int B, int Ns, int Nq,
+                 int k, int64_t *idx, float *dist2, void *ws, size_t ws_bytes, int algo, dsir_stream_t stream) {
+    (void)algo;
+    if (!support || !query || !idx || B <= 0 || Ns <= 0 || Nq < 0 || sup_stride < 3 || qry_stride < 3 || k <= 0)
+        return DSIR_ERR_BAD_ARG;
+    if (k > 32) return DSIR_ERR_UNSUPPORTED;
+    if (Ns < k) return DSIR_ERR_KNN_TOO_FEW;
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace W(ws, ws_bytes);
+    float4 *sup4 = W.take<float4>((size_t)B * Ns);
+    if (!W.ok()) return DSIR_ERR_WORKSPACE;
+    int rc = launch_pack_xyz4(support, sup_stride, (long long)B * Ns, sup4, st);
+    if (rc) return rc;
+    KnnBruteParams P{};
+    P.sup4 = sup4; P.sup_bs = Ns;
+    P.query = query; P.qry_bs = (long long)Nq * qry_stride; P.qry_stride = qry_stride;
+    P.Ns = Ns; P.Nq = Nq; P.k = k;
+    P.idx = idx; P.idx_bs = (long long)Nq * k; P.dist2 = dist2;
+    P.idx2 = nullptr; P.idx2_bs = 0; P.idx2_rows = 0;
+    return launch_knn_brute(P, B, st);
+}
+
+static int pyramid_levels(int N, const int *ratios, int L, PyramidLevels *lv) {
+    if (L < 1 || L > DSIR_MAX_LEVELS) return DSIR_ERR_UNSUPPORTED;
+    lv->L = L;
+    int n = N, off = 0, offsub = 0;
+    for (int l = 0; l < L; ++l) {
+        if (ratios[l] < 1) return DSIR_ERR_BAD_ARG;
+        lv->n[l] = n; lv->m[l] = n / ratios[l]; lv->off[l] = off; lv->offsub[l] = offsub;
+        off += n; offsub += n / ratios[l];
+        n = n / ratios[l];
+    }
+    lv->sumN = off; lv->sumSub = offsub;
+    return DSIR_OK;
+}
+
+size_t dsir_knn_pyramid_workspace_bytes(int B, int N, int k, const int *ratios, int L, int algo) {
+    (void)k; (void)ratios; (void)L; (void)algo;
+    if (B <= 0 || N <= 0) return 256;
+    return ws_block((size_t)B * N * sizeof(float4)) + 256;
+}
+
+int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *ratios, int L, int k, float *xyz_cat,
+                     int64_t *neigh, int64_t *sub, int64_t *interp, void *ws, size_t ws_bytes, int algo,
+                     dsir_stream_t stream) {
+    (void)algo;
+    if (!pts || !ratios || !neigh || !sub || !interp || B <= 0 || N <= 0 || pt_stride < 3 || k <= 0) return DSIR_ERR_BAD_ARG;
+    if (k > 32) return DSIR_ERR_UNSUPPORTED;
+    PyramidLevels lv;
+    int rc = pyramid_levels(N, ratios, L, &lv);
+    if (rc) return rc;
+    for (int l = 0; l < L; ++l)
+        if (lv.n[l] < k || lv.m[l] < 1) return DSIR_ERR_KNN_TOO_FEW;
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace W(ws, ws_bytes);
+    float4 *pts4 = W.take<float4>((size_t)B * N);
+    if (!W.ok()) return DSIR_ERR_WORKSPACE;
+    if ((rc = launch_pack_xyz4(pts, pt_stride, (long long)B * N, pts4, st))) return rc;
+    if (xyz_cat && (rc = launch_pyramid_xyz(pts, pt_stride, B, N, lv, xyz_cat, st))) return rc;
+    for (int l = 0; l < L; ++l) {
+        // every level cloud is the first n[l] points of the original (prefix sub-sampling, data_base.py:169)
+        KnnBruteParams P{};
+        P.sup4 = pts4; P.sup_bs = N;
+        P.query = (const float *)pts4; P.qry_bs = (long long)N * 4; P.qry_stride = 4;
+        P.Ns = lv.n[l]; P.Nq = lv.n[l]; P.k = k;
+        P.idx = neigh + (size_t)lv.off[l] * k; P.idx_bs = (long long)lv.sumN * k; P.dist2 = nullptr;
+        P.idx2 = sub + (size_t)lv.offsub[l] * k; P.idx2_bs = (long long)lv.sumSub * k; P.idx2_rows = lv.m[l];
+        if ((rc = launch_knn_brute(P, B, st))) return rc;
+        KnnBruteParams U = P;  // 1-NN of every level point into the sub-cloud (data_base.py:170)
+        U.Ns = lv.m[l]; U.k = 1;
+        U.idx = interp + lv.off[l]; U.idx_bs = lv.sumN;
+        U.idx2 = nullptr; U.idx2_rows = 0;
+        if ((rc = launch_knn_brute(U, B, st))) return rc;
+    }
+    return DSIR_OK;
+}
+
+/* ------------------------------------------------------------------ match ---------------------- */
+static bool feat_ok(const dsir_feat &f) { return f.ptr != nullptr; }
+
+size_t dsir_match_dense_workspace_bytes(int B, int J, int K) {
+    if (B <= 0 || J <= 0 || K <= 0) return 256;
+    return ws_block((size_t)B * J * sizeof(float)) + ws_block((size_t)B * K * sizeof(float)) + 256;
+}
+
+int dsir_match_dense(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int metric, float *dist, void *ws,
+                     size_t ws_bytes, dsir_stream_t stream) {
+    if (!feat_ok(fs) || !feat_ok(fr) || !dist || B <= 0 || C <= 0 || J <= 0 || K <= 0) return DSIR_ERR_BAD_ARG;
+    if (metric < DSIR_METRIC_L2 || metric > DSIR_METRIC_SQDIFF_SQRT) return DSIR_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    MatchParams P{};
+    P.fs = fs; P.fr = fr; P.B = B; P.C = C; P.J = J; P.K = K;
+    P.dense = dist; P.metric = metric;
+    if (metric == DSIR_METRIC_L2 || metric == DSIR_METRIC_EUCLIDEAN) {
+        Workspace W(ws, ws_bytes);
+        float *ns = W.take<float>((size_t)B * J);
+        float *nr = W.take<float>((size_t)B * K);
+        if (!W.ok()) return DSIR_ERR_WORKSPACE;
+        int rc;
+        if ((rc = launch_sqnorm(fs, B, C, J, ns, st))) return rc;
+        if ((rc = launch_sqnorm(fr, B, C, K, nr, st))) return rc;
+        P.ns = ns; P.nr = nr;
+    }
+    return launch_match_fp32(P, MATCH_MODE_DENSE, st);
+}
+
+size_t dsir_match_argmin_workspace_bytes(int B, int C, int J, int K, int algo) {
+    if (B <= 0 || J <= 0 || K <= 0) return 256;
+    size_t bytes = ws_block((size_t)B * J * sizeof(float)) + ws_block((size_t)B * K * sizeof(float)) + 256;
+    if (algo != DSIR_MATCH_FP32) bytes += match_tc_workspace_bytes(B, C, J, K);
+    return bytes;
+}
+
+int dsir_match_argmin(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int64_t *idx, float *min_d, void *ws,
+                      size_t ws_bytes, int algo, dsir_stream_t stream) {
+    if (!feat_ok(fs) || !feat_ok(fr) || !idx || B <= 0 || C <= 0 || J <= 0 || K <= 0) return DSIR_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace W(ws, ws_bytes);
+    float *ns = W.take<float>((size_t)B * J);
+    float *nr = W.take<float>((size_t)B * K);
+    if (!W.ok()) return DSIR_ERR_WORKSPACE;
+    int rc;
+    if ((rc = launch_sqnorm(fs, B, C, J, ns, st))) return rc;
+    if ((rc = launch_sqnorm(fr, B, C, K, nr, st))) return rc;
+    MatchParams P{};
+    P.fs = fs; P.fr = fr; P.B = B; P.C = C; P.J = J; P.K = K; P.ns = ns; P.nr = nr;
+    P.idx = idx; P.min_d = min_d;
+    bool tc_ok = match_tc_supported(fs, fr, B, C, J, K);
+    if (algo == DSIR_MATCH_TC && !tc_ok) return DSIR_ERR_UNSUPPORTED;
+    if (algo == DSIR_MATCH_TC || (algo == DSIR_MATCH_AUTO && tc_ok && match_tc_profitable(B, C, J, K))) {
+        size_t used = W.off;
+        return launch_match_tc(P, (char *)ws + used, ws_bytes - used, st);
+    }
+    return launch_match_fp32(P, MATCH_MODE_ARGMIN, st);
+}
+
+size_t dsir_match_soft_workspace_bytes(int B, int C, int J, int K) {
+    (void)C;
+    if (B <= 0 || J <= 0 || K <= 0) return 256;
+    return ws_block((size_t)B * J * sizeof(float)) + ws_block((size_t)B * K * sizeof(float)) + 256;
+}
+
+int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
+                    const float *col_bias, const float *xyz_ref, float *y_soft, float *lse, int topk,
+                    int64_t *topk_idx, float *topk_w, void *ws, size_t ws_bytes, dsir_stream_t stream) {
+    if (!feat_ok(fs) || !feat_ok(fr) || !beta || !alpha || B <= 0 || C <= 0 || J <= 0 || K <= 0) return DSIR_ERR_BAD_ARG;
+    if (y_soft && !xyz_ref) return DSIR_ERR_BAD_ARG;
+    if (topk != 0) { (void)topk_idx; (void)topk_w; return DSIR_ERR_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace W(ws, ws_bytes);
+    float *ns = W.take<float>((size_t)B * J);
+    float *nr = W.take<float>((size_t)B * K);
+    if (!W.ok()) return DSIR_ERR_WORKSPACE;
+    int rc;
+    if ((rc = launch_sqnorm(fs, B, C, J, ns, st))) return rc;
+    if ((rc = launch_sqnorm(fr, B, C, K, nr, st))) return rc;
+    MatchParams P{};
+    P.fs = fs; P.fr = fr; P.B = B; P.C = C; P.J = J; P.K = K; P.ns = ns; P.nr = nr;
+    P.beta = beta; P.alpha = alpha; P.col_bias = col_bias; P.xyz_ref = xyz_ref; P.y_soft = y_soft; P.lse = lse;
+    return launch_match_fp32(P, MATCH_MODE_SOFT, st);
+}
+
+int dsir_gather_points(const float *in, int B, int C, int N, const int64_t *idx, int M, float *out,
+                       dsir_stream_t stream) {
+    if (!in || !idx || !out || B <= 0 || C <= 0 || N <= 0 || M < 0) return DSIR_ERR_BAD_ARG;
+    return launch_gather_points(in, B, C, N, idx, M, out, (cudaStream_t)stream);
+}
+
+/* ------------------------------------------------------------------ Kabsch --------------------- */
+size_t dsir_kabsch_workspace_bytes(int B, int M) {
+    if (B <= 0 || M <= 0) return 256;
+    return ws_block((size_t)B * kabsch_num_blocks(M) * KB_NMOM * sizeof(double)) + 256;
+}
+
+static int kabsch_common(dsir_points src, dsir_points tgt, const float *w, int64_t w_bs, const int64_t *gather, int B,
+                         int M, double **partials, int *nblk, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!src.ptr || !tgt.ptr || B <= 0 || M <= 0) return DSIR_ERR_BAD_ARG;
+    Workspace W(ws, ws_bytes);
+    *nblk = kabsch_num_blocks(M);
+    *partials = W.take<double>((size_t)B * (*nblk) * KB_NMOM);
+    if (!W.ok()) return DSIR_ERR_WORKSPACE;
+    KabschParams P{};
+    P.src = src; P.tgt = tgt; P.w = w; P.w_bs = w_bs; P.gather = gather; P.B = B; P.M = M; P.partials = *partials;
+    return launch_kabsch_moments(P, *nblk, st);
+}
+
+int dsir_kabsch(dsir_points src, dsir_points tgt, const float *w, int64_t w_batch_stride, const int64_t *gather,
+                int B, int M, float *T, int32_t *status, double *moments, void *ws, size_t ws_bytes,
+                dsir_stream_t stream) {
+    if (!T) return DSIR_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *partials; int nblk;
+    int rc = kabsch_common(src, tgt, w, w_batch_stride, gather, B, M, &partials, &nblk, ws, ws_bytes, st);
+    if (rc) return rc;
+    return launch_kabsch_solve(partials, nblk, B, T, status, moments, nullptr, nullptr, 0, st);
+}
+
+int dsir_kabsch_moments(dsir_points src, dsir_points tgt, const float *w, int64_t w_batch_stride,
+                        const int64_t *gather, int B, int M, double *moments, void *ws, size_t ws_bytes,
+                        dsir_stream_t stream) {
+    if (!moments) return DSIR_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *partials; int nblk;
+    int rc = kabsch_common(src, tgt, w, w_batch_stride, gather, B, M, &partials, &nblk, ws, ws_bytes, st);
+    if (rc) return rc;
+    return launch_kabsch_reduce(partials, nblk, B, moments, st);
+}
+
+int dsir_kabsch_from_moments(const double *moments, int B, float *T, int32_t *status, dsir_stream_t stream) {
+    if (!moments || !T || B <= 0) return DSIR_ERR_BAD_ARG;
+    return launch_kabsch_solve(moments, 1, B, T, status, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+int dsir_kabsch_soft(dsir_points src, const float *y_soft, const float *rowmass, int B, int M, float *T,
+                     int32_t *status, void *ws, size_t ws_bytes, dsir_stream_t stream) {
+    if (!y_soft || !rowmass || !T) return DSIR_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    dsir_points tgt{y_soft, (int64_t)M * 3, 3, 1};
+    double *partials; int nblk;
+    int rc = kabsch_common(src, tgt, rowmass, M, nullptr, B, M, &partials, &nblk, ws, ws_bytes, st);
+    if (rc) return rc;
+    return launch_kabsch_solve(partials, nblk, B, T, status, nullptr, nullptr, nullptr, 1, st);
+}
+
+/* ------------------------------------------------------------------ SE(3) ---------------------- */
+int dsir_se3_apply(const float *T, int64_t T_batch_stride, dsir_points pts, int B, int N, float *out,
+                   int64_t out_batch_stride, int64_t out_point_stride, int64_t out_coord_stride,
+                   int rotate_only, dsir_stream_t stream) {
+    if (!T || !pts.ptr || !out || B <= 0 || N < 0) return DSIR_ERR_BAD_ARG;
+    return launch_se3_apply(T, T_batch_stride, pts, B, N, out, out_batch_stride, out_point_stride, out_coord_stride,
+                            rotate_only, (cudaStream_t)stream);
+}
+
+int dsir_se3_compose(const float *a, int64_t a_bs, const float *b, int64_t b_bs, int B, float *out,
+                     dsir_stream_t stream) {
+    if (!a || !b || !out || B <= 0) return DSIR_ERR_BAD_ARG;
+    return launch_se3_compose(a, a_bs, b, b_bs, B, out, (cudaStream_t)stream);
+}
+
+int dsir_se3_inverse(const float *T, int64_t T_bs, int B, float *out, dsir_stream_t stream) {
+    if (!T || !out || B <= 0) return DSIR_ERR_BAD_ARG;
+    return launch_se3_inverse(T, T_bs, B, out, (cudaStream_t)stream);
+}
+
+/* ------------------------------------------------------------------ loop ----------------------- */
+size_t dsir_align_loop_workspace_bytes(int B, int C, int J, int K, int algo) {
+    if (B <= 0 || J <= 0 || K <= 0) return 256;
+    return dsir_match_argmin_workspace_bytes(B, C, J, K, algo) + dsir_kabsch_workspace_bytes(B, J) +
+           ws_block((size_t)B * J * sizeof(int64_t)) + ws_block((size_t)B * 12 * sizeof(float)) + 256;
+}
+
+int dsir_align_loop(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, float *xyz_src, const float *xyz_ref,
+                    const float *weights, int iters, float *transforms, int64_t *pred_idx, int32_t *status,
+                    void *ws, size_t ws_bytes, int algo, dsir_stream_t stream) {
+    if (!feat_ok(fs) || !feat_ok(fr) || !xyz_src || !xyz_ref || !transforms || B <= 0 || C <= 0 || J <= 0 || K <= 0 ||
+        iters <= 0)
+        return DSIR_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace W(ws, ws_bytes);
+    int64_t *idx_scratch = W.take<int64_t>((size_t)B * J);
+    float *T_it = W.take<float>((size_t)B * 12);
+    if (!W.ok()) return DSIR_ERR_WORKSPACE;
+    size_t match_bytes = dsir_match_argmin_workspace_bytes(B, C, J, K, algo);
+    size_t kab_bytes = dsir_kabsch_workspace_bytes(B, J);
+    if (W.off + match_bytes + kab_bytes > ws_bytes) return DSIR_ERR_WORKSPACE;
+    char *match_ws = (char *)ws + W.off;
+    char *kab_ws = match_ws + match_bytes;
+
+    dsir_points src{xyz_src, (int64_t)3 * J, 1, J};  // [B,3,J]
+    dsir_points ref{xyz_ref, (int64_t)3 * K, 1, K};  // [B,3,K]
+    for (int it = 0; it < iters; ++it) {
+        int64_t *idx = pred_idx ? pred_idx + (size_t)it * B * J : idx_scratch;
+        int rc = dsir_match_argmin(fs, fr, B, C, J, K, idx, nullptr, match_ws, match_bytes, algo, stream);  // :558-569
+        if (rc) return rc;
+        double *partials; int nblk;
+        rc = kabsch_common(src, ref, weights, J, idx, B, J, &partials, &nblk, kab_ws, kab_bytes, st);    // :571,:588
+        if (rc) return rc;
+        float *T_cum = transforms + (size_t)it * B * 12;
+        const float *T_prev = it > 0 ? transforms + (size_t)(it - 1) * B * 12 : nullptr;
+        rc = launch_kabsch_solve(partials, nblk, B, T_it, status ? status + (size_t)it * B : nullptr, nullptr, T_prev,
+                                 T_cum, 0, st);                                                              // :595
+        if (rc) return rc;
+        rc = launch_se3_apply(T_it, 12, src, B, J, xyz_src, (long long)3 * J, 1, J, 0, st);                  // :590
+        if (rc) return rc;
+    }
+    return DSIR_OK;
+}
+
+}  // extern "C"

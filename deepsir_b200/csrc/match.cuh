@@ -1,0 +1,31 @@
+#pragma once
+#include "common.cuh"
+
+namespace dsir {
+
+struct MatchParams {
+    dsir_feat fs, fr;
+    int B, C, J, K;
+    const float *ns, *nr;  // squared norms [B,J], [B,K] (sequential fma chains over c)
+    // argmin outputs
+    int64_t *idx;
+    float *min_d;
+    // dense output
+    float *dense;
+    int metric;
+    // soft
+    const float *beta, *alpha, *col_bias, *xyz_ref;
+    float *y_soft, *lse;
+};
+
+enum { MATCH_MODE_ARGMIN = 0, MATCH_MODE_DENSE = 1, MATCH_MODE_SOFT = 2 };
+
+int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, cudaStream_t st);
+int launch_match_fp32(const MatchParams &P, int mode, cudaStream_t st);
+
+// the exact fp32 distance every path agrees on:  ((-2*dot) + ns) + nr,  dot = fma chain over c ascending
+__device__ __forceinline__ float l2_from_dot(float dot, float ns, float nr) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(-2.f, dot), ns), nr);
+}
+
+}  // namespace dsir

@@ -1,0 +1,260 @@
+// Feature-distance contraction on the fp32 CUDA cores, with three fused epilogues:
+//   ARGMIN : row-wise first-index minimum          (network/model.py:558-569 of the reference)
+//   DENSE  : materialised [B,J,K] matrix            (network/matchnet.py:49-192)
+//   SOFT   : affinity + online row softmax + soft target, [J,K] never written
+//            (network/matchnet.py:195-208,259; network/model.py:81-84)
+// This kernel DEFINES the fp32 value every other path must reproduce:
+//     dot_jk = fma(s_{C-1}, r_{C-1}, ... fma(s_0, r_0, 0))   (channels ascending)
+//     d_jk   = ((-2 * dot_jk) + |s_j|^2) + |r_k|^2            (op order of matchnet.py:110-112)
+// It is the refine/fallback stage of the tcgen05 path (match_tc.cu) and the whole path for the soft
+// variant, whose 1e-4 relative tolerance rules out tf32 inputs.
+#include "match.cuh"
+
+namespace dsir {
+
+constexpr int TM = 128, TN = 128, CK = 16, MT = 256;
+constexpr int PITCH = TM + 4;
+
+__global__ void sqnorm_kernel(dsir_feat f, int C, int N, float *__restrict__ out) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = blockIdx.y;
+    if (n >= N) return;
+    const float *p = f.ptr + (size_t)b * f.batch_stride + (size_t)n * f.point_stride;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) {
+        float v = p[(size_t)c * f.chan_stride];
+        acc = __fmaf_rn(v, v, acc);
+    }
+    out[(size_t)b * N + n] = acc;
+}
+
+int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, cudaStream_t st) {
+    dim3 grid(cdiv(N, 256), B);
+    sqnorm_kernel<<<grid, 256, 0, st>>>(f, C, N, out);
+    DSIR_LAUNCH_CHECK();
+    return DSIR_OK;
+}
+
+// INNER: 0 = dot product, 1 = sum of squared differences, 2 = sum of absolute differences
+template <int MODE, int INNER>
+__global__ __launch_bounds__(MT, 2) void match_fp32_kernel(MatchParams P) {
+    __shared__ __align__(16) float As[CK][PITCH];
+    __shared__ __align__(16) float Bs[CK][PITCH];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int b = blockIdx.y;
+    const int j0 = blockIdx.x * TM;
+    const float *fsb = P.fs.ptr + (size_t)b * P.fs.batch_stride;
+    const float *frb = P.fr.ptr + (size_t)b * P.fr.batch_stride;
+    const bool src_cn = P.fs.point_stride == 1;
+    const bool ref_cn = P.fr.point_stride == 1;
+
+    int rowi[8];
+    float nsv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        rowi[i] = j0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        nsv[i] = (MODE != MATCH_MODE_DENSE || INNER == 0) && rowi[i] < P.J && P.ns ? P.ns[(size_t)b * P.J + rowi[i]] : 0.f;
+    }
+
+    // per-row running state
+    float best_d[8];
+    int best_k[8];
+    float sm[8], sl[8], sx[8], sy[8], sz[8];
+    float beta = 0.f, alpha = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        best_d[i] = INFINITY; best_k[i] = 0;
+        sm[i] = -INFINITY; sl[i] = 0.f; sx[i] = 0.f; sy[i] = 0.f; sz[i] = 0.f;
+    }
+    if (MODE == MATCH_MODE_SOFT) { beta = P.beta[b]; alpha = P.alpha[b]; }
+
+    for (int k0 = 0; k0 < P.K; k0 += TN) {
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+        for (int c0 = 0; c0 < P.C; c0 += CK) {
+            // ---- stage a [CK x TM] slab of source and a [CK x TN] slab of reference features ----
+#pragma unroll
+            for (int e = tid; e < CK * TM; e += MT) {
+                int c, n;
+                if (src_cn) { c = e / TM; n = e % TM; } else { n = e / CK; c = e % CK; }
+                float v = 0.f;
+                if (c0 + c < P.C && j0 + n < P.J)
+                    v = fsb[(size_t)(c0 + c) * P.fs.chan_stride + (size_t)(j0 + n) * P.fs.point_stride];
+                As[c][n] = v;
+            }
+#pragma unroll
+            for (int e = tid; e < CK * TN; e += MT) {
+                int c, n;
+                if (ref_cn) { c = e / TN; n = e % TN; } else { n = e / CK; c = e % CK; }
+                float v = 0.f;
+                if (c0 + c < P.C && k0 + n < P.K)
+                    v = frb[(size_t)(c0 + c) * P.fr.chan_stride + (size_t)(k0 + n) * P.fr.point_stride];
+                Bs[c][n] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < CK; ++c) {
+                float4 a0 = *reinterpret_cast<const float4 *>(&As[c][ty * 4]);
+                float4 a1 = *reinterpret_cast<const float4 *>(&As[c][64 + ty * 4]);
+                float4 b0 = *reinterpret_cast<const float4 *>(&Bs[c][tx * 4]);
+                float4 b1 = *reinterpret_cast<const float4 *>(&Bs[c][64 + tx * 4]);
+                float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (INNER == 0) {
+                            acc[i][j] = __fmaf_rn(a[i], bb[j], acc[i][j]);
+                        } else if (INNER == 1) {
+                            float df = __fsub_rn(a[i], bb[j]);
+                            acc[i][j] = __fmaf_rn(df, df, acc[i][j]);
+                        } else {
+                            acc[i][j] = __fadd_rn(acc[i][j], fabsf(__fsub_rn(a[i], bb[j])));
+                        }
+                    }
+            }
+            __syncthreads();
+        }
+
+        // ---- fused epilogue on the 8x8 register tile ----
+        int colk[8];
+        float nrv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            colk[j] = k0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            nrv[j] = (INNER == 0 && P.nr && colk[j] < P.K) ? P.nr[(size_t)b * P.K + colk[j]] : 0.f;
+        }
+        if (MODE == MATCH_MODE_ARGMIN) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float d = l2_from_dot(acc[i][j], nsv[i], nrv[j]);
+                    if (colk[j] < P.K && d < best_d[i]) { best_d[i] = d; best_k[i] = colk[j]; }
+                }
+        } else if (MODE == MATCH_MODE_DENSE) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (rowi[i] >= P.J) continue;
+                float *o = P.dense + ((size_t)b * P.J + rowi[i]) * P.K;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (colk[j] >= P.K) continue;
+                    float v;
+                    if (INNER != 0) v = (P.metric == DSIR_METRIC_SQDIFF_SQRT) ? sqrtf(__fadd_rn(acc[i][j], 1e-16f)) : acc[i][j];
+                    else if (P.metric == DSIR_METRIC_ACOS_DOT) v = acosf(acc[i][j]);
+                    else {
+                        v = l2_from_dot(acc[i][j], nsv[i], nrv[j]);
+                        if (P.metric == DSIR_METRIC_EUCLIDEAN) v = sqrtf(__fadd_rn(v, 1e-16f));
+                    }
+                    o[colk[j]] = v;
+                }
+            }
+        } else {  // SOFT: online softmax over this thread's 8 columns of each row
+            float bias[8], rx[8], ry[8], rz[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                bool ok = colk[j] < P.K;
+                bias[j] = (ok && P.col_bias) ? P.col_bias[(size_t)b * P.K + colk[j]] : 0.f;
+                const float *r = P.xyz_ref + ((size_t)b * P.K + (ok ? colk[j] : 0)) * 3;
+                rx[j] = (ok && P.y_soft) ? r[0] : 0.f;
+                ry[j] = (ok && P.y_soft) ? r[1] : 0.f;
+                rz[j] = (ok && P.y_soft) ? r[2] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float lg[8];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float d = l2_from_dot(acc[i][j], nsv[i], nrv[j]);
+                    float a = __fadd_rn(__fmul_rn(-beta, __fsub_rn(d, alpha)), bias[j]);
+                    lg[j] = colk[j] < P.K ? a : -INFINITY;
+                    mx = fmaxf(mx, lg[j]);
+                }
+                float mnew = fmaxf(sm[i], mx);
+                if (mnew == -INFINITY) continue;
+                float sc = __expf(sm[i] - mnew);
+                float l = sl[i] * sc, x = sx[i] * sc, y = sy[i] * sc, z = sz[i] * sc;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float p = __expf(lg[j] - mnew);
+                    l += p;
+                    x = __fmaf_rn(p, rx[j], x);
+                    y = __fmaf_rn(p, ry[j], y);
+                    z = __fmaf_rn(p, rz[j], z);
+                }
+                sm[i] = mnew; sl[i] = l; sx[i] = x; sy[i] = y; sz[i] = z;
+            }
+        }
+    }
+
+    // ---- combine the 16 threads (tx) that share each row; they are 16 consecutive lanes ----
+    if (MODE == MATCH_MODE_ARGMIN) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float d = best_d[i];
+            int k = best_k[i];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                float d2 = __shfl_xor_sync(0xffffffffu, d, o);
+                int k2 = __shfl_xor_sync(0xffffffffu, k, o);
+                if (d2 < d || (d2 == d && k2 < k)) { d = d2; k = k2; }
+            }
+            if (tx == 0 && rowi[i] < P.J) {
+                P.idx[(size_t)b * P.J + rowi[i]] = (int64_t)k;
+                if (P.min_d) P.min_d[(size_t)b * P.J + rowi[i]] = d;
+            }
+        }
+    } else if (MODE == MATCH_MODE_SOFT) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float m = sm[i];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float sc = (sm[i] == -INFINITY) ? 0.f : __expf(sm[i] - m);
+            float l = sl[i] * sc, x = sx[i] * sc, y = sy[i] * sc, z = sz[i] * sc;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                l += __shfl_xor_sync(0xffffffffu, l, o);
+                x += __shfl_xor_sync(0xffffffffu, x, o);
+                y += __shfl_xor_sync(0xffffffffu, y, o);
+                z += __shfl_xor_sync(0xffffffffu, z, o);
+            }
+            if (tx == 0 && rowi[i] < P.J) {
+                size_t r = (size_t)b * P.J + rowi[i];
+                if (P.lse) P.lse[r] = m + logf(l);
+                if (P.y_soft) {
+                    // weights w = p/l sum to s = 1 (up to rounding): y = (sum w r) / (s + 1e-16)
+                    float inv = 1.f / l;
+                    P.y_soft[r * 3 + 0] = x * inv;
+                    P.y_soft[r * 3 + 1] = y * inv;
+                    P.y_soft[r * 3 + 2] = z * inv;
+                }
+            }
+        }
+    }
+}
+
+int launch_match_fp32(const MatchParams &P, int mode, cudaStream_t st) {
+    if (P.B <= 0 || P.J <= 0 || P.K <= 0 || P.C <= 0) return DSIR_ERR_BAD_ARG;
+    dim3 grid(cdiv(P.J, TM), P.B);
+    if (mode == MATCH_MODE_ARGMIN) match_fp32_kernel<MATCH_MODE_ARGMIN, 0><<<grid, MT, 0, st>>>(P);
+    else if (mode == MATCH_MODE_SOFT) match_fp32_kernel<MATCH_MODE_SOFT, 0><<<grid, MT, 0, st>>>(P);
+    else if (mode == MATCH_MODE_DENSE) {
+        if (P.metric == DSIR_METRIC_SQDIFF || P.metric == DSIR_METRIC_SQDIFF_SQRT) match_fp32_kernel<MATCH_MODE_DENSE, 1><<<grid, MT, 0, st>>>(P);
+        else if (P.metric == DSIR_METRIC_CITYBLOCK) match_fp32_kernel<MATCH_MODE_DENSE, 2><<<grid, MT, 0, st>>>(P);
+        else match_fp32_kernel<MATCH_MODE_DENSE, 0><<<grid, MT, 0, st>>>(P);
+    } else return DSIR_ERR_BAD_ARG;
+    DSIR_LAUNCH_CHECK();
+    return DSIR_OK;
+}
+
+}  // namespace dsir

@@ -1,0 +1,12 @@
+#pragma once
+#include "match.cuh"
+
+namespace dsir {
+
+// tcgen05/TMEM filter + exact fp32 refine (match_tc.cu)
+bool match_tc_supported(const dsir_feat &fs, const dsir_feat &fr, int B, int C, int J, int K);
+bool match_tc_profitable(int B, int C, int J, int K);
+size_t match_tc_workspace_bytes(int B, int C, int J, int K);
+int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace dsir

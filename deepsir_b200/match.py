@@ -1,0 +1,144 @@
+"""Feature distance + correspondence, mirroring network/matchnet.py and network/model.py:558-571 of the
+reference (same function names, argument meaning and shapes), executed by libdeepsir_b200.so."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+_EPS = 1e-16  # network/matchnet.py:_EPS
+
+
+def _dense(fs, fr, B, C, J, K, metric, keep, dev):
+    out = torch.empty(B, J, K, dtype=torch.float32, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.dsir_match_dense_workspace_bytes(B, J, K), dev)
+    L.check(lib.dsir_match_dense(fs, fr, B, C, J, K, metric, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                 L.stream_ptr(dev)), "dsir_match_dense")
+    del keep
+    return out
+
+
+def square_distance_V2(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """network/matchnet.py:96-113.  src [B,C,N], dst [B,C,M] -> [B,N,M]."""
+    dev = L.require_cuda(src, dst)
+    (fs, a), (fr, b) = L.feat_cn(src), L.feat_cn(dst)
+    return _dense(fs, fr, src.shape[0], src.shape[1], src.shape[2], dst.shape[2], L.METRIC_L2, (a, b), dev)
+
+
+def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """network/matchnet.py:49-66.  src [B,N,C], dst [B,M,C] -> [B,N,M]."""
+    dev = L.require_cuda(src, dst)
+    (fs, a), (fr, b) = L.feat_nc(src), L.feat_nc(dst)
+    return _dense(fs, fr, src.shape[0], src.shape[2], src.shape[1], dst.shape[1], L.METRIC_L2, (a, b), dev)
+
+
+def match_features_V2(feat_src, feat_ref, metric="l2"):
+    """network/matchnet.py:116-144.  feat_src [B,C,J], feat_ref [B,C,K] -> [B,J,K]."""
+    assert feat_src.shape[1] == feat_ref.shape[1]
+    dev = L.require_cuda(feat_src, feat_ref)
+    B, C, J = feat_src.shape
+    K = feat_ref.shape[2]
+    if metric == "l2":
+        code = L.METRIC_L2
+    elif metric == "euclidean":
+        code = L.METRIC_EUCLIDEAN
+    elif metric == "angle":
+        feat_src = feat_src / (torch.norm(feat_src, dim=1, keepdim=True) + _EPS)
+        feat_ref = feat_ref / (torch.norm(feat_ref, dim=1, keepdim=True) + _EPS)
+        code = L.METRIC_ACOS_DOT
+    else:
+        raise NotImplementedError
+    (fs, a), (fr, b) = L.feat_cn(feat_src), L.feat_cn(feat_ref)
+    return _dense(fs, fr, B, C, J, K, code, (a, b), dev)
+
+
+def match_features(feat_src, feat_ref, metric="l2"):
+    """network/matchnet.py:69-93.  feat_src [B,J,C], feat_ref [B,K,C] -> [B,J,K]."""
+    assert feat_src.shape[-1] == feat_ref.shape[-1]
+    dev = L.require_cuda(feat_src, feat_ref)
+    B, J, C = feat_src.shape
+    K = feat_ref.shape[1]
+    if metric == "l2":
+        code = L.METRIC_L2
+    elif metric == "angle":
+        feat_src = feat_src / (torch.norm(feat_src, dim=-1, keepdim=True) + _EPS)
+        feat_ref = feat_ref / (torch.norm(feat_ref, dim=-1, keepdim=True) + _EPS)
+        code = L.METRIC_ACOS_DOT
+    else:
+        raise NotImplementedError
+    (fs, a), (fr, b) = L.feat_nc(feat_src), L.feat_nc(feat_ref)
+    return _dense(fs, fr, B, C, J, K, code, (a, b), dev)
+
+
+def feat_dist(feat_src, feat_ref, metric="sqeuclidean"):
+    """network/matchnet.py:147-192 without the [B,C,J,K] intermediate.  [B,C,J],[B,C,K] -> [B,J,K]."""
+    assert feat_src.shape[1] == feat_ref.shape[1]
+    if metric == "angle":
+        return match_features_V2(feat_src, feat_ref, "angle")
+    code = {"sqeuclidean": L.METRIC_SQDIFF, "euclidean": L.METRIC_SQDIFF_SQRT, "cityblock": L.METRIC_CITYBLOCK}.get(metric)
+    if code is None:
+        raise NotImplementedError("The following metric is not implemented: {}".format(metric))
+    dev = L.require_cuda(feat_src, feat_ref)
+    (fs, a), (fr, b) = L.feat_cn(feat_src), L.feat_cn(feat_ref)
+    return _dense(fs, fr, feat_src.shape[0], feat_src.shape[1], feat_src.shape[2], feat_ref.shape[2], code, (a, b), dev)
+
+
+def match_argmin(feat_src, feat_ref, return_min=False, algo=L.MATCH_AUTO):
+    """The fused replacement of network/model.py:558-569 (chunked match_features_V2 + .min(dim=2)[1]):
+    feat_src [B,C,J], feat_ref [B,C,K] -> indexs int64 [B,J]; the [J,K] matrix is never written."""
+    assert feat_src.shape[1] == feat_ref.shape[1]
+    dev = L.require_cuda(feat_src, feat_ref)
+    B, C, J = feat_src.shape
+    K = feat_ref.shape[2]
+    (fs, a), (fr, b) = L.feat_cn(feat_src), L.feat_cn(feat_ref)
+    idx = torch.empty(B, J, dtype=torch.int64, device=dev)
+    mind = torch.empty(B, J, dtype=torch.float32, device=dev) if return_min else None
+    lib = L.lib()
+    ws = L.workspace(lib.dsir_match_argmin_workspace_bytes(B, C, J, K, algo), dev)
+    L.check(lib.dsir_match_argmin(fs, fr, B, C, J, K, idx.data_ptr(), L.ptr(mind), ws.data_ptr(), ws.numel(), algo,
+                                  L.stream_ptr(dev)), "dsir_match_argmin")
+    return (idx, mind) if return_min else idx
+
+
+def compute_affinity(beta, feat_distance, alpha=0.5):
+    """network/matchnet.py:195-208 (elementwise; kept for signature parity — the fused path is match_soft)."""
+    if isinstance(alpha, float):
+        return -beta[:, None, None] * (feat_distance - alpha)
+    return -beta[:, None, None] * (feat_distance - alpha[:, None, None])
+
+
+def match_soft(feat_src, feat_ref, xyz_ref, beta, alpha=0.5, col_bias=None):
+    """Fused compute_affinity (matchnet.py:195-208) + row softmax (sinkhorn row pass, :259) + soft target
+    (network/model.py:81-84).  feat [B,C,J],[B,C,K]; xyz_ref [B,K,3]; beta [B]; alpha float or [B].
+    Returns (y_soft [B,J,3], rowmass [B,J], lse [B,J])."""
+    dev = L.require_cuda(feat_src, feat_ref, xyz_ref, beta)
+    B, C, J = feat_src.shape
+    K = feat_ref.shape[2]
+    (fs, a), (fr, b) = L.feat_cn(feat_src), L.feat_cn(feat_ref)
+    beta = beta.to(torch.float32).contiguous()
+    alpha_t = torch.full((B,), float(alpha), dtype=torch.float32, device=dev) if isinstance(alpha, float) \
+        else alpha.to(torch.float32).contiguous()
+    xyz_ref = xyz_ref.contiguous()
+    cb = col_bias.contiguous() if col_bias is not None else None
+    y = torch.empty(B, J, 3, dtype=torch.float32, device=dev)
+    lse = torch.empty(B, J, dtype=torch.float32, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.dsir_match_soft_workspace_bytes(B, C, J, K), dev)
+    L.check(lib.dsir_match_soft(fs, fr, B, C, J, K, beta.data_ptr(), alpha_t.data_ptr(), L.ptr(cb), xyz_ref.data_ptr(),
+                                y.data_ptr(), lse.data_ptr(), 0, None, None, ws.data_ptr(), ws.numel(),
+                                L.stream_ptr(dev)), "dsir_match_soft")
+    return y, torch.ones(B, J, dtype=torch.float32, device=dev), lse
+
+
+def gather_neighbour_V3(inputs, neigh_idx):
+    """network/tools.py:211-221.  inputs [B,C,N], neigh_idx [B,M] int64 -> [B,C,M]."""
+    dev = L.require_cuda(inputs, neigh_idx)
+    B, C, N = inputs.shape
+    M = neigh_idx.shape[1]
+    inputs = inputs.contiguous()
+    neigh_idx = neigh_idx.to(torch.int64).contiguous()
+    out = torch.empty(B, C, M, dtype=torch.float32, device=dev)
+    L.check(L.lib().dsir_gather_points(inputs.data_ptr(), B, C, N, neigh_idx.data_ptr(), M, out.data_ptr(),
+                                       L.stream_ptr(dev)), "dsir_gather_points")
+    return out

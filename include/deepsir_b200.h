@@ -1,0 +1,166 @@
+/*
+ * deepsir_b200 — C ABI of the B200-native (sm_100a) correspondence-and-pose hot path.
+ *
+ * Every entry point replaces one PyTorch-level function (or inline block) of the reference
+ * LeoQLi/DeepSIR; the reference file:line each one stands in for is cited next to it.  The library is
+ * a drop-in for that path only: plain device pointers and sizes, caller-owned memory (inputs, outputs
+ * and workspace), an explicit cudaStream_t (passed as void*), no torch types, no hidden host
+ * synchronisation, no CPU fallback.  All functions return DSIR_OK (0) or a negative DSIR_ERR_* code
+ * and never throw or exit.  All tensors are dense fp32 / int64 in device memory unless stated.
+ *
+ * How a maintainer binds this from the reference (ctypes stub): see INTEGRATION.md.
+ */
+#ifndef DEEPSIR_B200_H_
+#define DEEPSIR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *dsir_stream_t; /* a cudaStream_t; NULL = legacy default stream */
+
+enum {
+    DSIR_OK = 0,
+    DSIR_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, unknown enum */
+    DSIR_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels implement (e.g. k > 32) */
+    DSIR_ERR_WORKSPACE = -3,    /* workspace pointer null/misaligned or too small */
+    DSIR_ERR_CUDA = -4,         /* a CUDA runtime/driver call failed; see dsir_last_cuda_error() */
+    DSIR_ERR_KNN_TOO_FEW = -5,  /* fewer support points than k (the reference kernel raises) */
+    DSIR_ERR_NO_DEVICE = -6     /* no sm_100 device: this library has no other code path */
+};
+
+/* feature layout of the match entry points */
+enum { DSIR_LAYOUT_CN = 0 /* [B,C,N], network/matchnet.py:96 */, DSIR_LAYOUT_NC = 1 /* [B,N,C], matchnet.py:49 */ };
+/* metric of dsir_match_dense (network/matchnet.py:116-144) */
+enum { DSIR_METRIC_L2 = 0, DSIR_METRIC_EUCLIDEAN = 1, DSIR_METRIC_ACOS_DOT = 2, DSIR_METRIC_SQDIFF = 3, DSIR_METRIC_CITYBLOCK = 4,
+       DSIR_METRIC_SQDIFF_SQRT = 5 /* feat_dist 'euclidean': sqrt(sum (s-r)^2 + 1e-16) */ };
+/* algorithm selectors (0 = let the library choose) */
+enum { DSIR_KNN_AUTO = 0, DSIR_KNN_BRUTE = 1, DSIR_KNN_GRID = 2 };
+enum { DSIR_MATCH_AUTO = 0, DSIR_MATCH_FP32 = 1 /* CUDA-core exact */, DSIR_MATCH_TC = 2 /* tcgen05 filter + fp32 refine */ };
+
+int dsir_version(void);
+const char *dsir_strerror(int code);
+const char *dsir_last_cuda_error(void); /* text of the last CUDA error seen by this thread */
+/* 0 when the current device is sm_100 (B200); DSIR_ERR_NO_DEVICE otherwise */
+int dsir_device_check(void);
+/* number of kernels this library has enqueued since it was loaded (all threads) */
+uint64_t dsir_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * xyz k-nearest neighbours.  Replaces torch_points_kernels.knn(pos_support, pos, k) as called at
+ * dataloader/data_base.py:165,170.  d2 = fma(dz,dz, fma(dy,dy, dx*dx)) in fp32; results ascending in
+ * (d2, support index) — ties go to the lower index.
+ *   support [B,Ns,sup_stride>=3]  query [B,Nq,qry_stride>=3]  (strides in floats; xyz are the first 3)
+ *   idx [B,Nq,k] int64            dist2 [B,Nq,k] fp32 or NULL
+ * ---------------------------------------------------------------------------------------------- */
+size_t dsir_knn_workspace_bytes(int B, int Ns, int Nq, int k, int algo);
+int dsir_knn_xyz(const float *support, int sup_stride, const float *query, int qry_stride, int B, int Ns, int Nq,
+                 int k, int64_t *idx, float *dist2, void *ws, size_t ws_bytes, int algo, dsir_stream_t stream);
+
+/* The 4-level pyramid of DataBase.nn_search (dataloader/data_base.py:153-183) for one cloud tensor
+ * pts [B,N,pt_stride]: per level self-kNN (k), pool = first N_l/ratio rows, 1-NN of every level point
+ * into the first N_l/ratio points; level-local indices, levels concatenated along the point axis:
+ *   xyz_cat [B,sumN,3]  neigh [B,sumN,k]  sub [B,sumSub,k]  interp [B,sumN,1]                       */
+size_t dsir_knn_pyramid_workspace_bytes(int B, int N, int k, const int *ratios, int L, int algo);
+int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *ratios, int L, int k, float *xyz_cat,
+                     int64_t *neigh, int64_t *sub, int64_t *interp, void *ws, size_t ws_bytes, int algo,
+                     dsir_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Feature distance.  d_jk = ((-2 <s_j, r_k>) + |s_j|^2) + |r_k|^2 in fp32, the op order of
+ * square_distance_V2 (network/matchnet.py:110-112).  Features are addressed as
+ *   f[b, c, n] = base[b * batch_stride + c * chan_stride + n * point_stride]        (strides in floats)
+ * so [B,C,N], [B,N,C] and the row slices of network/model.py:565 are all passed without copies.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dsir_feat {
+    const float *ptr;
+    int64_t batch_stride, chan_stride, point_stride;
+} dsir_feat;
+
+/* materialising form: match_features[_V2] / square_distance[_V2] / feat_dist (matchnet.py:49-192) -> dist [B,J,K] */
+size_t dsir_match_dense_workspace_bytes(int B, int J, int K);
+int dsir_match_dense(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int metric, float *dist, void *ws,
+                     size_t ws_bytes, dsir_stream_t stream);
+
+/* fused distance + row argmin: replaces the chunked block network/model.py:558-569.
+ *   idx [B,J] int64 = first index of the row minimum; min_d [B,J] fp32 or NULL.                     */
+size_t dsir_match_argmin_workspace_bytes(int B, int C, int J, int K, int algo);
+int dsir_match_argmin(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int64_t *idx, float *min_d, void *ws,
+                      size_t ws_bytes, int algo, dsir_stream_t stream);
+
+/* fused distance + affinity + row softmax + soft target (never materialises [J,K]):
+ *   a_jk = -beta_b (d_jk - alpha_b) (+ col_bias[b,k])           compute_affinity, matchnet.py:195-208
+ *   lse_j = log sum_k exp(a_jk);  w_jk = exp(a_jk - lse_j)      row pass of sinkhorn, matchnet.py:259
+ *   y_j = sum_k w_jk xyz_ref[b,k,:] / (sum_k w_jk + 1e-16)      soft target, network/model.py:81-84
+ * outputs: y_soft [B,J,3] (or NULL), lse [B,J] (or NULL); topk > 0 additionally returns the topk largest
+ * weights per row, descending, ties to the lower index: topk_idx [B,J,topk] int64, topk_w [B,J,topk]. */
+size_t dsir_match_soft_workspace_bytes(int B, int C, int J, int K);
+int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
+                    const float *col_bias, const float *xyz_ref, float *y_soft, float *lse, int topk,
+                    int64_t *topk_idx, float *topk_w, void *ws, size_t ws_bytes, dsir_stream_t stream);
+
+/* gather_neighbour_V3 (network/tools.py:211-221): out[b,c,m] = in[b,c,idx[b,m]]; in [B,C,N], idx [B,M] */
+int dsir_gather_points(const float *in, int B, int C, int N, const int64_t *idx, int M, float *out,
+                       dsir_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weighted Kabsch.  Replaces compute_rigid_transform_2 (network/model.py:22-66) including its host
+ * round trip (fp64 LAPACK SVD at :47).  Points are addressed as p[b,m,i] = base[b*bs + m*ps + i*cs]
+ * so both [B,M,3] (model.py:586) and [B,3,M] (the loop's layout) work without a transpose copy.
+ *   weights w[b,m] = w_base[b * w_bs + m]
+ *   gather (nullable) [B,M] int64: tgt point for row m is tgt[b, gather[b,m]] (fuses model.py:571)
+ *   T [B,3,4] fp32;  status [B] int32: 0 ok, 1 degenerate (rank<2 / non-finite) -> identity written
+ *   moments (nullable) [B,17] fp64: additive raw moments {S|w|, Sw, Swx(3), Swy(3), Swxy(9)}
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dsir_points {
+    const float *ptr;
+    int64_t batch_stride, point_stride, coord_stride;
+} dsir_points;
+
+size_t dsir_kabsch_workspace_bytes(int B, int M);
+int dsir_kabsch(dsir_points src, dsir_points tgt, const float *w, int64_t w_batch_stride, const int64_t *gather,
+                int B, int M, float *T, int32_t *status, double *moments, void *ws, size_t ws_bytes,
+                dsir_stream_t stream);
+/* first half only (for row-block sharding across GPUs): moments [B,17] of this rank's rows */
+int dsir_kabsch_moments(dsir_points src, dsir_points tgt, const float *w, int64_t w_batch_stride,
+                        const int64_t *gather, int B, int M, double *moments, void *ws, size_t ws_bytes,
+                        dsir_stream_t stream);
+/* second half: centred covariance from (all-reduced) moments, fp64 3x3 SVD, det fix, R,t */
+int dsir_kabsch_from_moments(const double *moments, int B, float *T, int32_t *status, dsir_stream_t stream);
+/* soft variant, compute_rigid_transform (network/model.py:68-116) given the fused soft targets:
+ * src [B,M,3], y_soft [B,M,3], rowmass [B,M] (sum_k W_jk) */
+int dsir_kabsch_soft(dsir_points src, const float *y_soft, const float *rowmass, int B, int M, float *T,
+                     int32_t *status, void *ws, size_t ws_bytes, dsir_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SE(3) helpers (common/math/se3_torch.py).  T are [B,3,4] fp32 (a [B,4,4] input is passed with
+ * row_stride 4 and batch_stride 16 — only the first three rows are read).
+ * ---------------------------------------------------------------------------------------------- */
+int dsir_se3_apply(const float *T, int64_t T_batch_stride, dsir_points pts, int B, int N, float *out,
+                   int64_t out_batch_stride, int64_t out_point_stride, int64_t out_coord_stride,
+                   int rotate_only, dsir_stream_t stream);                         /* se3_torch.py:51-100 */
+int dsir_se3_compose(const float *a, int64_t a_bs, const float *b, int64_t b_bs, int B, float *out,
+                     dsir_stream_t stream);                                        /* se3_torch.py:28-48 */
+int dsir_se3_inverse(const float *T, int64_t T_bs, int B, float *out, dsir_stream_t stream); /* :10-25 */
+
+/* ------------------------------------------------------------------------------------------------
+ * The iterative re-match / re-solve loop of forward_align_4 (network/model.py:551-601) with fixed
+ * features and weights (the two neural stages are outside the path): per iteration
+ *   idx = argmin match(feat_src, feat_ref); tgt = xyz_ref[idx]; T = kabsch(xyz_src, tgt, w);
+ *   xyz_src <- T xyz_src;  T_total <- T o T_total
+ * entirely on `stream`, no host synchronisation.
+ *   xyz_src [B,3,J] fp32 IN/OUT, xyz_ref [B,3,K], weights [B,J]
+ *   transforms [iters,B,3,4] cumulative; pred_idx [iters,B,J] int64 (or NULL); status [iters,B] int32
+ * ---------------------------------------------------------------------------------------------- */
+size_t dsir_align_loop_workspace_bytes(int B, int C, int J, int K, int algo);
+int dsir_align_loop(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, float *xyz_src, const float *xyz_ref,
+                    const float *weights, int iters, float *transforms, int64_t *pred_idx, int32_t *status,
+                    void *ws, size_t ws_bytes, int algo, dsir_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPSIR_B200_H_ */

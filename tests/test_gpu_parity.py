@@ -1,0 +1,315 @@
+"""Parity of the sm_100a path (called through the C-ABI library via the host mirror) against the CPU oracle
+and the golden fixtures produced by the reference.  Bars (BASELINE.json north_star):
+  * KNN index sets and hard correspondences: bit-exact (ties to the lower index)
+  * soft weights / targets: 1e-4 relative;  R: 1e-3 deg;  t: 1e-4 m
+"""
+import numpy as np
+import pytest
+import torch
+
+import deepsir_b200 as D
+from deepsir_b200 import synth
+from oracle import deepsir_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROT_TOL_DEG, TRANS_TOL_M, SOFT_RTOL = 1e-3, 1e-4, 1e-4
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def assert_pose_close(T_gpu, T_ref, scale=1.0):
+    T_gpu = T_gpu.cpu()
+    ang = O.rotation_angle_deg(T_gpu[:, :, :3], T_ref[:, :, :3]).max().item()
+    dt = (T_gpu[:, :, 3] - T_ref[:, :, 3]).norm(dim=1).max().item()
+    assert ang <= ROT_TOL_DEG, f"rotation differs by {ang} deg"
+    assert dt <= TRANS_TOL_M * scale, f"translation differs by {dt} m"
+
+
+# ------------------------------------------------------------------------------------------- KNN
+@pytest.mark.parametrize("algo", [D.KNN_BRUTE, D.KNN_AUTO])
+def test_knn_random_cloud_bit_exact(algo):
+    g = torch.Generator().manual_seed(3)
+    sup = torch.stack([synth.kitti_cloud(2500, g) for _ in range(2)])
+    qry = torch.stack([synth.kitti_cloud(777, g) for _ in range(2)])
+    for k in (1, 3, 16, 20):
+        i_o, d_o = O.knn(sup[:, :, :3].contiguous(), qry[:, :, :3].contiguous(), k)
+        i_g, d_g = D.knn(cu(sup), cu(qry), k, algo=algo)   # stride-4 inputs, xyz are the first 3 columns
+        assert i_g.dtype == torch.int64 and i_g.shape == (2, 777, k)
+        assert torch.equal(i_g.cpu(), i_o), k
+        assert torch.equal(d_g.cpu(), d_o), k
+
+
+@pytest.mark.parametrize("algo", [D.KNN_BRUTE, D.KNN_AUTO])
+def test_knn_ties_duplicates_and_errors(algo):
+    ax = torch.arange(9, dtype=torch.float32)
+    lat = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, -1, 3).contiguous()
+    i_o, d_o = O.knn(lat, lat, 16)
+    i_g, d_g = D.knn(cu(lat), cu(lat), 16, algo=algo)
+    assert torch.equal(i_g.cpu(), i_o) and torch.equal(d_g.cpu(), d_o)
+    b = synth.make_batch(1, 3000, 8, "kitti", config=1, first_pair=77, tiled_frac=0.27)   # FixedResampler duplicates
+    p = b["points_src"][:, :, :3].contiguous()
+    i_o, d_o = O.knn(p, p, 16)
+    i_g, d_g = D.knn(cu(p), cu(p), 16, algo=algo)
+    assert (d_o[:, :, 1] == 0).sum() > 500
+    assert torch.equal(i_g.cpu(), i_o) and torch.equal(d_g.cpu(), d_o)
+    with pytest.raises(D.DeepSIRError):
+        D.knn(cu(lat[:, :10]), cu(lat), 16, algo=algo)
+
+
+@pytest.mark.parametrize("algo", [D.KNN_BRUTE, D.KNN_AUTO])
+def test_knn_pyramid_matches_nn_search(algo):
+    b = synth.make_batch(2, 4096, 8, "kitti", config=1)
+    for key in ("points_src", "points_ref"):
+        o = O.nn_search_c(b[key], 16, (4, 4, 4, 4))
+        g = D.nn_search_cloud(cu(b[key]), 16, (4, 4, 4, 4), algo=algo)
+        assert g["xyz"].shape == (2, 5440, 3) and g["sub_idx"].shape == (2, 1360, 16)
+        for name in ("xyz", "neigh_idx", "sub_idx", "interp_idx"):
+            assert torch.equal(g[name].cpu(), o[name]), (key, name)
+    d = D.nn_search({k: cu(v) for k, v in b.items() if k.startswith("points")})
+    assert d["points_src_neigh_idx"].dtype == torch.int64 and d["points_ref_interp_idx"].shape == (2, 5440, 1)
+
+
+def test_knn_full_size_properties():
+    """C2 size (16384 points): properties that do not need the CPU brute force on the whole cloud + an oracle
+    check on a slice of the queries."""
+    b = synth.make_batch(2, 16384, 8, "kitti", config=2)
+    p = cu(b["points_src"])
+    i_g, d_g = D.knn(p, p, 16)
+    assert torch.equal(i_g[:, :, 0].cpu(), torch.arange(16384).expand(2, -1))        # self is the nearest
+    assert (d_g[:, :, 1:] >= d_g[:, :, :-1]).all()
+    sub = b["points_src"][:, :512, :3].contiguous()
+    i_o, d_o = O.knn(b["points_src"][:, :, :3].contiguous(), sub, 16)
+    assert torch.equal(i_g[:, :512].cpu(), i_o) and torch.equal(d_g[:, :512].cpu(), d_o)
+    i_b, d_b = D.knn(p, p, 16, algo=D.KNN_BRUTE)
+    assert torch.equal(i_b, i_g) and torch.equal(d_b, d_g)
+
+
+# ------------------------------------------------------------------------------------------- match
+def test_match_dense_golden(golden):
+    g = golden("match_dense")
+    fs, fr = cu(g["feat_src"]), cu(g["feat_ref"])
+    assert torch.allclose(D.match_features_V2(fs, fr, "l2").cpu(), g["l2"], atol=3e-6, rtol=0)
+    assert torch.allclose(D.match_features_V2(fs, fr, "euclidean").cpu(), g["euclidean"], atol=3e-6, rtol=0)
+    assert torch.allclose(D.match_features_V2(fs, fr, "angle").cpu(), g["angle"], atol=5e-6, rtol=0)
+    assert torch.allclose(D.square_distance_V2(fs, fr).cpu(), g["l2"], atol=3e-6, rtol=0)
+    nc = D.match_features(fs.permute(0, 2, 1).contiguous(), fr.permute(0, 2, 1).contiguous(), "l2")
+    assert torch.allclose(nc.cpu(), g["nc_l2"], atol=3e-6, rtol=0)
+    assert torch.allclose(D.feat_dist(fs, fr, "sqeuclidean").cpu(), g["fd_sq"], atol=3e-6, rtol=0)
+    assert torch.allclose(D.feat_dist(fs, fr, "cityblock").cpu(), g["fd_city"], atol=2e-5, rtol=0)
+    assert torch.allclose(D.feat_dist(fs, fr, "euclidean").cpu(), g["fd_euc"], atol=3e-6, rtol=0)
+    # xyz use of square_distance (test.py:145), C = 3, [B,N,C] layout
+    a, b = torch.randn(2, 100, 3) * 30, torch.randn(2, 90, 3) * 30
+    assert torch.allclose(D.square_distance(cu(a), cu(b)).cpu(), O.square_distance(a, b), atol=2e-3, rtol=1e-6)
+
+
+@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_AUTO])
+def test_match_argmin_golden(golden, algo):
+    g = golden("match_argmin_1500")
+    b = synth.make_batch(2, 1500, 64, "kitti", config=1)
+    idx = D.match_argmin(cu(b["feat_src"]), cu(b["feat_ref"]), algo=algo)
+    assert idx.dtype == torch.int64 and torch.equal(idx.cpu(), g["idx_full"])
+    g = golden("match_argmin_7000")
+    b = synth.make_batch(1, 7000, 32, "3dmatch", config=3)
+    assert torch.equal(D.match_argmin(cu(b["feat_src"]), cu(b["feat_ref"]), algo=algo).cpu(), g["idx"])
+    g = golden("match_argmin_ties")        # duplicated reference columns: first index wins
+    assert torch.equal(D.match_argmin(cu(g["feat_src"]), cu(g["feat_ref"]), algo=algo).cpu(), g["idx"])
+
+
+@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_AUTO])
+@pytest.mark.parametrize("shape", [(2, 64, 1000, 1300), (1, 32, 333, 257), (1, 64, 4096, 4096), (3, 3, 200, 50), (1, 40, 129, 1)])
+def test_match_argmin_random_features_vs_oracle(algo, shape):
+    """No planted matches: small top-2 gaps.  Rows whose fp64 gap is below fp32 round-off are 'tie-ambiguous'
+    (the reference's own sgemm order decides them); every other row must be bit-exact."""
+    B, C, J, K = shape
+    fs = synth.random_features(B, C, J, 11)
+    fr = synth.random_features(B, C, K, 12)
+    ref = O.match_argmin(fs, fr)
+    got = D.match_argmin(cu(fs), cu(fr), algo=algo).cpu()
+    i64, gap = O.match_top2_fp64(fs, fr)
+    ambiguous = gap < 2e-6 if K > 1 else torch.zeros_like(ref, dtype=torch.bool)
+    assert ambiguous.float().mean() < 0.01
+    assert torch.equal(got[~ambiguous], ref[~ambiguous])
+    assert torch.equal(got[~ambiguous], i64[~ambiguous])
+
+
+@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_AUTO])
+def test_match_argmin_sliced_views_equal_full(algo):
+    """network/model.py:565 passes feat_src[:, :, n*stride:(n+1)*stride]: views must work without copies and the
+    chunked result must equal the single fused call."""
+    b = synth.make_batch(2, 2600, 64, "kitti", config=1, first_pair=3)
+    fs, fr = cu(b["feat_src"]), cu(b["feat_ref"])
+    full = D.match_argmin(fs, fr, algo=algo)
+    parts = [D.match_argmin(fs[:, :, lo:lo + 1000], fr, algo=algo) for lo in range(0, 2600, 1000)]
+    assert torch.equal(torch.cat(parts, 1), full)
+    idx, mind = D.match_argmin(fs, fr, return_min=True, algo=algo)
+    dense = D.match_features_V2(fs[:, :, :300], fr)
+    assert torch.equal(dense.min(dim=2)[1], idx[:, :300])
+    assert torch.equal(dense.min(dim=2)[0], mind[:, :300])
+
+
+@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_AUTO])
+def test_match_argmin_full_size_planted(algo):
+    """BASELINE config 2 size (16384 x 16384, D=64): planted permutation recovered on every inlier row; the row
+    minimum agrees with the library's own dense rows on a sample."""
+    b = synth.make_batch(1, 16384, 64, "kitti", config=2)
+    fs, fr = cu(b["feat_src"]), cu(b["feat_ref"])
+    idx, mind = D.match_argmin(fs, fr, return_min=True, algo=algo)
+    inl = b["inlier"][0]
+    assert torch.equal(idx[0].cpu()[inl], b["perm"][0][inl])
+    rows = torch.arange(0, 16384, 61, device=DEV)
+    dense = D.match_features_V2(fs[:, :, rows].contiguous(), fr)
+    assert torch.equal(dense.min(dim=2)[1], idx[:, rows])
+    assert torch.equal(dense.min(dim=2)[0], mind[:, rows])
+
+
+def test_gather_golden(golden):
+    g = golden("gather_v3")
+    assert torch.equal(D.gather_neighbour_V3(cu(g["inputs"]), cu(g["idx"])).cpu(), g["out"])
+
+
+# ------------------------------------------------------------------------------------------- soft
+@pytest.mark.parametrize("shape", [(2, 32, 500, 640), (1, 64, 130, 257), (2, 32, 1000, 1000)])
+def test_match_soft_vs_oracle(shape):
+    B, C, J, K = shape
+    b = synth.make_batch(B, max(J, K), C, "3dmatch", config=3, first_pair=20)
+    fs, fr = b["feat_src"][:, :, :J].contiguous(), b["feat_ref"][:, :, :K].contiguous()
+    xyz = b["points_ref"][:, :K, :3].contiguous()
+    beta = torch.tensor([10.0, 6.0, 3.0][:B])
+    alpha = torch.tensor([0.5, 0.3, 0.1][:B])
+    w, y, s, lse = O.soft_correspondence(fs, fr, xyz, beta, alpha)
+    y_g, s_g, lse_g = D.match_soft(cu(fs), cu(fr), cu(xyz), cu(beta), cu(alpha))
+    assert torch.allclose(lse_g.cpu(), lse, rtol=SOFT_RTOL, atol=1e-5)
+    assert torch.allclose(s_g.cpu(), s, rtol=SOFT_RTOL, atol=0)
+    assert torch.allclose(y_g.cpu(), y, rtol=SOFT_RTOL, atol=1e-4)
+    # weights reconstructed from lse match the oracle's weights to 1e-4 relative where they matter
+    a = O.compute_affinity(beta, O.match_features_V2(fs, fr), alpha)
+    w_g = torch.exp(a - lse_g.cpu()[:, :, None])
+    big = w > 1e-6
+    assert ((w_g - w).abs()[big] / w[big]).max() < 5 * SOFT_RTOL
+    # scalar alpha form of compute_affinity
+    y2, _, _ = D.match_soft(cu(fs), cu(fr), cu(xyz), cu(beta), 0.5)
+    _, y2o, _, _ = O.soft_correspondence(fs, fr, xyz, beta, 0.5)
+    assert torch.allclose(y2.cpu(), y2o, rtol=SOFT_RTOL, atol=1e-4)
+
+
+def test_soft_pipeline_pose():
+    b = synth.make_batch(2, 800, 32, "3dmatch", config=3, first_pair=40)
+    src = b["points_src"][:, :, :3].contiguous()
+    ref = b["points_ref"][:, :, :3].contiguous()
+    beta = torch.tensor([10.0, 10.0])
+    w, y, s, _ = O.soft_correspondence(b["feat_src"], b["feat_ref"], ref, beta, 0.5)
+    T_o, _ = O.compute_rigid_transform(src, ref, w)
+    y_g, s_g, _ = D.match_soft(cu(b["feat_src"]), cu(b["feat_ref"]), cu(ref), cu(beta), 0.5)
+    T_g, inv = D.kabsch_soft(cu(src), y_g, s_g)
+    assert not bool(inv)
+    assert_pose_close(T_g, T_o)
+    T_g2, _ = D.compute_rigid_transform(cu(src), cu(ref), cu(w))   # signature-compatible form ([B,M,N] weights)
+    assert_pose_close(T_g2, T_o)
+
+
+# ------------------------------------------------------------------------------------------- Kabsch / SE3
+def test_kabsch_golden(golden):
+    g = golden("kabsch2")
+    for name in ["planted", "uniform_w", "planar", "reflection", "neg_w", "single_heavy"]:
+        T, inv = D.compute_rigid_transform_2(cu(g[name + "_src"]), cu(g[name + "_tgt"]), cu(g[name + "_w"]))
+        assert T.shape == (3, 3, 4) and T.dtype == torch.float32 and not bool(inv), name
+        assert (torch.det(T[:, :, :3].cpu()) > 0).all(), name
+        assert_pose_close(T, g[name + "_T"])
+
+
+def test_kabsch_planted_and_layouts():
+    b = synth.make_batch(4, 16384, 8, "kitti", config=2, first_pair=8)
+    src = b["points_src"][:, :, :3].contiguous()
+    tgt = torch.stack([b["points_ref"][i, b["perm"][i], :3] for i in range(4)])
+    T_o, _ = O.compute_rigid_transform_2(src, tgt, b["weights"])
+    T_g, st = D.compute_rigid_transform_2(cu(src), cu(tgt), cu(b["weights"]), return_status=True)
+    assert (st == 0).all()
+    assert_pose_close(T_g, T_o)
+    # fused gather + [B,3,N] layout (the loop's form)
+    xs = cu(src).permute(0, 2, 1).contiguous()
+    xr = cu(b["points_ref"][:, :, :3]).permute(0, 2, 1).contiguous()
+    T_f, st = D.kabsch_gather(xs, xr, cu(b["perm"]), cu(b["weights"]))
+    assert torch.equal(T_f, T_g)
+    # strided [B,M,3] view of a [B,M,4] tensor (no copy)
+    T_v, _ = D.compute_rigid_transform_2(cu(b["points_src"])[:, :, :3], cu(tgt), cu(b["weights"]))
+    assert torch.equal(T_v, T_g)
+    # row-block sharded moments add up
+    m = sum(D.kabsch_moments(cu(src[:, lo:lo + 4096]), cu(tgt[:, lo:lo + 4096]), cu(b["weights"][:, lo:lo + 4096]))
+            for lo in range(0, 16384, 4096))
+    T_m, st = D.kabsch_from_moments(m)
+    assert_pose_close(T_m, T_o)
+    assert torch.allclose(m.cpu(), O.kabsch_moments_fp64(src, tgt, b["weights"]), rtol=1e-12, atol=1e-9)
+
+
+def test_kabsch_degenerate_cases():
+    line = torch.linspace(0, 1, 50)[None, :, None] * torch.tensor([1.0, 2.0, 3.0])
+    T, st = D.compute_rigid_transform_2(cu(line), cu(line + 1.0), cu(torch.ones(1, 50, 1)), return_status=True)
+    assert st.item() == 1 and torch.equal(T.cpu(), O.se3_identity(1))
+    pts = torch.randn(2, 30, 3)
+    T, inv = D.compute_rigid_transform_2(cu(pts), cu(pts), cu(torch.zeros(2, 30, 1)))
+    assert bool(inv) and torch.equal(T.cpu(), O.se3_identity(2))
+    bad = pts.clone(); bad[0, 3, 1] = float("nan")
+    T, st = D.compute_rigid_transform_2(cu(bad), cu(pts), cu(torch.ones(2, 30, 1)), return_status=True)
+    assert st.tolist() == [1, 0]
+    # identity / pure translation / 180 degree turn
+    T, _ = D.compute_rigid_transform_2(cu(pts), cu(pts + torch.tensor([1.0, -2.0, 3.0])), cu(torch.ones(2, 30, 1)))
+    assert_pose_close(T, torch.cat([torch.eye(3), torch.tensor([[1.0], [-2.0], [3.0]])], 1).expand(2, -1, -1))
+    Rz = torch.diag(torch.tensor([-1.0, -1.0, 1.0]))
+    T, _ = D.compute_rigid_transform_2(cu(pts), cu(pts @ Rz.t()), cu(torch.ones(2, 30, 1)))
+    assert_pose_close(T, torch.cat([Rz, torch.zeros(3, 1)], 1).expand(2, -1, -1))
+
+
+def test_se3_golden(golden):
+    g = golden("se3")
+    S = D.se3_torch
+    Ta, Tb, pts = cu(g["Ta"]), cu(g["Tb"]), cu(g["pts"])
+    assert torch.equal(S.identity(4), g["identity"])
+    assert torch.allclose(S.inverse(Ta).cpu(), g["inverse"], atol=1e-6, rtol=0)
+    assert torch.allclose(S.concatenate(Ta, Tb).cpu(), g["concat"], atol=1e-6, rtol=0)
+    assert torch.allclose(S.transform(Ta, pts).cpu(), g["transform"], atol=2e-5, rtol=0)
+    assert torch.allclose(S.transform_V2(Ta, pts.permute(0, 2, 1).contiguous()).cpu(), g["transform_v2"], atol=2e-5, rtol=0)
+    T44 = torch.cat([Ta, torch.tensor([0, 0, 0, 1.0], device=DEV).expand(4, 1, 4)], 1)      # (B,4,4) inputs
+    assert torch.allclose(S.concatenate(T44, Tb).cpu(), g["concat"], atol=1e-6, rtol=0)
+    out, nrm = S.transform(Ta, pts, pts)
+    assert torch.allclose(nrm.cpu(), g["pts"] @ g["Ta"][:, :, :3].transpose(1, 2), atol=2e-5, rtol=0)
+
+
+# ------------------------------------------------------------------------------------------- loop
+@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_AUTO])
+def test_loop_golden_and_oracle(golden, algo):
+    g = golden("loop_oxford_1200")
+    b = synth.make_batch(2, 1200, 64, "oxford", config=5)
+    xs = b["points_src"][:, :, :3].permute(0, 2, 1).contiguous()
+    xr = b["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
+    tr, pred, xyz, st = D.align_loop(cu(b["feat_src"]), cu(b["feat_ref"]), cu(xs), cu(xr), cu(b["weights"]), 3, algo=algo)
+    assert (st == 0).all() and len(tr) == 3
+    assert torch.equal(torch.stack(pred).cpu(), g["pred"])
+    for i in range(3):
+        assert_pose_close(tr[i], g["transforms"][i])
+    assert torch.allclose(xyz.cpu(), g["xyz_src_final"], atol=2e-4, rtol=0)
+    pp = D.pred_pairs(pred[-1])
+    assert pp.dtype == torch.int32 and pp.device.type == "cpu" and pp.shape == (2, 1200, 2)
+    # per-iteration form with callbacks == fused form
+    tr2, pred2, xyz2, _ = D.align_loop(cu(b["feat_src"]), cu(b["feat_ref"]), cu(xs), cu(xr), cu(b["weights"]), 3,
+                                       weight_fn=lambda s, r: cu(b["weights"]), algo=algo)
+    assert torch.equal(torch.stack(pred2), torch.stack(pred))
+    for i in range(3):
+        assert torch.allclose(tr2[i], tr[i], atol=1e-6)
+
+
+def test_loop_ten_iterations_converges():
+    """BASELINE config 5 shape at reduced batch: 10 ICP-style iterations on Oxford-shaped 20k clouds."""
+    b = synth.make_batch(1, 20000, 64, "oxford", config=5, first_pair=9)
+    xs = b["points_src"][:, :, :3].permute(0, 2, 1).contiguous()
+    xr = b["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
+    tr, pred, xyz, st = D.align_loop(cu(b["feat_src"]), cu(b["feat_ref"]), cu(xs), cu(xr), cu(b["weights"]), 10)
+    assert (st == 0).all()
+    assert O.rotation_angle_deg(tr[-1].cpu()[:, :, :3], b["transform_gt"][:, :, :3]).max() < 0.5
+    # after the first solve the residual transform is ~identity: cumulative transforms stay put
+    assert O.rotation_angle_deg(tr[-1].cpu()[:, :, :3], tr[0].cpu()[:, :, :3]).max() < 1e-2
+    # transforms[i] is the running composition (model.py:595)
+    moved = D.se3_torch.transform_V2(tr[-1], cu(xs))
+    assert torch.allclose(moved, xyz, atol=5e-4)
