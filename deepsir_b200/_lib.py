@@ -78,6 +78,8 @@ _SIGS = {
     "dsir_match_argmin_workspace_bytes": (_c.c_size_t, [_c.c_int] * 5),
     "dsir_match_argmin": (_c.c_int, [Feat, Feat, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                      _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
+    "dsir_match_argmin_rescued_rows": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                                  _c.c_void_p, _c.c_void_p]),
     "dsir_match_soft_workspace_bytes": (_c.c_size_t, [_c.c_int] * 4),
     "dsir_match_soft": (_c.c_int, [Feat, Feat, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                    _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,

@@ -84,7 +84,7 @@ def feat_dist(feat_src, feat_ref, metric="sqeuclidean"):
     return _dense(fs, fr, feat_src.shape[0], feat_src.shape[1], feat_src.shape[2], feat_ref.shape[2], code, (a, b), dev)
 
 
-def match_argmin(feat_src, feat_ref, return_min=False, algo=L.MATCH_AUTO):
+def match_argmin(feat_src, feat_ref, return_min=False, algo=L.MATCH_AUTO, return_rescued=False):
     """The fused replacement of network/model.py:558-569 (chunked match_features_V2 + .min(dim=2)[1]):
     feat_src [B,C,J], feat_ref [B,C,K] -> indexs int64 [B,J]; the [J,K] matrix is never written."""
     assert feat_src.shape[1] == feat_ref.shape[1]
@@ -98,6 +98,12 @@ def match_argmin(feat_src, feat_ref, return_min=False, algo=L.MATCH_AUTO):
     ws = L.workspace(lib.dsir_match_argmin_workspace_bytes(B, C, J, K, algo), dev)
     L.check(lib.dsir_match_argmin(fs, fr, B, C, J, K, idx.data_ptr(), L.ptr(mind), ws.data_ptr(), ws.numel(), algo,
                                   L.stream_ptr(dev)), "dsir_match_argmin")
+    if return_rescued:  # diagnostic of the tcgen05 path; forces a stream sync
+        import ctypes
+        n = ctypes.c_int32(-1)
+        L.check(lib.dsir_match_argmin_rescued_rows(ws.data_ptr(), ws.numel(), B, C, J, K, ctypes.addressof(n),
+                                                   L.stream_ptr(dev)), "dsir_match_argmin_rescued_rows")
+        return (idx, mind, n.value) if return_min else (idx, n.value)
     return (idx, mind) if return_min else idx
 
 

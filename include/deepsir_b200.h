@@ -91,6 +91,11 @@ size_t dsir_match_argmin_workspace_bytes(int B, int C, int J, int K, int algo);
 int dsir_match_argmin(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int64_t *idx, float *min_d, void *ws,
                       size_t ws_bytes, int algo, dsir_stream_t stream);
 
+/* diagnostic for the tcgen05 path (synchronises `stream`): rows of the LAST dsir_match_argmin call on this workspace
+ * whose candidate list saturated and were recomputed exhaustively in fp32.  host_out is a HOST int32. */
+int dsir_match_argmin_rescued_rows(const void *ws, size_t ws_bytes, int B, int C, int J, int K, int32_t *host_out,
+                                   dsir_stream_t stream);
+
 /* fused distance + affinity + row softmax + soft target (never materialises [J,K]):
  *   a_jk = -beta_b (d_jk - alpha_b) (+ col_bias[b,k])           compute_affinity, matchnet.py:195-208
  *   lse_j = log sum_k exp(a_jk);  w_jk = exp(a_jk - lse_j)      row pass of sinkhorn, matchnet.py:259

@@ -115,6 +115,10 @@ def match_top2_fp64(feat_src, feat_ref, chunk=2048):
     for lo in range(0, fs.shape[2], chunk):
         s = fs[:, :, lo:lo + chunk]
         d = -2 * torch.matmul(s.permute(0, 2, 1), fr) + (s * s).sum(1)[:, :, None] + nr
+        if d.shape[2] < 2:
+            idx.append(torch.zeros(d.shape[:2], dtype=torch.int64))
+            gap.append(torch.full(d.shape[:2], float("inf"), dtype=torch.float64))
+            continue
         v, i = torch.topk(d, 2, dim=2, largest=False)
         idx.append(i[:, :, 0])
         gap.append(v[:, :, 1] - v[:, :, 0])

@@ -105,7 +105,7 @@ def test_match_dense_golden(golden):
     assert torch.allclose(D.square_distance(cu(a), cu(b)).cpu(), O.square_distance(a, b), atol=2e-3, rtol=1e-6)
 
 
-@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_AUTO])
+@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_TC, D.MATCH_AUTO])
 def test_match_argmin_golden(golden, algo):
     g = golden("match_argmin_1500")
     b = synth.make_batch(2, 1500, 64, "kitti", config=1)
@@ -118,7 +118,7 @@ def test_match_argmin_golden(golden, algo):
     assert torch.equal(D.match_argmin(cu(g["feat_src"]), cu(g["feat_ref"]), algo=algo).cpu(), g["idx"])
 
 
-@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_AUTO])
+@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_TC, D.MATCH_AUTO])
 @pytest.mark.parametrize("shape", [(2, 64, 1000, 1300), (1, 32, 333, 257), (1, 64, 4096, 4096), (3, 3, 200, 50), (1, 40, 129, 1)])
 def test_match_argmin_random_features_vs_oracle(algo, shape):
     """No planted matches: small top-2 gaps.  Rows whose fp64 gap is below fp32 round-off are 'tie-ambiguous'
@@ -135,7 +135,7 @@ def test_match_argmin_random_features_vs_oracle(algo, shape):
     assert torch.equal(got[~ambiguous], i64[~ambiguous])
 
 
-@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_AUTO])
+@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_TC, D.MATCH_AUTO])
 def test_match_argmin_sliced_views_equal_full(algo):
     """network/model.py:565 passes feat_src[:, :, n*stride:(n+1)*stride]: views must work without copies and the
     chunked result must equal the single fused call."""
@@ -150,7 +150,7 @@ def test_match_argmin_sliced_views_equal_full(algo):
     assert torch.equal(dense.min(dim=2)[0], mind[:, :300])
 
 
-@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_AUTO])
+@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_TC, D.MATCH_AUTO])
 def test_match_argmin_full_size_planted(algo):
     """BASELINE config 2 size (16384 x 16384, D=64): planted permutation recovered on every inlier row; the row
     minimum agrees with the library's own dense rows on a sample."""
@@ -163,6 +163,36 @@ def test_match_argmin_full_size_planted(algo):
     dense = D.match_features_V2(fs[:, :, rows].contiguous(), fr)
     assert torch.equal(dense.min(dim=2)[1], idx[:, rows])
     assert torch.equal(dense.min(dim=2)[0], mind[:, rows])
+
+
+def test_match_tc_equals_fp32_and_rarely_rescues():
+    """The tcgen05 filter + fp32 refine must return the SAME indices and minima as the fp32 kernel, and the
+    exhaustive rescue path must stay (almost) idle — otherwise the tensor-core stage is not doing the work."""
+    b = synth.make_batch(2, 8192, 64, "kitti", config=2, first_pair=100)
+    fs, fr = cu(b["feat_src"]), cu(b["feat_ref"])
+    i_tc, d_tc, n_resc = D.match_argmin(fs, fr, return_min=True, algo=D.MATCH_TC, return_rescued=True)
+    i_32, d_32 = D.match_argmin(fs, fr, return_min=True, algo=D.MATCH_FP32)
+    assert torch.equal(i_tc, i_32) and torch.equal(d_tc, d_32)
+    assert n_resc <= 2, f"{n_resc} of 16384 planted rows went to the rescue path"
+    # random (un-planted) unit features, D = 64 and D = 32, ragged sizes: still identical, rescue rate small
+    for (B, C, J, K) in [(1, 64, 5000, 7777), (2, 32, 3001, 4100), (1, 48, 700, 9000), (1, 8, 300, 300)]:
+        fs, fr = cu(synth.random_features(B, C, J, 5)), cu(synth.random_features(B, C, K, 6))
+        i_tc, d_tc, n_resc = D.match_argmin(fs, fr, return_min=True, algo=D.MATCH_TC, return_rescued=True)
+        i_32, d_32 = D.match_argmin(fs, fr, return_min=True, algo=D.MATCH_FP32)
+        assert torch.equal(i_tc, i_32) and torch.equal(d_tc, d_32), (B, C, J, K)
+        assert n_resc <= 0.05 * B * J + 1 or C <= 8, (n_resc, B, C, J, K)
+    # adversarial: every reference row identical -> every row saturates -> all rescued, first index wins
+    fr = cu(synth.random_features(1, 64, 1, 9)).expand(1, 64, 600).contiguous()
+    fs = cu(synth.random_features(1, 64, 300, 10))
+    i_tc, n_resc = D.match_argmin(fs, fr, algo=D.MATCH_TC, return_rescued=True)
+    assert n_resc == 300 and (i_tc == 0).all()
+    # un-normalised features with a large dynamic range
+    g = torch.Generator().manual_seed(1)
+    fs = cu(torch.randn(1, 64, 2000, generator=g) * torch.logspace(-2, 2, 2000)[None, None, :])
+    fr = cu(torch.randn(1, 64, 2500, generator=g) * 3.0)
+    i_tc, d_tc = D.match_argmin(fs, fr, return_min=True, algo=D.MATCH_TC)
+    i_32, d_32 = D.match_argmin(fs, fr, return_min=True, algo=D.MATCH_FP32)
+    assert torch.equal(i_tc, i_32) and torch.equal(d_tc, d_32)
 
 
 def test_gather_golden(golden):
@@ -278,7 +308,7 @@ def test_se3_golden(golden):
 
 
 # ------------------------------------------------------------------------------------------- loop
-@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_AUTO])
+@pytest.mark.parametrize("algo", [D.MATCH_FP32, D.MATCH_TC, D.MATCH_AUTO])
 def test_loop_golden_and_oracle(golden, algo):
     g = golden("loop_oxford_1200")
     b = synth.make_batch(2, 1200, 64, "oxford", config=5)
