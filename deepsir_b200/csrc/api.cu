@@ -51,17 +51,52 @@ int dsir_device_check(void) {
 }
 
 /* ------------------------------------------------------------------ KNN ------------------------ */
+namespace {
+
+struct GridSlot {
+    KnnGridHeader *hdr;
+    int *cell_start;
+    float4 *sorted;
+    int n;
+};
+
+size_t grid_slot_bytes(int B, int n) {
+    return ws_block((size_t)B * sizeof(KnnGridHeader)) + ws_block((size_t)B * (KNN_GRID_GMAX + 1) * sizeof(int)) +
+           ws_block((size_t)B * n * sizeof(float4));
+}
+
+bool take_grid_slot(Workspace &W, int B, int n, GridSlot *s) {
+    s->hdr = W.take<KnnGridHeader>((size_t)B);
+    s->cell_start = W.take<int>((size_t)B * (KNN_GRID_GMAX + 1));
+    s->sorted = W.take<float4>((size_t)B * n);
+    s->n = n;
+    return W.ok();
+}
+
+bool use_grid(int algo, int Ns) {
+    if (algo == DSIR_KNN_BRUTE) return false;
+    if (algo == DSIR_KNN_GRID) return true;
+    return Ns >= KNN_GRID_MIN_POINTS;
+}
+
+constexpr float GRID_CELLS_PER_POINT = 2.0f;
+constexpr float GRID_R0_CELLS = 0.75f;
+
+}  // namespace
+
 size_t dsir_knn_workspace_bytes(int B, int Ns, int Nq, int k, int algo) {
-    (void)Nq; (void)k; (void)algo;
+    (void)k;
     if (B <= 0 || Ns <= 0) return 256;
-    return ws_block((size_t)B * Ns * sizeof(float4)) + 256;
+    size_t bytes = ws_block((size_t)B * Ns * sizeof(float4)) + 256;
+    if (use_grid(algo, Ns)) bytes += grid_slot_bytes(B, Ns) + (Nq > 0 ? grid_slot_bytes(B, Nq) + ws_block((size_t)B * Nq * sizeof(float4)) : 0);
+    return bytes;
 }
 
 int dsir_knn_xyz(const float *support, int sup_stride, const float *query, int qry_stride, int B, int Ns, int Nq,
                  int k, int64_t *idx, float *dist2, void *ws, size_t ws_bytes, int algo, dsir_stream_t stream) {
-    (void)algo;
     if (!support || !query || !idx || B <= 0 || Ns <= 0 || Nq < 0 || sup_stride < 3 || qry_stride < 3 || k <= 0)
         return DSIR_ERR_BAD_ARG;
+    if (algo < DSIR_KNN_AUTO || algo > DSIR_KNN_GRID) return DSIR_ERR_BAD_ARG;
     if (k > 32) return DSIR_ERR_UNSUPPORTED;
     if (Ns < k) return DSIR_ERR_KNN_TOO_FEW;
     cudaStream_t st = (cudaStream_t)stream;
@@ -70,13 +105,38 @@ int dsir_knn_xyz(const float *support, int sup_stride, const float *query, int q
     if (!W.ok()) return DSIR_ERR_WORKSPACE;
     int rc = launch_pack_xyz4(support, sup_stride, (long long)B * Ns, sup4, st);
     if (rc) return rc;
-    KnnBruteParams P{};
-    P.sup4 = sup4; P.sup_bs = Ns;
-    P.query = query; P.qry_bs = (long long)Nq * qry_stride; P.qry_stride = qry_stride;
-    P.Ns = Ns; P.Nq = Nq; P.k = k;
-    P.idx = idx; P.idx_bs = (long long)Nq * k; P.dist2 = dist2;
-    P.idx2 = nullptr; P.idx2_bs = 0; P.idx2_rows = 0;
-    return launch_knn_brute(P, B, st);
+    if (!use_grid(algo, Ns)) {
+        KnnBruteParams P{};
+        P.sup4 = sup4; P.sup_bs = Ns;
+        P.query = query; P.qry_bs = (long long)Nq * qry_stride; P.qry_stride = qry_stride;
+        P.Ns = Ns; P.Nq = Nq; P.k = k;
+        P.idx = idx; P.idx_bs = (long long)Nq * k; P.dist2 = dist2;
+        return launch_knn_brute(P, B, st);
+    }
+    // grid over the support; the queries are binned into their own grid as well so that they are visited in a
+    // cell-coherent order (for a self-query the two grids coincide)
+    const bool self = (query == support) && Nq == Ns && qry_stride == sup_stride;
+    GridSlot gs, gq;
+    if (!take_grid_slot(W, B, Ns, &gs)) return DSIR_ERR_WORKSPACE;
+    KnnGridBuildParams BP{};
+    BP.pts4 = sup4; BP.pts_bs = Ns; BP.gmax = KNN_GRID_GMAX; BP.cells_per_point = GRID_CELLS_PER_POINT;
+    BP.n[0] = Ns; BP.hdr[0] = gs.hdr; BP.cell_start[0] = gs.cell_start; BP.sorted[0] = gs.sorted;
+    if ((rc = launch_knn_grid_build(BP, 1, B, st))) return rc;
+    gq = gs;
+    if (!self && Nq > 0) {
+        float4 *q4 = W.take<float4>((size_t)B * Nq);
+        if (!W.ok() || !take_grid_slot(W, B, Nq, &gq)) return DSIR_ERR_WORKSPACE;
+        if ((rc = launch_pack_xyz4(query, qry_stride, (long long)B * Nq, q4, st))) return rc;
+        KnnGridBuildParams QP = BP;
+        QP.pts4 = q4; QP.pts_bs = Nq; QP.n[0] = Nq; QP.hdr[0] = gq.hdr; QP.cell_start[0] = gq.cell_start; QP.sorted[0] = gq.sorted;
+        if ((rc = launch_knn_grid_build(QP, 1, B, st))) return rc;
+    }
+    KnnGridQueryParams Q{};
+    Q.hdr = gs.hdr; Q.cell_start = gs.cell_start; Q.sorted = gs.sorted; Q.gmax = KNN_GRID_GMAX; Q.Ns = Ns;
+    Q.q_sorted = gq.sorted; Q.q_sorted_bs = Nq;
+    Q.Nq = Nq; Q.k = k; Q.r0_cells = GRID_R0_CELLS;
+    Q.idx = idx; Q.idx_bs = (long long)Nq * k; Q.dist2 = dist2;
+    return launch_knn_grid_query(Q, B, st);
 }
 
 static int pyramid_levels(int N, const int *ratios, int L, PyramidLevels *lv) {
@@ -93,17 +153,36 @@ static int pyramid_levels(int N, const int *ratios, int L, PyramidLevels *lv) {
     return DSIR_OK;
 }
 
+// distinct support sizes of a pyramid that get a grid: n[0], n[1], ..., and the last sub-cloud m[L-1]
+static int pyramid_grid_sizes(const PyramidLevels &lv, int algo, int *sizes) {
+    int ng = 0;
+    for (int l = 0; l <= lv.L; ++l) {
+        int n = l < lv.L ? lv.n[l] : lv.m[lv.L - 1];
+        bool dup = false;
+        for (int g = 0; g < ng; ++g) dup = dup || sizes[g] == n;
+        if (!dup && n > 0 && use_grid(algo, n)) sizes[ng++] = n;
+    }
+    return ng;
+}
+
 size_t dsir_knn_pyramid_workspace_bytes(int B, int N, int k, const int *ratios, int L, int algo) {
-    (void)k; (void)ratios; (void)L; (void)algo;
+    (void)k;
     if (B <= 0 || N <= 0) return 256;
-    return ws_block((size_t)B * N * sizeof(float4)) + 256;
+    size_t bytes = ws_block((size_t)B * N * sizeof(float4)) + 256;
+    PyramidLevels lv;
+    if (ratios && pyramid_levels(N, ratios, L, &lv) == DSIR_OK) {
+        int sizes[DSIR_MAX_LEVELS + 1];
+        int ng = pyramid_grid_sizes(lv, algo, sizes);
+        for (int g = 0; g < ng; ++g) bytes += grid_slot_bytes(B, sizes[g]);
+    }
+    return bytes;
 }
 
 int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *ratios, int L, int k, float *xyz_cat,
                      int64_t *neigh, int64_t *sub, int64_t *interp, void *ws, size_t ws_bytes, int algo,
                      dsir_stream_t stream) {
-    (void)algo;
     if (!pts || !ratios || !neigh || !sub || !interp || B <= 0 || N <= 0 || pt_stride < 3 || k <= 0) return DSIR_ERR_BAD_ARG;
+    if (algo < DSIR_KNN_AUTO || algo > DSIR_KNN_GRID) return DSIR_ERR_BAD_ARG;
     if (k > 32) return DSIR_ERR_UNSUPPORTED;
     PyramidLevels lv;
     int rc = pyramid_levels(N, ratios, L, &lv);
@@ -116,20 +195,67 @@ int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *r
     if (!W.ok()) return DSIR_ERR_WORKSPACE;
     if ((rc = launch_pack_xyz4(pts, pt_stride, (long long)B * N, pts4, st))) return rc;
     if (xyz_cat && (rc = launch_pyramid_xyz(pts, pt_stride, B, N, lv, xyz_cat, st))) return rc;
+
+    // one build launch for every grid of the pyramid (every level cloud is a prefix of the packed cloud)
+    int sizes[DSIR_MAX_LEVELS + 1];
+    const int ng = pyramid_grid_sizes(lv, algo, sizes);
+    GridSlot slots[DSIR_MAX_LEVELS + 1];
+    if (ng > 0) {
+        KnnGridBuildParams BP{};
+        BP.pts4 = pts4; BP.pts_bs = N; BP.gmax = KNN_GRID_GMAX; BP.cells_per_point = GRID_CELLS_PER_POINT;
+        for (int g = 0; g < ng; ++g) {
+            if (!take_grid_slot(W, B, sizes[g], &slots[g])) return DSIR_ERR_WORKSPACE;
+            BP.n[g] = sizes[g]; BP.hdr[g] = slots[g].hdr; BP.cell_start[g] = slots[g].cell_start; BP.sorted[g] = slots[g].sorted;
+        }
+        if ((rc = launch_knn_grid_build(BP, ng, B, st))) return rc;
+    }
+    auto find_slot = [&](int n) -> const GridSlot * {
+        for (int g = 0; g < ng; ++g)
+            if (slots[g].n == n) return &slots[g];
+        return nullptr;
+    };
+
     for (int l = 0; l < L; ++l) {
-        // every level cloud is the first n[l] points of the original (prefix sub-sampling, data_base.py:169)
-        KnnBruteParams P{};
-        P.sup4 = pts4; P.sup_bs = N;
-        P.query = (const float *)pts4; P.qry_bs = (long long)N * 4; P.qry_stride = 4;
-        P.Ns = lv.n[l]; P.Nq = lv.n[l]; P.k = k;
-        P.idx = neigh + (size_t)lv.off[l] * k; P.idx_bs = (long long)lv.sumN * k; P.dist2 = nullptr;
-        P.idx2 = sub + (size_t)lv.offsub[l] * k; P.idx2_bs = (long long)lv.sumSub * k; P.idx2_rows = lv.m[l];
-        if ((rc = launch_knn_brute(P, B, st))) return rc;
-        KnnBruteParams U = P;  // 1-NN of every level point into the sub-cloud (data_base.py:170)
-        U.Ns = lv.m[l]; U.k = 1;
-        U.idx = interp + lv.off[l]; U.idx_bs = lv.sumN;
-        U.idx2 = nullptr; U.idx2_rows = 0;
-        if ((rc = launch_knn_brute(U, B, st))) return rc;
+        const GridSlot *gl = find_slot(lv.n[l]);   // grid over the level cloud (support of the self-kNN, query order)
+        const GridSlot *gm = find_slot(lv.m[l]);   // grid over the sub-cloud (support of the 1-NN up-sampling)
+        int64_t *nb = neigh + (size_t)lv.off[l] * k;
+        int64_t *pool = sub + (size_t)lv.offsub[l] * k;
+        int64_t *up = interp + lv.off[l];
+        // ---- self-kNN of the level cloud (data_base.py:165); rows < m[l] are also the pooling indices (:168) ----
+        if (gl) {
+            KnnGridQueryParams Q{};
+            Q.hdr = gl->hdr; Q.cell_start = gl->cell_start; Q.sorted = gl->sorted; Q.gmax = KNN_GRID_GMAX; Q.Ns = lv.n[l];
+            Q.q_sorted = gl->sorted; Q.q_sorted_bs = lv.n[l];
+            Q.Nq = lv.n[l]; Q.k = k; Q.r0_cells = GRID_R0_CELLS;
+            Q.idx = nb; Q.idx_bs = (long long)lv.sumN * k;
+            Q.idx2 = pool; Q.idx2_bs = (long long)lv.sumSub * k; Q.idx2_rows = lv.m[l];
+            if ((rc = launch_knn_grid_query(Q, B, st))) return rc;
+        } else {
+            KnnBruteParams P{};
+            P.sup4 = pts4; P.sup_bs = N;
+            P.query = (const float *)pts4; P.qry_bs = (long long)N * 4; P.qry_stride = 4;
+            P.Ns = lv.n[l]; P.Nq = lv.n[l]; P.k = k;
+            P.idx = nb; P.idx_bs = (long long)lv.sumN * k;
+            P.idx2 = pool; P.idx2_bs = (long long)lv.sumSub * k; P.idx2_rows = lv.m[l];
+            if ((rc = launch_knn_brute(P, B, st))) return rc;
+        }
+        // ---- 1-NN of every level point into the sub-cloud (data_base.py:170) ----
+        if (gm) {
+            KnnGridQueryParams Q{};
+            Q.hdr = gm->hdr; Q.cell_start = gm->cell_start; Q.sorted = gm->sorted; Q.gmax = KNN_GRID_GMAX; Q.Ns = lv.m[l];
+            if (gl) { Q.q_sorted = gl->sorted; Q.q_sorted_bs = lv.n[l]; }
+            else { Q.query = (const float *)pts4; Q.qry_bs = (long long)N * 4; Q.qry_stride = 4; }
+            Q.Nq = lv.n[l]; Q.k = 1; Q.r0_cells = GRID_R0_CELLS;
+            Q.idx = up; Q.idx_bs = lv.sumN;
+            if ((rc = launch_knn_grid_query(Q, B, st))) return rc;
+        } else {
+            KnnBruteParams U{};
+            U.sup4 = pts4; U.sup_bs = N;
+            U.query = (const float *)pts4; U.qry_bs = (long long)N * 4; U.qry_stride = 4;
+            U.Ns = lv.m[l]; U.Nq = lv.n[l]; U.k = 1;
+            U.idx = up; U.idx_bs = lv.sumN;
+            if ((rc = launch_knn_brute(U, B, st))) return rc;
+        }
     }
     return DSIR_OK;
 }

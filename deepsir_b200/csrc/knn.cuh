@@ -38,3 +38,58 @@ int launch_pyramid_xyz(const float *pts, int stride, int B, int N, const Pyramid
                        cudaStream_t st);
 
 }  // namespace dsir
+
+// ---------------------------------------------------------------------------------------------------
+// grid variant (knn_grid.cu)
+// ---------------------------------------------------------------------------------------------------
+namespace dsir {
+
+constexpr int KNN_GRID_GMAX = 32768;     // cells per grid (shared-memory histogram of the build kernel)
+constexpr int KNN_GRID_MIN_POINTS = 512;  // below this the brute-force kernel is used
+
+struct KnnGridHeader {
+    float lo[3];
+    float h, inv_h;
+    int gx, gy, gz;
+    float slack;  // absolute rounding slack added to every search radius
+    float diag;
+    int pad[6];
+};
+
+struct KnnGridBuildParams {
+    const float4 *pts4;  // [B][pts_bs] packed xyz0; grid g is built over the first n[g] points of every cloud
+    long long pts_bs;
+    int n[DSIR_MAX_LEVELS + 1];
+    KnnGridHeader *hdr[DSIR_MAX_LEVELS + 1];  // [B]
+    int *cell_start[DSIR_MAX_LEVELS + 1];     // [B][gmax+1]
+    float4 *sorted[DSIR_MAX_LEVELS + 1];      // [B][n[g]]  (x,y,z,index bits) in cell order
+    int gmax;
+    float cells_per_point;
+};
+
+struct KnnGridQueryParams {
+    const KnnGridHeader *hdr;  // support grid
+    const int *cell_start;
+    const float4 *sorted;
+    int gmax, Ns;
+    // queries: either another grid's sorted array (cell-coherent order, original index in .w) or a raw array
+    const float4 *q_sorted;
+    long long q_sorted_bs;
+    const float *query;
+    long long qry_bs;
+    int qry_stride;
+    int Nq, k;
+    float r0_cells;  // first search radius in cell sizes
+    int64_t *idx;
+    long long idx_bs;
+    float *dist2;
+    int64_t *idx2;
+    long long idx2_bs;
+    int idx2_rows;
+};
+
+size_t knn_grid_smem_bytes(int gmax);
+int launch_knn_grid_build(const KnnGridBuildParams &P, int ngrids, int B, cudaStream_t st);
+int launch_knn_grid_query(const KnnGridQueryParams &P, int B, cudaStream_t st);
+
+}  // namespace dsir

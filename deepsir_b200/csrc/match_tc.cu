@@ -28,7 +28,8 @@ constexpr int TC_T = 4;             // candidates kept per row per split
 constexpr int TC_BM = 256;          // source rows per work item (two M=128 accumulators)
 constexpr int TC_BN = 128;          // reference rows per unit (one N=128 MMA)
 constexpr int TC_STAGES = 4;        // B ring depth
-constexpr int TC_THREADS = 256;     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int TC_THREADS = 384;     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
+constexpr int TC_EPI_WARPS = 8;     // warps 4-7 own row block 0, warps 8-11 row block 1; TMEM lane quadrant = warp % 4
 constexpr int TC_MAX_SPLIT = 8;
 constexpr float TC_PAD_NORM = 3.0e38f;
 constexpr uint32_t TILE_BYTES = 128 * 128;  // one TMA box: 128 rows x 32 floats (128 B, swizzled)
@@ -110,6 +111,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// the wait names the destination registers so that no consumer can be scheduled above it
+__device__ __forceinline__ void tmem_wait8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ float tmem_ld1_sync(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
+    return __uint_as_float(r);
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row groups 1024 B apart (SBO), LBO unused (=1)
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
@@ -146,22 +165,33 @@ __device__ __forceinline__ void cand_insert(float (&cv)[T], int (&ci)[T], float 
     }
 }
 
-// 32 accumulator columns of one row: x = acc + nr; keep everything that comes within margin of the running min
-__device__ __forceinline__ void filter32(const uint32_t (&v)[32], const float *nr, int col0, float margin, float &thr,
-                                         float (&cv)[TC_T], int (&ci)[TC_T]) {
+// 8 accumulator columns of one row: x = acc + nr.  Fast path: eight adds, a min tree, one vote.  Whenever some lane of
+// the warp sees a value within `margin` of its running minimum, the (rare) slow path re-reads exactly the flagged
+// columns from TMEM one at a time, so the hot loop stays a few dozen instructions (it must live in the L0 I-cache).
+__device__ __forceinline__ void filter8(const uint32_t (&v)[8], const float *nr8, int col0, uint32_t taddr, float margin,
+                                        float &thr, float (&cv)[TC_T], int (&ci)[TC_T]) {
+    const float4 n0 = *reinterpret_cast<const float4 *>(nr8);
+    const float4 n1 = *reinterpret_cast<const float4 *>(nr8 + 4);
+    float x[8];
+    x[0] = __fadd_rn(__uint_as_float(v[0]), n0.x); x[1] = __fadd_rn(__uint_as_float(v[1]), n0.y);
+    x[2] = __fadd_rn(__uint_as_float(v[2]), n0.z); x[3] = __fadd_rn(__uint_as_float(v[3]), n0.w);
+    x[4] = __fadd_rn(__uint_as_float(v[4]), n1.x); x[5] = __fadd_rn(__uint_as_float(v[5]), n1.y);
+    x[6] = __fadd_rn(__uint_as_float(v[6]), n1.z); x[7] = __fadd_rn(__uint_as_float(v[7]), n1.w);
+    const float m = fminf(fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), fminf(fminf(x[4], x[5]), fminf(x[6], x[7])));
+    if (__any_sync(0xffffffffu, m < thr)) {
+        unsigned mask = 0;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        float x[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = __fadd_rn(__uint_as_float(v[g * 8 + e]), nr[g * 8 + e]);
-        float m = fminf(fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), fminf(fminf(x[4], x[5]), fminf(x[6], x[7])));
-        if (m < thr) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if (x[e] < thr) {
-                    cand_insert<TC_T>(cv, ci, x[e], col0 + g * 8 + e);
-                    thr = cv[0] + margin;
-                }
+        for (int e = 0; e < 8; ++e) mask |= (x[e] < thr) ? (1u << e) : 0u;
+        unsigned um = __reduce_or_sync(0xffffffffu, mask);
+#pragma unroll 1
+        while (um) {
+            const int e = __ffs(um) - 1;
+            um &= um - 1;
+            const float xe = __fadd_rn(tmem_ld1_sync(taddr + e), nr8[e]);   // bit-identical to x[e]
+            if (xe < thr) {
+                cand_insert<TC_T>(cv, ci, xe, col0 + e);
+                thr = cv[0] + margin;
+            }
         }
     }
 }
@@ -198,8 +228,8 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapA);
         prefetch_tmap(&mapB);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1 + 4); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1 + TC_EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_WARPS * 32); }
         mbar_init(full_a, 1);
         mbar_init(empty_a, 1);
         mbar_fence_init();
@@ -274,45 +304,37 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
     } else if (warp >= 4) {
         // =========================== epilogue: TMEM -> registers -> candidate lists ===========================
         const int q = warp & 3;                       // TMEM lane quadrant of this warp
-        const int trow = q * 32 + lane;               // row inside a 128-row block
+        const int a = (warp - 4) >> 2;                // row block (accumulator half) of this warp
+        const int trow = q * 32 + lane;               // row inside the 128-row block
         PipeState pb{0, 0}, pa{0, 0};
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
             const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
-            float cv[2][TC_T];
-            int ci[2][TC_T];
-            float thr[2], margin[2];
-            const float rmax = P.rmax[b];
+            float cv[TC_T];
+            int ci[TC_T];
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
-#pragma unroll
-                for (int t = 0; t < TC_T; ++t) { cv[a][t] = INFINITY; ci[a][t] = -1; }
-                thr[a] = INFINITY;
-                const int j = rb * TC_BM + a * 128 + trow;
-                const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
-                // 2 * eps, eps = 2 * (2^-9 + 2^-20) |s||r|  (tf32 truncation of both operands of -2<s,r>), +5 %
-                margin[a] = 8.2e-3f * sqrtf(nsj) * sqrtf(rmax) + 1e-30f;
-            }
+            for (int t = 0; t < TC_T; ++t) { cv[t] = INFINITY; ci[t] = -1; }
+            float thr = INFINITY;
+            const int j = rb * TC_BM + a * 128 + trow;
+            const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
+            // 2 * eps, eps = 2 * (2^-9 + 2^-20) |s||r|  (tf32 truncation of both operands of -2<s,r>), +5 %
+            const float margin = 8.2e-3f * sqrtf(nsj) * sqrtf(P.rmax[b]) + 1e-30f;
             for (int u = u0; u < u1; ++u) {
                 mbar_wait(&tmem_full[pa.stage], pa.phase);
                 tc_fence_after();
                 const float *nr = sNr + pb.stage * TC_BN;
+                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pa.stage * 256 + a * 128);
+                const int col0 = u * TC_BN;
+                uint32_t va[8], vb[8];
+                tmem_ld8(tbase, va);
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v0[32], v1[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pa.stage * 256 + c * 32);
-                    tmem_ld32(taddr, v0);
-                    tmem_ld32(taddr + 128, v1);
-                    float nrv[32];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float4 t4 = *reinterpret_cast<const float4 *>(nr + c * 32 + e * 4);
-                        nrv[e * 4 + 0] = t4.x; nrv[e * 4 + 1] = t4.y; nrv[e * 4 + 2] = t4.z; nrv[e * 4 + 3] = t4.w;
-                    }
-                    tmem_ld_wait();
-                    const int col0 = u * TC_BN + c * 32;
-                    filter32(v0, nrv, col0, margin[0], thr[0], cv[0], ci[0]);
-                    filter32(v1, nrv, col0, margin[1], thr[1], cv[1], ci[1]);
+                for (int g = 0; g < TC_BN / 8; g += 2) {      // ping-pong: the next group's load flies during this group's math
+                    tmem_wait8(va);
+                    tmem_ld8(tbase + (g + 1) * 8, vb);
+                    filter8(va, nr + g * 8, col0 + g * 8, tbase + g * 8, margin, thr, cv, ci);
+                    tmem_wait8(vb);
+                    if (g + 2 < TC_BN / 8) tmem_ld8(tbase + (g + 2) * 8, va);
+                    filter8(vb, nr + (g + 1) * 8, col0 + (g + 1) * 8, tbase + (g + 1) * 8, margin, thr, cv, ci);
                 }
                 tc_fence_before();
                 mbar_arrive(&tmem_empty[pa.stage]);
@@ -321,14 +343,12 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                 pb.advance(TC_STAGES);
                 pa.advance(2);
             }
+            const size_t row = (size_t)b * P.Jpad + (size_t)j - (size_t)0;
+            float *ov = P.cand_val + (((size_t)b * P.Jpad + (size_t)rb * TC_BM + a * 128 + trow) * P.S + sp) * TC_T;
+            int *oi = P.cand_idx + (((size_t)b * P.Jpad + (size_t)rb * TC_BM + a * 128 + trow) * P.S + sp) * TC_T;
+            (void)row;
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const size_t row = (size_t)b * P.Jpad + (size_t)rb * TC_BM + a * 128 + trow;
-                float *ov = P.cand_val + (row * P.S + sp) * TC_T;
-                int *oi = P.cand_idx + (row * P.S + sp) * TC_T;
-#pragma unroll
-                for (int t = 0; t < TC_T; ++t) { ov[t] = cv[a][t]; oi[t] = ci[a][t]; }
-            }
+            for (int t = 0; t < TC_T; ++t) { ov[t] = cv[t]; oi[t] = ci[t]; }
         }
     }
     tc_fence_before();
@@ -386,6 +406,7 @@ struct RefineParams {
     float *min_d;
     int *rescue_count;
     int *rescue_rows;  // [B*J] flat row ids
+    unsigned long long *rescue_keys;  // [B*J] (ordered distance bits << 32) | index, atomicMin target
 };
 
 __device__ __forceinline__ float exact_dist(const float *__restrict__ srow, const float *__restrict__ brow, int C, float nsj, float nrk) {
@@ -440,49 +461,74 @@ __global__ void match_tc_refine_kernel(RefineParams P) {
         if (rescue) {
             int pos = atomicAdd(P.rescue_count, 1);
             P.rescue_rows[pos] = (int)row;
+            P.rescue_keys[pos] = ~0ull;
         }
     }
 }
 
-// rescue: exhaustive exact fp32 scan of the listed rows, one CTA per row at a time
-__global__ __launch_bounds__(256) void match_tc_rescue_kernel(RefineParams P) {
+// rescue: exhaustive exact fp32 scan of the listed rows.  Work unit = (listed row, 2048-column chunk) so that a
+// handful of rows still spreads over the whole chip; partial results meet in a 64-bit atomicMin whose key orders
+// (distance, index) lexicographically.
+__device__ __forceinline__ unsigned int float_order_bits(float f) {
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_bits(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+constexpr int RESCUE_CHUNK = 2048;
+
+__global__ __launch_bounds__(256) void match_tc_rescue_kernel(RefineParams P, unsigned long long *keys) {
     __shared__ float srow[128];
-    __shared__ float rd[8];
-    __shared__ int rk[8];
+    __shared__ unsigned long long red[8];
     const int count = *P.rescue_count;
-    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    const int nchunk = (P.K + RESCUE_CHUNK - 1) / RESCUE_CHUNK;
+    const long long units = (long long)count * nchunk;
+    for (long long uidx = blockIdx.x; uidx < units; uidx += gridDim.x) {
+        const int i = (int)(uidx / nchunk), ch = (int)(uidx % nchunk);
         const int row = P.rescue_rows[i];
         const int b = row / P.J, j = row % P.J;
         __syncthreads();
         for (int c = threadIdx.x; c < P.Cp; c += blockDim.x) srow[c] = P.a_copy[((size_t)b * P.J + j) * P.Cp + c];
         __syncthreads();
         const float nsj = P.ns[(size_t)b * P.J + j];
-        float best = INFINITY;
-        int bk = 0;
-        for (int k = threadIdx.x; k < P.K; k += blockDim.x) {
+        unsigned long long best = ~0ull;
+        const int kend = min(P.K, (ch + 1) * RESCUE_CHUNK);
+        for (int k = ch * RESCUE_CHUNK + threadIdx.x; k < kend; k += blockDim.x) {
             float d = exact_dist(srow, P.b_copy + ((size_t)b * P.K + k) * P.Cp, P.Cp, nsj, P.nr[(size_t)b * P.K + k]);
-            if (d < best) { best = d; bk = k; }
+            if (d == d) {
+                unsigned long long key = ((unsigned long long)float_order_bits(d) << 32) | (unsigned int)k;
+                best = key < best ? key : best;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            float d2 = __shfl_xor_sync(0xffffffffu, best, o);
-            int k2 = __shfl_xor_sync(0xffffffffu, bk, o);
-            if (d2 < best || (d2 == best && k2 < bk)) { best = d2; bk = k2; }
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
         }
-        if ((threadIdx.x & 31) == 0) { rd[threadIdx.x >> 5] = best; rk[threadIdx.x >> 5] = bk; }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int w = 1; w < 8; ++w)
-                if (rd[w] < best || (rd[w] == best && rk[w] < bk)) { best = rd[w]; bk = rk[w]; }
-            P.idx[row] = (int64_t)bk;
-            if (P.min_d) P.min_d[row] = best;
+            for (int w = 1; w < 8; ++w) best = red[w] < best ? red[w] : best;
+            if (best != ~0ull) atomicMin(&keys[i], best);
         }
+    }
+}
+
+__global__ void match_tc_rescue_finalize_kernel(RefineParams P, const unsigned long long *keys) {
+    const int count = *P.rescue_count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const int row = P.rescue_rows[i];
+        const unsigned long long key = keys[i];
+        const bool none = key == ~0ull;  // every distance was NaN: same answer as the fp32 kernel (index 0, +inf)
+        P.idx[row] = none ? 0 : (int64_t)(unsigned int)(key & 0xffffffffull);
+        if (P.min_d) P.min_d[row] = none ? INFINITY : float_from_order_bits((unsigned int)(key >> 32));
     }
 }
 
 struct TcPlan {
     int Cp, KB, RB, U, S, Jpad, Kpad;
-    size_t off_a, off_b, off_nrpad, off_rmax, off_cval, off_cidx, off_count, off_rows, total;
+    size_t off_a, off_b, off_nrpad, off_rmax, off_cval, off_cidx, off_count, off_rows, off_keys, total;
 };
 
 TcPlan make_plan(int B, int C, int J, int K) {
@@ -512,6 +558,7 @@ TcPlan make_plan(int B, int C, int J, int K) {
     p.off_cidx = take((size_t)B * p.Jpad * S * TC_T * 4);
     p.off_count = take(256);
     p.off_rows = take((size_t)B * J * 4);
+    p.off_keys = take((size_t)B * J * 8);
     p.total = off + 1024;
     return p;
 }
@@ -587,10 +634,13 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     R.B = P.B; R.J = P.J; R.K = P.K; R.C = P.C; R.Cp = pl.Cp; R.S = pl.S; R.Jpad = pl.Jpad;
     R.a_copy = a_copy; R.b_copy = b_copy; R.ns = P.ns; R.nr = P.nr; R.rmax = rmax; R.cand_val = cval; R.cand_idx = cidx;
     R.idx = P.idx; R.min_d = P.min_d; R.rescue_count = count; R.rescue_rows = rows;
+    R.rescue_keys = (unsigned long long *)(base + pl.off_keys);
     const long long nrows = (long long)P.B * P.J;
     match_tc_refine_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(R);
     DSIR_LAUNCH_CHECK();
-    match_tc_rescue_kernel<<<sms * 2, 256, 0, st>>>(R);
+    match_tc_rescue_kernel<<<sms * 4, 256, 0, st>>>(R, R.rescue_keys);
+    DSIR_LAUNCH_CHECK();
+    match_tc_rescue_finalize_kernel<<<sms, 256, 0, st>>>(R, R.rescue_keys);
     DSIR_LAUNCH_CHECK();
     return DSIR_OK;
 }
