@@ -2,6 +2,7 @@
 // caller's workspace, and enqueues kernels on the caller's stream.  No host synchronisation, no
 // allocation, no global state besides a thread-local "last CUDA error" string.
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kabsch.cuh"
@@ -79,8 +80,13 @@ bool use_grid(int algo, int Ns) {
     return Ns >= KNN_GRID_MIN_POINTS;
 }
 
-constexpr float GRID_CELLS_PER_POINT = 2.0f;
-constexpr float GRID_R0_CELLS = 0.75f;
+// tunables (overridable for experiments through DSIR_GRID_CPP / DSIR_GRID_R0)
+float env_float(const char *name, float dflt) {
+    const char *v = getenv(name);
+    return v ? (float)atof(v) : dflt;
+}
+const float GRID_CELLS_PER_POINT = env_float("DSIR_GRID_CPP", 1.0f);
+const float GRID_R0_CELLS = env_float("DSIR_GRID_R0", 1.0f);
 
 }  // namespace
 

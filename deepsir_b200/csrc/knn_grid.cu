@@ -148,18 +148,31 @@ __global__ __launch_bounds__(GRID_BUILD_THREADS) void knn_grid_build_kernel(KnnG
     }
 }
 
-// lexicographic (d, idx) sorted insertion; caller guarantees (d, s) < (bd[K-1], bi[K-1])
+// lexicographic (d, idx) sorted insertion; caller guarantees (d, s) < (bd[K-1], bi[K-1]).  Distance ties are rare
+// (duplicated points), so the index comparisons live on a separate, warp-uniformly branched path.
 template <int KMAX>
 __device__ __forceinline__ void topk_insert_lex(float (&bd)[KMAX], int (&bi)[KMAX], float d, int s) {
+    bool tie = false;
 #pragma unroll
-    for (int p = KMAX - 1; p >= 0; --p) {
-        const int pm = p > 0 ? p - 1 : 0;
-        bool shift = (p > 0) && (d < bd[pm] || (d == bd[pm] && s < bi[pm]));
-        bool here = !shift && (d < bd[p] || (d == bd[p] && s < bi[p]));
-        float nd = shift ? bd[pm] : (here ? d : bd[p]);
-        int ni = shift ? bi[pm] : (here ? s : bi[p]);
-        bd[p] = nd;
-        bi[p] = ni;
+    for (int p = 0; p < KMAX; ++p) tie = tie || (d == bd[p]);
+    if (!tie) {
+#pragma unroll
+        for (int p = KMAX - 1; p >= 0; --p) {
+            const int pm = p > 0 ? p - 1 : 0;
+            const bool shift = (p > 0) && (d < bd[pm]);
+            const bool here = !shift && (d < bd[p]);
+            bd[p] = shift ? bd[pm] : (here ? d : bd[p]);
+            bi[p] = shift ? bi[pm] : (here ? s : bi[p]);
+        }
+    } else {
+#pragma unroll
+        for (int p = KMAX - 1; p >= 0; --p) {
+            const int pm = p > 0 ? p - 1 : 0;
+            const bool shift = (p > 0) && (d < bd[pm] || (d == bd[pm] && s < bi[pm]));
+            const bool here = !shift && (d < bd[p] || (d == bd[p] && s < bi[p]));
+            bd[p] = shift ? bd[pm] : (here ? d : bd[p]);
+            bi[p] = shift ? bi[pm] : (here ? s : bi[p]);
+        }
     }
 }
 
@@ -211,14 +224,25 @@ __global__ __launch_bounds__(128) void knn_grid_query_kernel(KnnGridQueryParams 
                     const int r0 = run == 0 ? a0 : b0, r1 = run == 0 ? a1 : b1;
                     if (r0 > r1) continue;
                     const int s = cs[row + r0], e = cs[row + r1 + 1];
-                    for (int i = s; i < e; ++i) {
-                        const float4 p = S[i];
-                        const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
-                        float d = __fmul_rn(dx, dx);
-                        d = __fmaf_rn(dy, dy, d);
-                        d = __fmaf_rn(dz, dz, d);
-                        const int pi = __float_as_int(p.w);
-                        if (d < bd[KMAX - 1] || (d == bd[KMAX - 1] && pi < bi[KMAX - 1])) topk_insert_lex<KMAX>(bd, bi, d, pi);
+                    // four candidates per trip: four independent load->distance chains hide the load latency
+                    for (int i = s; i < e; i += 4) {
+                        float d4[4];
+                        int p4[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const bool ok = i + u < e;
+                            const float4 p = S[ok ? i + u : s];
+                            const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+                            float d = __fmul_rn(dx, dx);
+                            d = __fmaf_rn(dy, dy, d);
+                            d = __fmaf_rn(dz, dz, d);
+                            d4[u] = ok ? d : INFINITY;
+                            p4[u] = ok ? __float_as_int(p.w) : 0x7fffffff;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (d4[u] < bd[KMAX - 1] || (d4[u] == bd[KMAX - 1] && p4[u] < bi[KMAX - 1]))
+                                topk_insert_lex<KMAX>(bd, bi, d4[u], p4[u]);
                     }
                 }
             }

@@ -124,6 +124,15 @@ __device__ __forceinline__ void tmem_wait8(uint32_t (&r)[8]) {
                  :
                  : "memory");
 }
+__device__ __forceinline__ void tmem_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ float tmem_ld1_sync(uint32_t taddr) {
     uint32_t r;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
@@ -165,29 +174,35 @@ __device__ __forceinline__ void cand_insert(float (&cv)[T], int (&ci)[T], float 
     }
 }
 
-// 8 accumulator columns of one row: x = acc + nr.  Fast path: eight adds, a min tree, one vote.  Whenever some lane of
-// the warp sees a value within `margin` of its running minimum, the (rare) slow path re-reads exactly the flagged
-// columns from TMEM one at a time, so the hot loop stays a few dozen instructions (it must live in the L0 I-cache).
-__device__ __forceinline__ void filter8(const uint32_t (&v)[8], const float *nr8, int col0, uint32_t taddr, float margin,
-                                        float &thr, float (&cv)[TC_T], int (&ci)[TC_T]) {
-    const float4 n0 = *reinterpret_cast<const float4 *>(nr8);
-    const float4 n1 = *reinterpret_cast<const float4 *>(nr8 + 4);
-    float x[8];
-    x[0] = __fadd_rn(__uint_as_float(v[0]), n0.x); x[1] = __fadd_rn(__uint_as_float(v[1]), n0.y);
-    x[2] = __fadd_rn(__uint_as_float(v[2]), n0.z); x[3] = __fadd_rn(__uint_as_float(v[3]), n0.w);
-    x[4] = __fadd_rn(__uint_as_float(v[4]), n1.x); x[5] = __fadd_rn(__uint_as_float(v[5]), n1.y);
-    x[6] = __fadd_rn(__uint_as_float(v[6]), n1.z); x[7] = __fadd_rn(__uint_as_float(v[7]), n1.w);
-    const float m = fminf(fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), fminf(fminf(x[4], x[5]), fminf(x[6], x[7])));
-    if (__any_sync(0xffffffffu, m < thr)) {
+// 32 accumulator columns of one row: x = acc + nr.  Fast path: 32 independent adds, a min tree, ONE vote.  Whenever
+// some lane of the warp sees a value within `margin` of its running minimum, the (rare) slow path re-reads exactly
+// the flagged columns from TMEM one at a time, so the hot loop stays small enough for the instruction cache and
+// carries no per-element branches.
+__device__ __forceinline__ void filter32(const uint32_t (&v)[32], const float *nr32, int col0, uint32_t taddr, float margin,
+                                         float &thr, float (&cv)[TC_T], int (&ci)[TC_T]) {
+    float x[32];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float4 n4 = *reinterpret_cast<const float4 *>(nr32 + 4 * e);
+        x[4 * e + 0] = __fadd_rn(__uint_as_float(v[4 * e + 0]), n4.x);
+        x[4 * e + 1] = __fadd_rn(__uint_as_float(v[4 * e + 1]), n4.y);
+        x[4 * e + 2] = __fadd_rn(__uint_as_float(v[4 * e + 2]), n4.z);
+        x[4 * e + 3] = __fadd_rn(__uint_as_float(v[4 * e + 3]), n4.w);
+    }
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = fminf(fminf(x[4 * e], x[4 * e + 1]), fminf(x[4 * e + 2], x[4 * e + 3]));
+    const float mm = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
+    if (__any_sync(0xffffffffu, mm < thr)) {
         unsigned mask = 0;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) mask |= (x[e] < thr) ? (1u << e) : 0u;
+        for (int e = 0; e < 32; ++e) mask |= (x[e] < thr) ? (1u << e) : 0u;
         unsigned um = __reduce_or_sync(0xffffffffu, mask);
 #pragma unroll 1
         while (um) {
             const int e = __ffs(um) - 1;
             um &= um - 1;
-            const float xe = __fadd_rn(tmem_ld1_sync(taddr + e), nr8[e]);   // bit-identical to x[e]
+            const float xe = __fadd_rn(tmem_ld1_sync(taddr + e), nr32[e]);   // bit-identical to x[e]
             if (xe < thr) {
                 cand_insert<TC_T>(cv, ci, xe, col0 + e);
                 thr = cv[0] + margin;
@@ -256,7 +271,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                     for (int kb = 0; kb < KB; ++kb)
                         tma_load_3d(sA + (a * KB + kb) * TILE_BYTES, &mapA, kb * 32, rb * TC_BM + a * 128, b, full_a);
                 for (int u = u0; u < u1; ++u) {
-                    mbar_wait(&empty_b[pb.stage], pb.phase ^ 1u);
+                    while (!mbar_try_wait(&empty_b[pb.stage], pb.phase ^ 1u)) __nanosleep(64);
                     mbar_expect_tx(&full_b[pb.stage], KB * TILE_BYTES + TC_BN * 4);
 #pragma unroll
                     for (int kb = 0; kb < KB; ++kb)
@@ -325,16 +340,16 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                 const float *nr = sNr + pb.stage * TC_BN;
                 const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pa.stage * 256 + a * 128);
                 const int col0 = u * TC_BN;
-                uint32_t va[8], vb[8];
-                tmem_ld8(tbase, va);
+                uint32_t va[32], vb[32];
+                tmem_ld32(tbase, va);
 #pragma unroll 1
-                for (int g = 0; g < TC_BN / 8; g += 2) {      // ping-pong: the next group's load flies during this group's math
-                    tmem_wait8(va);
-                    tmem_ld8(tbase + (g + 1) * 8, vb);
-                    filter8(va, nr + g * 8, col0 + g * 8, tbase + g * 8, margin, thr, cv, ci);
-                    tmem_wait8(vb);
-                    if (g + 2 < TC_BN / 8) tmem_ld8(tbase + (g + 2) * 8, va);
-                    filter8(vb, nr + (g + 1) * 8, col0 + (g + 1) * 8, tbase + (g + 1) * 8, margin, thr, cv, ci);
+                for (int g = 0; g < TC_BN / 32; g += 2) {     // ping-pong: the next 32 columns fly during this step's math
+                    tmem_wait32(va);
+                    tmem_ld32(tbase + (g + 1) * 32, vb);
+                    filter32(va, nr + g * 32, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci);
+                    tmem_wait32(vb);
+                    if (g + 2 < TC_BN / 32) tmem_ld32(tbase + (g + 2) * 32, va);
+                    filter32(vb, nr + (g + 1) * 32, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci);
                 }
                 tc_fence_before();
                 mbar_arrive(&tmem_empty[pa.stage]);
