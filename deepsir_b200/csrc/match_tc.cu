@@ -1,22 +1,37 @@
 // Fused feature-distance + row-argmin on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a.
 //
-// Replaces the chunked block network/model.py:558-569 of the reference (match_features_V2 + .min(dim=2)[1]),
+// Replaces the chunked block network/model.py:558-569 of the reference (match_features_V2 + .min(dim=2)[1]);
 // the [J,K] score matrix never leaves TMEM/registers.  Bit-exactness on the indices is kept by a
 // FILTER-AND-REFINE scheme:
 //
-//   prep    K-major (point-major) fp32 copies of both feature sets; the reference copy is scaled by -2
-//           (exact), padded reference norms, per-batch max reference norm.
-//   filter  persistent warp-specialised kernel: TMA (SWIZZLE_128B boxes) -> tcgen05.mma kind::tf32,
-//           M=128 x N=128 accumulators in TMEM (2 row blocks x 2 stages = 512 columns) -> epilogue warps
-//           read them back with tcgen05.ld and keep, per source row, the T smallest approximate values
-//           x_jk = nr_k - 2<s_j,r_k>_tf32 that ever came within `margin_j` of the running minimum.
-//           margin_j = 2 * eps_j where eps_j bounds the tf32 input-truncation error of x_jk, so the exact fp32
+//   prep    point-major (K-major) fp32 copies of both feature sets (reference side scaled by -2, exact) for the
+//           refine stage, and fp16 copies for the tensor cores: every value is multiplied by a per-batch power of
+//           two sigma (exact) that brings the largest feature norm below 1, then rounded to fp16.  The squared
+//           reference norm is FOLDED INTO THE CONTRACTION: 16 extra channels carry 1,1,1,0.. on the source side and
+//           the three-term fp16 split (hi, lo, lolo) of sigma^2 |r_k|^2 on the reference side, so the accumulator
+//           already holds  x_jk = sigma^2 (|r_k|^2 - 2 <s_j, r_k>)  and the epilogue needs no add and no shared
+//           memory.
+//   filter  persistent warp-specialised kernel, one CTA per SM, 640 threads:
+//             warp 0      TMA producer  (SWIZZLE_128B feature boxes + SWIZZLE_32B norm boxes -> mbarrier ring)
+//             warp 1      one thread issues tcgen05.mma kind::f16 (M=128, N=128, K=16; 5 per tile) and
+//                         tcgen05.commit; four M=128 accumulators (512 source rows per work item) fill the 512
+//                         TMEM columns, so the accumulator of row block i is drained while the tensor pipe works
+//                         on the other three
+//             warp 2      TMEM allocation
+//             warps 4-19  epilogue: tcgen05.ld 32 columns at a time, a 3-input-min tree, ONE warp vote per 32
+//                         columns; only when some row sees a value within `margin` of its running minimum does the
+//                         slow path re-read the flagged columns and insert them into the row's sorted candidate
+//                         list.
+//           margin_j = 2 eps_j, where eps_j bounds the fp16-input error of x_jk (see tc_margin), so the exact fp32
 //           argmin is always among the kept candidates unless the list saturated.
 //   refine  per row: candidates within margin of the approximate minimum are re-scored in exact fp32 with the
 //           op order of match_fp32.cu (fma chain over channels, ((-2 dot)+ns)+nr) and the (value, index)
 //           lexicographic minimum is taken -> identical indices AND minima to the fp32 kernel.
 //   rescue  rows whose list saturated (or held no finite candidate) are recomputed exhaustively in fp32.
 #include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
 
 #include "match_tc.cuh"
 
@@ -24,15 +39,19 @@ namespace dsir {
 
 namespace {
 
-constexpr int TC_T = 4;             // candidates kept per row per split
-constexpr int TC_BM = 256;          // source rows per work item (two M=128 accumulators)
-constexpr int TC_BN = 128;          // reference rows per unit (one N=128 MMA)
-constexpr int TC_STAGES = 4;        // B ring depth
-constexpr int TC_THREADS = 384;     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
-constexpr int TC_EPI_WARPS = 8;     // warps 4-7 own row block 0, warps 8-11 row block 1; TMEM lane quadrant = warp % 4
+constexpr int TC_T = 4;                       // candidates kept per row per split
+constexpr int TC_RBS = 4;                     // 128-row blocks (accumulators) per work item
+constexpr int TC_BM = 128 * TC_RBS;           // source rows per work item
+constexpr int TC_BN = 128;                    // reference rows per unit (one N=128 MMA)
+constexpr int TC_STAGES = 5;                  // B ring depth
+constexpr int TC_EPI_WARPS = 4 * TC_RBS;      // warp 4+4i+q drains TMEM lane quadrant q of accumulator i
+constexpr int TC_THREADS = (4 + TC_EPI_WARPS) * 32;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle
 constexpr int TC_MAX_SPLIT = 8;
-constexpr float TC_PAD_NORM = 3.0e38f;
-constexpr uint32_t TILE_BYTES = 128 * 128;  // one TMA box: 128 rows x 32 floats (128 B, swizzled)
+constexpr int TC_CH = 64;                     // fp16 channels per point in the tensor-core copy (one 128-byte swizzle row)
+constexpr int TC_AUG = 16;                    // folded-norm channels (one K=16 MMA)
+constexpr float TC_PAD_NORM = 60000.0f;       // folded norm of padded reference rows: larger than any real x_jk (<= 3)
+constexpr uint32_t MAIN_TILE = 128 * TC_CH * 2;   // 16 KB: 128 rows x 64 halves, 128-byte swizzle
+constexpr uint32_t AUG_TILE = 128 * TC_AUG * 2;   //  4 KB: 128 rows x 16 halves, 32-byte swizzle
 
 // ---------------------------------------------------------------------------------------------------------
 // driver entry point for tensor-map encoding (no libcuda link dependency)
@@ -53,16 +72,16 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// [B][N][Cp] fp32, box = 32 channels x 128 rows, 128-byte swizzle; rows/batches beyond the extent read as zero
-bool make_feat_tmap(CUtensorMap *m, const float *base, int B, int N, int Cp) {
+// [B][N][W] fp16, box = W channels x 128 rows; rows/batches beyond the extent read as zero
+bool make_half_tmap(CUtensorMap *m, const __half *base, int B, int N, int W, CUtensorMapSwizzle swz) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)N, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)N * Cp * 4};
-    cuuint32_t box[3] = {32, 128, 1};
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)W * 2, (cuuint64_t)N * W * 2};
+    cuuint32_t box[3] = {(cuuint32_t)W, 128, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -89,12 +108,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -110,20 +129,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-}
 // the wait names the destination registers so that no consumer can be scheduled above it
-__device__ __forceinline__ void tmem_wait8(uint32_t (&r)[8]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
-                 :
-                 : "memory");
-}
 __device__ __forceinline__ void tmem_wait32(uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
@@ -138,20 +144,30 @@ __device__ __forceinline__ float tmem_ld1_sync(uint32_t taddr) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
     return __uint_as_float(r);
 }
+__device__ __forceinline__ float fmin3(float a, float b, float c) {   // FMNMX3 (sm_100+)
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row groups 1024 B apart (SBO), LBO unused (=1)
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+// K-major shared-memory matrix descriptors (sm_100): 8-row groups `sbo` bytes apart, LBO unused (=1)
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo, uint32_t layout) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;            // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset
-    d |= (uint64_t)1 << 46;            // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+    d |= (uint64_t)1 << 16;             // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(sbo >> 4) << 32;    // stride byte offset
+    d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
+    d |= (uint64_t)layout << 61;        // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
     return d;
 }
 
-// instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor: D=f32, A=B=f16, both K-major, N=128, M=128
+constexpr uint32_t TC_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 struct PipeState {
     int stage;
@@ -160,6 +176,22 @@ struct PipeState {
         if (++stage == n) { stage = 0; phase ^= 1u; }
     }
 };
+
+// Bound on |x_hat_jk - x_jk| in scaled units, x = sigma^2 (|r|^2 - 2<s,r>), for fp16-rounded operands with fp32
+// accumulation; a = sigma |s_j|, R = sigma max_k |r_k| (both <= 1):
+//   2^-9 (1+2^-12) a R          rounding of s' and -2r' to fp16 (unit round-off 2^-11 each, Cauchy-Schwarz)
+//   2^-25 sqrt(C) (a + 2R)      fp16 subnormal spacing (values below 2^-14)
+//   80 * 2^-22 (2aR + R^2)      fp32 accumulation of the 80 products inside the tensor core (4x an IEEE chain)
+//   2^-24 + 2^-30 R^2           three-term fp16 split of the folded norm
+// margin = 2 eps (+2 %): every column whose exact value could be the row minimum lies within margin of the
+// approximate minimum.
+__device__ __forceinline__ float tc_margin(float ns_j, float rmax_b, float sigma, int C) {
+    const float a = sigma * sqrtf(ns_j);
+    const float R = sigma * sqrtf(rmax_b);
+    const float eps = 1.9536e-3f * a * R + 2.9803e-8f * sqrtf((float)C) * (a + 2.f * R) + 1.9074e-5f * (2.f * a * R + R * R) +
+                      5.97e-8f + 9.4e-10f * R * R;
+    return 2.04f * eps + 1e-30f;
+}
 
 template <int T>
 __device__ __forceinline__ void cand_insert(float (&cv)[T], int (&ci)[T], float x, int col) {
@@ -174,77 +206,79 @@ __device__ __forceinline__ void cand_insert(float (&cv)[T], int (&ci)[T], float 
     }
 }
 
-// 32 accumulator columns of one row: x = acc + nr.  Fast path: 32 independent adds, a min tree, ONE vote.  Whenever
-// some lane of the warp sees a value within `margin` of its running minimum, the (rare) slow path re-reads exactly
-// the flagged columns from TMEM one at a time, so the hot loop stays small enough for the instruction cache and
-// carries no per-element branches.
-__device__ __forceinline__ void filter32(const uint32_t (&v)[32], const float *nr32, int col0, uint32_t taddr, float margin,
-                                         float &thr, float (&cv)[TC_T], int (&ci)[TC_T]) {
-    float x[32];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const float4 n4 = *reinterpret_cast<const float4 *>(nr32 + 4 * e);
-        x[4 * e + 0] = __fadd_rn(__uint_as_float(v[4 * e + 0]), n4.x);
-        x[4 * e + 1] = __fadd_rn(__uint_as_float(v[4 * e + 1]), n4.y);
-        x[4 * e + 2] = __fadd_rn(__uint_as_float(v[4 * e + 2]), n4.z);
-        x[4 * e + 3] = __fadd_rn(__uint_as_float(v[4 * e + 3]), n4.w);
-    }
-    float m[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) m[e] = fminf(fminf(x[4 * e], x[4 * e + 1]), fminf(x[4 * e + 2], x[4 * e + 3]));
-    const float mm = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
+// 32 accumulator columns of one row.  Fast path: a 3-input-min tree (15 FMNMX3 + 1 FMNMX) and ONE vote.  Whenever
+// some lane of the warp sees a value within `margin` of its running minimum, the slow path re-reads exactly the
+// flagged columns from TMEM one at a time, so the hot loop stays small and carries no per-element branches.
+__device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint32_t taddr, float margin, float &thr,
+                                         float (&cv)[TC_T], int (&ci)[TC_T]) {
+#define F(i) __uint_as_float(v[i])
+    const float a0 = fmin3(F(0), F(1), F(2)), a1 = fmin3(F(3), F(4), F(5)), a2 = fmin3(F(6), F(7), F(8));
+    const float a3 = fmin3(F(9), F(10), F(11)), a4 = fmin3(F(12), F(13), F(14)), a5 = fmin3(F(15), F(16), F(17));
+    const float a6 = fmin3(F(18), F(19), F(20)), a7 = fmin3(F(21), F(22), F(23)), a8 = fmin3(F(24), F(25), F(26));
+    const float a9 = fmin3(F(27), F(28), F(29));
+    const float b0 = fmin3(a0, a1, a2), b1 = fmin3(a3, a4, a5), b2 = fmin3(a6, a7, a8), b3 = fmin3(a9, F(30), F(31));
+    const float mm = fminf(fmin3(b0, b1, b2), b3);
     if (__any_sync(0xffffffffu, mm < thr)) {
         unsigned mask = 0;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) mask |= (x[e] < thr) ? (1u << e) : 0u;
+        for (int e = 0; e < 32; ++e) mask |= (F(e) < thr) ? (1u << e) : 0u;
         unsigned um = __reduce_or_sync(0xffffffffu, mask);
 #pragma unroll 1
         while (um) {
             const int e = __ffs(um) - 1;
             um &= um - 1;
-            const float xe = __fadd_rn(tmem_ld1_sync(taddr + e), nr32[e]);   // bit-identical to x[e]
+            const float xe = tmem_ld1_sync(taddr + e);   // bit-identical to v[e]
             if (xe < thr) {
                 cand_insert<TC_T>(cv, ci, xe, col0 + e);
                 thr = cv[0] + margin;
             }
         }
     }
+#undef F
 }
 
 struct TcParams {
-    int B, J, K, C, Cp;
-    int RB, U, S;           // row blocks (256), units (128), k-splits
+    int B, J, K, C;
+    int RB, U, S;           // row blocks (512), units (128), k-splits
     int Jpad, Kpad;
     const float *ns;        // [B,J] exact squared norms
-    const float *nr_pad;    // [B,Kpad] exact squared norms, TC_PAD_NORM beyond K
     const float *rmax;      // [B] max reference squared norm
-    float *cand_val;        // [B][Jpad][S][T]
+    const float *scale;     // [B] sigma (power of two)
+    float *cand_val;        // [B][Jpad][S][T]  (scaled units)
     int *cand_idx;
+    unsigned long long *dbg;  // [grid][4]: start ns, end ns, cycles, units (diagnostic, always written)
 };
 
-template <int KB>  // 32-channel blocks (Cp = 32*KB)
+template <int NKS>  // 16-channel k-steps of the feature part (NKS = ceil(C / 16), C <= 64)
 __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                         const __grid_constant__ CUtensorMap mapB,
+                                                                        const __grid_constant__ CUtensorMap mapAaug,
+                                                                        const __grid_constant__ CUtensorMap mapBaug,
                                                                         TcParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = smem;                                            // [2][KB][16 KB]
-    uint8_t *sB = sA + 2 * KB * TILE_BYTES;                        // [STAGES][KB][16 KB]
-    float *sNr = (float *)(sB + TC_STAGES * KB * TILE_BYTES);      // [STAGES][128]
-    uint64_t *bars = (uint64_t *)(sNr + TC_STAGES * TC_BN);
+    uint8_t *sA = smem;                                            // [RBS][16 KB]
+    uint8_t *sAaug = sA + TC_RBS * MAIN_TILE;                      // [4 KB]
+    uint8_t *sB = sAaug + AUG_TILE;                                // [STAGES][16 KB]
+    uint8_t *sBaug = sB + TC_STAGES * MAIN_TILE;                   // [STAGES][4 KB]
+    uint64_t *bars = (uint64_t *)(sBaug + TC_STAGES * AUG_TILE);
     uint64_t *full_b = bars, *empty_b = bars + TC_STAGES;
-    uint64_t *tmem_full = bars + 2 * TC_STAGES, *tmem_empty = tmem_full + 2;
-    uint64_t *full_a = tmem_empty + 2, *empty_a = full_a + 1;
+    uint64_t *tmem_full = bars + 2 * TC_STAGES, *tmem_empty = tmem_full + TC_RBS;
+    uint64_t *full_a = tmem_empty + TC_RBS, *empty_a = full_a + 1;
     uint32_t *tmem_slot = (uint32_t *)(empty_a + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_items = P.B * P.RB * P.S;
+    unsigned long long *dbg_s = (unsigned long long *)(tmem_slot + 2);   // start time / start clock, parked in smem
+    if (threadIdx.x == 0) { dbg_s[0] = globaltimer_ns(); dbg_s[1] = clock64(); }
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapA);
         prefetch_tmap(&mapB);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1 + TC_EPI_WARPS); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_WARPS * 32); }
+        prefetch_tmap(&mapAaug);
+        prefetch_tmap(&mapBaug);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int a = 0; a < TC_RBS; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
         mbar_init(full_a, 1);
         mbar_init(empty_a, 1);
         mbar_fence_init();
@@ -260,24 +294,22 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
         if (lane == 0) {
             PipeState pb{0, 0};
             uint32_t iphase = 0;
+            bool first = true;
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
                 const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
                 const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
                 mbar_wait(empty_a, iphase ^ 1u);
-                mbar_expect_tx(full_a, 2 * KB * TILE_BYTES);
+                mbar_expect_tx(full_a, TC_RBS * MAIN_TILE + (first ? AUG_TILE : 0u));
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
-#pragma unroll
-                    for (int kb = 0; kb < KB; ++kb)
-                        tma_load_3d(sA + (a * KB + kb) * TILE_BYTES, &mapA, kb * 32, rb * TC_BM + a * 128, b, full_a);
+                for (int a = 0; a < TC_RBS; ++a)
+                    tma_load_3d(sA + a * MAIN_TILE, &mapA, 0, rb * TC_BM + a * 128, b, full_a);
+                if (first) tma_load_3d(sAaug, &mapAaug, 0, 0, 0, full_a);   // constant 1,1,1,0.. tile, loaded once
+                first = false;
                 for (int u = u0; u < u1; ++u) {
-                    while (!mbar_try_wait(&empty_b[pb.stage], pb.phase ^ 1u)) __nanosleep(64);
-                    mbar_expect_tx(&full_b[pb.stage], KB * TILE_BYTES + TC_BN * 4);
-#pragma unroll
-                    for (int kb = 0; kb < KB; ++kb)
-                        tma_load_3d(sB + (pb.stage * KB + kb) * TILE_BYTES, &mapB, kb * 32, u * TC_BN, b, &full_b[pb.stage]);
-                    bulk_g2s(sNr + pb.stage * TC_BN, P.nr_pad + (size_t)b * P.Kpad + (size_t)u * TC_BN, TC_BN * 4,
-                             &full_b[pb.stage]);
+                    while (!mbar_try_wait(&empty_b[pb.stage], pb.phase ^ 1u)) __nanosleep(32);
+                    mbar_expect_tx(&full_b[pb.stage], MAIN_TILE + AUG_TILE);
+                    tma_load_3d(sB + pb.stage * MAIN_TILE, &mapB, 0, u * TC_BN, b, &full_b[pb.stage]);
+                    tma_load_3d(sBaug + pb.stage * AUG_TILE, &mapBaug, 0, u * TC_BN, b, &full_b[pb.stage]);
                     pb.advance(TC_STAGES);
                 }
                 iphase ^= 1u;
@@ -286,31 +318,35 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            PipeState pb{0, 0}, pa{0, 0};
-            uint32_t iphase = 0;
+            PipeState pb{0, 0};
+            uint32_t iphase = 0, aphase = 0;
+            const uint64_t descA0 = make_kmajor_desc(smem_u32(sA), 1024, 2);
+            const uint64_t descAaug = make_kmajor_desc(smem_u32(sAaug), 256, 6);
+            const uint64_t descB0 = make_kmajor_desc(smem_u32(sB), 1024, 2);
+            const uint64_t descBaug0 = make_kmajor_desc(smem_u32(sBaug), 256, 6);
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
                 const int sp = it % P.S;
                 const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
                 mbar_wait(full_a, iphase);
                 for (int u = u0; u < u1; ++u) {
                     mbar_wait(&full_b[pb.stage], pb.phase);
-                    mbar_wait(&tmem_empty[pa.stage], pa.phase ^ 1u);
-                    tc_fence_after();
+                    const uint64_t descB = descB0 + (uint64_t)((uint32_t)pb.stage * (MAIN_TILE >> 4));
+                    const uint64_t descBaug = descBaug0 + (uint64_t)((uint32_t)pb.stage * (AUG_TILE >> 4));
 #pragma unroll
-                    for (int a = 0; a < 2; ++a) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(pa.stage * 256 + a * 128);
+                    for (int a = 0; a < TC_RBS; ++a) {
+                        mbar_wait(&tmem_empty[a], aphase ^ 1u);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(a * 128);
+                        const uint64_t descA = descA0 + (uint64_t)(a * (MAIN_TILE >> 4));
 #pragma unroll
-                        for (int ks = 0; ks < KB * 4; ++ks) {
-                            const int kb = ks >> 2, kk = ks & 3;
-                            uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + (a * KB + kb) * TILE_BYTES) + kk * 32);
-                            uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (pb.stage * KB + kb) * TILE_BYTES) + kk * 32);
-                            mma_tf32(d_tmem, da, db, TC_IDESC, ks > 0 ? 1u : 0u);
-                        }
+                        for (int ks = 0; ks < NKS; ++ks)     // +32 bytes (16 halves) inside the 128-byte swizzle row
+                            mma_f16(d_tmem, descA + (uint64_t)(ks * 2), descB + (uint64_t)(ks * 2), TC_IDESC, ks > 0 ? 1u : 0u);
+                        mma_f16(d_tmem, descAaug, descBaug, TC_IDESC, 1u);   // + sigma^2 |r_k|^2
+                        tc_commit(&tmem_full[a]);          // accumulator a ready for its epilogue warps
                     }
-                    tc_commit(&empty_b[pb.stage]);     // B stage reusable once these MMAs retire (and the epilogue is done with nr)
-                    tc_commit(&tmem_full[pa.stage]);   // accumulators ready for the epilogue
+                    tc_commit(&empty_b[pb.stage]);         // B stage reusable once these MMAs retire
                     pb.advance(TC_STAGES);
-                    pa.advance(2);
+                    aphase ^= 1u;
                 }
                 tc_commit(empty_a);
                 iphase ^= 1u;
@@ -319,9 +355,9 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
     } else if (warp >= 4) {
         // =========================== epilogue: TMEM -> registers -> candidate lists ===========================
         const int q = warp & 3;                       // TMEM lane quadrant of this warp
-        const int a = (warp - 4) >> 2;                // row block (accumulator half) of this warp
+        const int a = (warp - 4) >> 2;                // accumulator (row block) of this warp
         const int trow = q * 32 + lane;               // row inside the 128-row block
-        PipeState pb{0, 0}, pa{0, 0};
+        uint32_t aphase = 0;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
             const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
@@ -332,13 +368,11 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
             float thr = INFINITY;
             const int j = rb * TC_BM + a * 128 + trow;
             const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
-            // 2 * eps, eps = 2 * (2^-9 + 2^-20) |s||r|  (tf32 truncation of both operands of -2<s,r>), +5 %
-            const float margin = 8.2e-3f * sqrtf(nsj) * sqrtf(P.rmax[b]) + 1e-30f;
+            const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C);
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 128);
             for (int u = u0; u < u1; ++u) {
-                mbar_wait(&tmem_full[pa.stage], pa.phase);
+                mbar_wait(&tmem_full[a], aphase);
                 tc_fence_after();
-                const float *nr = sNr + pb.stage * TC_BN;
-                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pa.stage * 256 + a * 128);
                 const int col0 = u * TC_BN;
                 uint32_t va[32], vb[32];
                 tmem_ld32(tbase, va);
@@ -346,24 +380,19 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                 for (int g = 0; g < TC_BN / 32; g += 2) {     // ping-pong: the next 32 columns fly during this step's math
                     tmem_wait32(va);
                     tmem_ld32(tbase + (g + 1) * 32, vb);
-                    filter32(va, nr + g * 32, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci);
+                    filter32(va, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci);
                     tmem_wait32(vb);
                     if (g + 2 < TC_BN / 32) tmem_ld32(tbase + (g + 2) * 32, va);
-                    filter32(vb, nr + (g + 1) * 32, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci);
+                    filter32(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci);
                 }
                 tc_fence_before();
-                mbar_arrive(&tmem_empty[pa.stage]);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_b[pb.stage]);
-                pb.advance(TC_STAGES);
-                pa.advance(2);
+                if (lane == 0) mbar_arrive(&tmem_empty[a]);
+                aphase ^= 1u;
             }
-            const size_t row = (size_t)b * P.Jpad + (size_t)j - (size_t)0;
-            float *ov = P.cand_val + (((size_t)b * P.Jpad + (size_t)rb * TC_BM + a * 128 + trow) * P.S + sp) * TC_T;
-            int *oi = P.cand_idx + (((size_t)b * P.Jpad + (size_t)rb * TC_BM + a * 128 + trow) * P.S + sp) * TC_T;
-            (void)row;
-#pragma unroll
-            for (int t = 0; t < TC_T; ++t) { ov[t] = cv[t]; oi[t] = ci[t]; }
+            const size_t slot = (((size_t)b * P.Jpad + (size_t)j) * P.S + sp) * TC_T;
+            *reinterpret_cast<float4 *>(P.cand_val + slot) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+            *reinterpret_cast<int4 *>(P.cand_idx + slot) = make_int4(ci[0], ci[1], ci[2], ci[3]);
         }
     }
     tc_fence_before();
@@ -372,10 +401,20 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    if (threadIdx.x == 0 && P.dbg) {
+        unsigned long long *d = P.dbg + (size_t)blockIdx.x * 4;
+        d[0] = dbg_s[0]; d[1] = globaltimer_ns(); d[2] = clock64() - dbg_s[1];
+        unsigned long long units = 0;
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+            const int sp = it % P.S;
+            units += (unsigned long long)((long long)(sp + 1) * P.U / P.S - (long long)sp * P.U / P.S);
+        }
+        d[3] = units;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// prep: [B,C,N] (any strides) -> K-major copy [B][N][Cp] * scale, channels C..Cp zero
+// prep 1: [B,C,N] (any strides) -> K-major fp32 copy [B][N][Cp] * scale, channels C..Cp zero
 // ---------------------------------------------------------------------------------------------------------
 __global__ void tc_transpose_kernel(dsir_feat f, int C, int N, int Cp, float scale, float *__restrict__ out) {
     __shared__ float tile[32][33];
@@ -395,16 +434,78 @@ __global__ void tc_transpose_kernel(dsir_feat f, int C, int N, int Cp, float sca
     }
 }
 
-__global__ void tc_pad_norms_kernel(const float *__restrict__ nr, int K, int Kpad, float *__restrict__ nr_pad,
-                                    int *__restrict__ rmax_bits) {
+// per-batch maximum of non-negative norms (atomicMax on the float bits); a NaN compares above every finite value
+__global__ void tc_max_norm_kernel(const float *__restrict__ nrm, int N, int *__restrict__ out_a, int *__restrict__ out_b) {
     const int b = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    float v = TC_PAD_NORM;
     float m = 0.f;
-    if (k < K) { v = nr[(size_t)b * K + k]; m = v; }
-    if (k < Kpad) nr_pad[(size_t)b * Kpad + k] = v;
-    m = warp_max(m);  // NaN-free maxima only; a NaN norm sends its rows to the rescue path via NaN candidates
-    if ((threadIdx.x & 31) == 0) atomicMax(&rmax_bits[b], __float_as_int(m));
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        const float v = nrm[(size_t)b * N + n];
+        m = (v > m || v != v) ? v : m;
+    }
+    int bits = __float_as_int(m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&out_a[b], bits);
+        if (out_b) atomicMax(&out_b[b], bits);
+    }
+}
+
+// sigma_b = 2^-e with 2^e > sqrt(max squared norm of the batch) (1 when the maximum is 0 or not finite)
+__device__ __forceinline__ float tc_sigma(float amax) {
+    if (!(amax > 0.f) || !(amax < INFINITY)) return 1.f;
+    int e = ilogbf(sqrtf(amax)) + 1;
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    return exp2f((float)-e);
+}
+
+// prep 2: K-major fp32 copy (already scaled by `pre`: 1 or -2) -> fp16 tensor-core copy [B][N][64] * sigma, and for the
+// reference side the folded-norm channels [B][Npad][16] = {hi, lo, lolo, 0..} of sigma^2 |r|^2 (TC_PAD_NORM beyond N).
+// One thread = 8 channels of one point.  Block (0,0) also writes the constant source-side norm tile and sigma.
+__global__ void tc_convert_kernel(const float *__restrict__ in32, int N, int Npad, int Cp, const float *__restrict__ amax,
+                                  const float *__restrict__ nrm, __half *__restrict__ out16, __half *__restrict__ aug,
+                                  __half *__restrict__ aug_const, float *__restrict__ scale_out) {
+    const int b = blockIdx.y;
+    const float sigma = tc_sigma(amax[b]);
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = (int)(t >> 3), g = (int)(t & 7);
+    if (n < N) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (g * 8 < Cp) {
+            const float4 *p = reinterpret_cast<const float4 *>(in32 + ((size_t)b * N + n) * Cp + g * 8);
+            const float4 x = p[0], y = p[1];
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+        }
+        __align__(16) __half h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(v[i] * sigma);
+        *reinterpret_cast<uint4 *>(out16 + ((size_t)b * N + n) * TC_CH + g * 8) = *reinterpret_cast<const uint4 *>(h);
+    }
+    if (aug && n < Npad && g < 2) {
+        __align__(16) __half h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(0.f);
+        if (g == 0) {
+            if (n < N) {
+                const float x = nrm[(size_t)b * N + n] * sigma * sigma;
+                const __half hi = __float2half_rn(x);
+                const float r1 = x - __half2float(hi);
+                const __half lo = __float2half_rn(r1);
+                const __half lolo = __float2half_rn(r1 - __half2float(lo));
+                h[0] = hi; h[1] = lo; h[2] = lolo;
+            } else {
+                h[0] = __float2half_rn(TC_PAD_NORM);
+            }
+        }
+        *reinterpret_cast<uint4 *>(aug + ((size_t)b * Npad + n) * TC_AUG + g * 8) = *reinterpret_cast<const uint4 *>(h);
+    }
+    if (aug_const && blockIdx.x == 0 && b == 0) {
+        for (int i = threadIdx.x; i < 128 * TC_AUG; i += blockDim.x)
+            aug_const[i] = __float2half_rn((i % TC_AUG) < 3 ? 1.f : 0.f);
+    }
+    if (scale_out && blockIdx.x == 0 && threadIdx.x == 0) scale_out[b] = sigma;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -414,7 +515,7 @@ struct RefineParams {
     int B, J, K, C, Cp, S, Jpad;
     const float *a_copy;  // [B][J][Cp]
     const float *b_copy;  // [B][K][Cp]  (= -2 r)
-    const float *ns, *nr, *rmax;
+    const float *ns, *nr, *rmax, *scale;
     const float *cand_val;
     const int *cand_idx;
     int64_t *idx;
@@ -450,7 +551,7 @@ __global__ void match_tc_refine_kernel(RefineParams P) {
     const bool valid = k >= 0 && k < P.K && v < 1e38f;
     const float gmin = warp_min(valid ? v : INFINITY);
     const float nsj = P.ns[(size_t)b * P.J + j];
-    const float margin = 8.2e-3f * sqrtf(nsj) * sqrtf(P.rmax[b]) + 1e-30f;
+    const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C);   // candidate values are in scaled units
     const bool take = valid && v <= gmin + margin;
     // saturation: the last slot of some split is still within the margin -> something may have been dropped
     const bool sat = valid && ((lane % TC_T) == TC_T - 1) && take;
@@ -542,14 +643,15 @@ __global__ void match_tc_rescue_finalize_kernel(RefineParams P, const unsigned l
 }
 
 struct TcPlan {
-    int Cp, KB, RB, U, S, Jpad, Kpad;
-    size_t off_a, off_b, off_nrpad, off_rmax, off_cval, off_cidx, off_count, off_rows, off_keys, total;
+    int Cp, NKS, RB, U, S, Jpad, Kpad;
+    size_t off_a, off_b, off_a16, off_b16, off_baug, off_aaug, off_rmax, off_amax, off_scale, off_cval, off_cidx, off_count,
+        off_rows, off_keys, off_dbg, total;
 };
 
 TcPlan make_plan(int B, int C, int J, int K) {
     TcPlan p;
     p.Cp = (C + 31) / 32 * 32;
-    p.KB = p.Cp / 32;
+    p.NKS = (C + 15) / 16;
     p.RB = (J + TC_BM - 1) / TC_BM;
     p.U = (K + TC_BN - 1) / TC_BN;
     p.Jpad = p.RB * TC_BM;
@@ -567,26 +669,32 @@ TcPlan make_plan(int B, int C, int J, int K) {
     auto take = [&](size_t bytes) { size_t o = off; off += ws_block(bytes); return o; };
     p.off_a = take((size_t)B * J * p.Cp * 4);
     p.off_b = take((size_t)B * K * p.Cp * 4);
-    p.off_nrpad = take((size_t)B * p.Kpad * 4);
+    p.off_a16 = take((size_t)B * J * TC_CH * 2);
+    p.off_b16 = take((size_t)B * K * TC_CH * 2);
+    p.off_baug = take((size_t)B * p.Kpad * TC_AUG * 2);
+    p.off_aaug = take((size_t)128 * TC_AUG * 2);
     p.off_rmax = take((size_t)B * 4);
+    p.off_amax = take((size_t)B * 4);
+    p.off_scale = take((size_t)B * 4);
     p.off_cval = take((size_t)B * p.Jpad * S * TC_T * 4);
     p.off_cidx = take((size_t)B * p.Jpad * S * TC_T * 4);
     p.off_count = take(256);
     p.off_rows = take((size_t)B * J * 4);
     p.off_keys = take((size_t)B * J * 8);
+    p.off_dbg = take((size_t)256 * 4 * 8);
     p.total = off + 1024;
     return p;
 }
 
-size_t filter_smem_bytes(int KB) {
-    return 1024 + (size_t)(2 + TC_STAGES) * KB * TILE_BYTES + TC_STAGES * TC_BN * 4 + 256;
+constexpr size_t filter_smem_bytes() {
+    return 1024 + (size_t)(TC_RBS + TC_STAGES) * MAIN_TILE + (size_t)(1 + TC_STAGES) * AUG_TILE + 512;
 }
 
 }  // namespace
 
 bool match_tc_supported(const dsir_feat &fs, const dsir_feat &fr, int B, int C, int J, int K) {
     (void)fs; (void)fr;
-    if (C < 1 || C > 64) return false;
+    if (C < 1 || C > TC_CH) return false;
     if ((long long)B * J >= (1ll << 31) || (long long)B * K >= (1ll << 31)) return false;
     return get_encode_fn() != nullptr;
 }
@@ -597,7 +705,7 @@ bool match_tc_profitable(int B, int C, int J, int K) {
 }
 
 size_t match_tc_workspace_bytes(int B, int C, int J, int K) {
-    if (C > 64) return 0;
+    if (C > TC_CH) return 0;
     return make_plan(B, C, J, K).total;
 }
 
@@ -606,11 +714,14 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     char *base = (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     if (ws == nullptr || (size_t)(base - (char *)ws) + pl.total - 1024 > ws_bytes) return DSIR_ERR_WORKSPACE;
     float *a_copy = (float *)(base + pl.off_a), *b_copy = (float *)(base + pl.off_b);
-    float *nr_pad = (float *)(base + pl.off_nrpad), *rmax = (float *)(base + pl.off_rmax);
+    __half *a16 = (__half *)(base + pl.off_a16), *b16 = (__half *)(base + pl.off_b16);
+    __half *baug = (__half *)(base + pl.off_baug), *aaug = (__half *)(base + pl.off_aaug);
+    float *rmax = (float *)(base + pl.off_rmax), *amax = (float *)(base + pl.off_amax), *scale = (float *)(base + pl.off_scale);
     float *cval = (float *)(base + pl.off_cval);
     int *cidx = (int *)(base + pl.off_cidx), *count = (int *)(base + pl.off_count), *rows = (int *)(base + pl.off_rows);
 
-    DSIR_CUDA_TRY(cudaMemsetAsync(rmax, 0, (size_t)P.B * 4, st));
+    // rmax and amax are adjacent 256-byte blocks: one memset clears both
+    DSIR_CUDA_TRY(cudaMemsetAsync(rmax, 0, pl.off_scale - pl.off_rmax, st));
     DSIR_CUDA_TRY(cudaMemsetAsync(count, 0, 4, st));
     {
         dim3 blk(32, 8);
@@ -619,35 +730,51 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
         DSIR_LAUNCH_CHECK();
         tc_transpose_kernel<<<gb, blk, 0, st>>>(P.fr, P.C, P.K, pl.Cp, -2.0f, b_copy);
         DSIR_LAUNCH_CHECK();
-        dim3 gn(cdiv(pl.Kpad, 256), P.B);
-        tc_pad_norms_kernel<<<gn, 256, 0, st>>>(P.nr, P.K, pl.Kpad, nr_pad, (int *)rmax);
+        tc_max_norm_kernel<<<dim3(std::min(cdiv(P.K, 1024), 64), P.B), 256, 0, st>>>(P.nr, P.K, (int *)rmax, (int *)amax);
+        DSIR_LAUNCH_CHECK();
+        tc_max_norm_kernel<<<dim3(std::min(cdiv(P.J, 1024), 64), P.B), 256, 0, st>>>(P.ns, P.J, (int *)amax, nullptr);
+        DSIR_LAUNCH_CHECK();
+        tc_convert_kernel<<<dim3((unsigned)(((long long)P.J * 8 + 255) / 256), P.B), 256, 0, st>>>(
+            a_copy, P.J, P.J, pl.Cp, amax, nullptr, a16, nullptr, aaug, scale);
+        DSIR_LAUNCH_CHECK();
+        tc_convert_kernel<<<dim3((unsigned)(((long long)pl.Kpad * 8 + 255) / 256), P.B), 256, 0, st>>>(
+            b_copy, P.K, pl.Kpad, pl.Cp, amax, P.nr, b16, baug, nullptr, nullptr);
         DSIR_LAUNCH_CHECK();
     }
-    CUtensorMap mapA, mapB;
-    if (!make_feat_tmap(&mapA, a_copy, P.B, P.J, pl.Cp) || !make_feat_tmap(&mapB, b_copy, P.B, P.K, pl.Cp))
+    CUtensorMap mapA, mapB, mapAaug, mapBaug;
+    if (!make_half_tmap(&mapA, a16, P.B, P.J, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_half_tmap(&mapB, b16, P.B, P.K, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_half_tmap(&mapAaug, aaug, 1, 128, TC_AUG, CU_TENSOR_MAP_SWIZZLE_32B) ||
+        !make_half_tmap(&mapBaug, baug, P.B, pl.Kpad, TC_AUG, CU_TENSOR_MAP_SWIZZLE_32B))
         return DSIR_ERR_UNSUPPORTED;
 
     TcParams T{};
-    T.B = P.B; T.J = P.J; T.K = P.K; T.C = P.C; T.Cp = pl.Cp; T.RB = pl.RB; T.U = pl.U; T.S = pl.S;
-    T.Jpad = pl.Jpad; T.Kpad = pl.Kpad; T.ns = P.ns; T.nr_pad = nr_pad; T.rmax = rmax; T.cand_val = cval; T.cand_idx = cidx;
+    T.B = P.B; T.J = P.J; T.K = P.K; T.C = P.C; T.RB = pl.RB; T.U = pl.U; T.S = pl.S;
+    T.Jpad = pl.Jpad; T.Kpad = pl.Kpad; T.ns = P.ns; T.rmax = rmax; T.scale = scale; T.cand_val = cval; T.cand_idx = cidx;
+    T.dbg = (unsigned long long *)(base + pl.off_dbg);
     const int items = P.B * pl.RB * pl.S;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = items < sms ? items : sms;
-    const size_t smem = filter_smem_bytes(pl.KB);
-    if (pl.KB == 1) {
-        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        match_tc_filter_kernel<1><<<grid, TC_THREADS, smem, st>>>(mapA, mapB, T);
-    } else {
-        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        match_tc_filter_kernel<2><<<grid, TC_THREADS, smem, st>>>(mapA, mapB, T);
+    const int grid = items < sms ? items : (sms > 256 ? 256 : sms);
+    const size_t smem = filter_smem_bytes();
+#define DSIR_TC_LAUNCH(NKS)                                                                                                   \
+    do {                                                                                                                      \
+        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_filter_kernel<NKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        match_tc_filter_kernel<NKS><<<grid, TC_THREADS, smem, st>>>(mapA, mapB, mapAaug, mapBaug, T);                         \
+    } while (0)
+    switch (pl.NKS) {
+        case 1: DSIR_TC_LAUNCH(1); break;
+        case 2: DSIR_TC_LAUNCH(2); break;
+        case 3: DSIR_TC_LAUNCH(3); break;
+        default: DSIR_TC_LAUNCH(4); break;
     }
+#undef DSIR_TC_LAUNCH
     DSIR_LAUNCH_CHECK();
 
     RefineParams R{};
     R.B = P.B; R.J = P.J; R.K = P.K; R.C = P.C; R.Cp = pl.Cp; R.S = pl.S; R.Jpad = pl.Jpad;
-    R.a_copy = a_copy; R.b_copy = b_copy; R.ns = P.ns; R.nr = P.nr; R.rmax = rmax; R.cand_val = cval; R.cand_idx = cidx;
+    R.a_copy = a_copy; R.b_copy = b_copy; R.ns = P.ns; R.nr = P.nr; R.rmax = rmax; R.scale = scale; R.cand_val = cval; R.cand_idx = cidx;
     R.idx = P.idx; R.min_d = P.min_d; R.rescue_count = count; R.rescue_rows = rows;
     R.rescue_keys = (unsigned long long *)(base + pl.off_keys);
     const long long nrows = (long long)P.B * P.J;
@@ -666,6 +793,33 @@ int match_tc_rescued_rows(const void *ws, int B, int C, int J, int K, int *out, 
     const char *base = (const char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     DSIR_CUDA_TRY(cudaMemcpyAsync(out, base + pl.off_count, 4, cudaMemcpyDeviceToHost, st));
     DSIR_CUDA_TRY(cudaStreamSynchronize(st));
+    return DSIR_OK;
+}
+
+// diagnostic: device-side timing of the LAST filter launch on this workspace (synchronises the stream):
+// out[0] = kernel span in ns (last CTA end - first CTA start, %globaltimer), out[1] = mean SM cycles per CTA,
+// out[2] = mean cycles per 512x128 unit (the tensor-pipe floor is 4 x 5 x 64 = 1280)
+int match_tc_filter_timing(const void *ws, int B, int C, int J, int K, double *out, cudaStream_t st) {
+    const TcPlan pl = make_plan(B, C, J, K);
+    const char *base = (const char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    static thread_local unsigned long long h[256 * 4];
+    DSIR_CUDA_TRY(cudaMemcpyAsync(h, base + pl.off_dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    DSIR_CUDA_TRY(cudaStreamSynchronize(st));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int items = B * pl.RB * pl.S;
+    const int grid = items < sms ? items : (sms > 256 ? 256 : sms);
+    unsigned long long t0 = ~0ull, t1 = 0, cyc = 0, units = 0;
+    for (int i = 0; i < grid; ++i) {
+        t0 = h[4 * i] < t0 ? h[4 * i] : t0;
+        t1 = h[4 * i + 1] > t1 ? h[4 * i + 1] : t1;
+        cyc += h[4 * i + 2];
+        units += h[4 * i + 3];
+    }
+    out[0] = (double)(t1 - t0);
+    out[1] = (double)cyc / grid;
+    out[2] = units ? (double)cyc / (double)units : 0.0;
     return DSIR_OK;
 }
 

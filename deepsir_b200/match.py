@@ -84,7 +84,7 @@ def feat_dist(feat_src, feat_ref, metric="sqeuclidean"):
     return _dense(fs, fr, feat_src.shape[0], feat_src.shape[1], feat_src.shape[2], feat_ref.shape[2], code, (a, b), dev)
 
 
-def match_argmin(feat_src, feat_ref, return_min=False, algo=L.MATCH_AUTO, return_rescued=False):
+def match_argmin(feat_src, feat_ref, return_min=False, algo=L.MATCH_AUTO, return_rescued=False, timing=None):
     """The fused replacement of network/model.py:558-569 (chunked match_features_V2 + .min(dim=2)[1]):
     feat_src [B,C,J], feat_ref [B,C,K] -> indexs int64 [B,J]; the [J,K] matrix is never written."""
     assert feat_src.shape[1] == feat_ref.shape[1]
@@ -98,6 +98,12 @@ def match_argmin(feat_src, feat_ref, return_min=False, algo=L.MATCH_AUTO, return
     ws = L.workspace(lib.dsir_match_argmin_workspace_bytes(B, C, J, K, algo), dev)
     L.check(lib.dsir_match_argmin(fs, fr, B, C, J, K, idx.data_ptr(), L.ptr(mind), ws.data_ptr(), ws.numel(), algo,
                                   L.stream_ptr(dev)), "dsir_match_argmin")
+    if timing is not None:  # diagnostic: device-side span/cycles of the tcgen05 filter kernel; forces a stream sync
+        import ctypes
+        t = (ctypes.c_double * 3)()
+        L.check(lib.dsir_match_argmin_filter_timing(ws.data_ptr(), ws.numel(), B, C, J, K, ctypes.addressof(t),
+                                                    L.stream_ptr(dev)), "dsir_match_argmin_filter_timing")
+        timing.update(span_ns=t[0], cycles_per_cta=t[1], cycles_per_unit=t[2])
     if return_rescued:  # diagnostic of the tcgen05 path; forces a stream sync
         import ctypes
         n = ctypes.c_int32(-1)

@@ -96,6 +96,12 @@ int dsir_match_argmin(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, in
 int dsir_match_argmin_rescued_rows(const void *ws, size_t ws_bytes, int B, int C, int J, int K, int32_t *host_out,
                                    dsir_stream_t stream);
 
+/* diagnostic for the tcgen05 path (synchronises `stream`): device-side timing of the LAST filter kernel launched on this
+ * workspace.  host_out[0] = kernel span in ns (%globaltimer, last CTA end - first CTA start), host_out[1] = mean SM
+ * cycles per CTA, host_out[2] = mean SM cycles per 512x128 unit (tensor-pipe floor: 1280).  host_out is HOST memory. */
+int dsir_match_argmin_filter_timing(const void *ws, size_t ws_bytes, int B, int C, int J, int K, double *host_out,
+                                    dsir_stream_t stream);
+
 /* fused distance + affinity + row softmax + soft target (never materialises [J,K]):
  *   a_jk = -beta_b (d_jk - alpha_b) (+ col_bias[b,k])           compute_affinity, matchnet.py:195-208
  *   lse_j = log sum_k exp(a_jk);  w_jk = exp(a_jk - lse_j)      row pass of sinkhorn, matchnet.py:259
