@@ -65,6 +65,8 @@ _SIGS = {
     "dsir_last_cuda_error": (_c.c_char_p, []),
     "dsir_device_check": (_c.c_int, []),
     "dsir_launch_count": (_c.c_uint64, []),
+    "dsir_profile_begin": (_c.c_int, [_c.c_void_p]),
+    "dsir_profile_report": (_c.c_int, [_c.c_void_p, _c.c_size_t]),
     "dsir_knn_workspace_bytes": (_c.c_size_t, [_c.c_int] * 5),
     "dsir_knn_xyz": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                 _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),

@@ -3,6 +3,11 @@
 // allocation, no global state besides a thread-local "last CUDA error" string.
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "kabsch.cuh"
@@ -15,6 +20,22 @@ static thread_local cudaError_t g_last_err = cudaSuccess;
 void set_last_cuda_error(cudaError_t e) { g_last_err = e; }
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- in-situ profiler (diagnostic) ----
+bool g_profile_on = false;
+namespace {
+struct ProfMark { cudaEvent_t ev; const char *file; int line; };
+std::vector<ProfMark> g_marks;
+std::mutex g_prof_mu;
+}  // namespace
+void profile_mark(cudaStream_t st, const char *file, int line) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_marks.size() >= 65536) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    g_marks.push_back({ev, file, line});
+}
 }  // namespace dsir
 
 using namespace dsir;
@@ -49,6 +70,52 @@ int dsir_device_check(void) {
         return DSIR_ERR_NO_DEVICE;
     }
     return major == 10 ? DSIR_OK : DSIR_ERR_NO_DEVICE;
+}
+
+int dsir_profile_begin(dsir_stream_t stream) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto &m : g_marks) cudaEventDestroy(m.ev);
+    g_marks.clear();
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return DSIR_ERR_CUDA;
+    cudaEventRecord(ev, (cudaStream_t)stream);
+    g_marks.push_back({ev, "begin", 0});
+    g_profile_on = true;
+    return DSIR_OK;
+}
+
+int dsir_profile_report(char *buf, size_t buf_bytes) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_profile_on = false;
+    if (!buf || buf_bytes == 0) return DSIR_ERR_BAD_ARG;
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<int, double>> agg;
+    std::vector<std::string> order;
+    double total = 0.0;
+    for (size_t i = 1; i < g_marks.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_marks[i - 1].ev, g_marks[i].ev) != cudaSuccess) { cudaGetLastError(); continue; }
+        const char *f = strrchr(g_marks[i].file, '/');
+        std::string key = std::string(f ? f + 1 : g_marks[i].file) + ":" + std::to_string(g_marks[i].line);
+        if (!agg.count(key)) order.push_back(key);
+        agg[key].first += 1;
+        agg[key].second += ms * 1e3;
+        total += ms * 1e3;
+    }
+    std::string out;
+    char line[256];
+    for (auto &k : order) {
+        snprintf(line, sizeof line, "%-28s launches %5d  total %10.1f us  %5.1f%%\n", k.c_str(), agg[k].first, agg[k].second,
+                 total > 0 ? 100.0 * agg[k].second / total : 0.0);
+        out += line;
+    }
+    snprintf(line, sizeof line, "%-28s launches %5d  total %10.1f us\n", "TOTAL", (int)g_marks.size() - 1, total);
+    out += line;
+    for (auto &m : g_marks) cudaEventDestroy(m.ev);
+    g_marks.clear();
+    strncpy(buf, out.c_str(), buf_bytes - 1);
+    buf[buf_bytes - 1] = 0;
+    return DSIR_OK;
 }
 
 /* ------------------------------------------------------------------ KNN ------------------------ */
@@ -311,8 +378,6 @@ int dsir_match_argmin(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, in
     float *nr = W.take<float>((size_t)B * K);
     if (!W.ok()) return DSIR_ERR_WORKSPACE;
     int rc;
-    if ((rc = launch_sqnorm(fs, B, C, J, ns, st))) return rc;
-    if ((rc = launch_sqnorm(fr, B, C, K, nr, st))) return rc;
     MatchParams P{};
     P.fs = fs; P.fr = fr; P.B = B; P.C = C; P.J = J; P.K = K; P.ns = ns; P.nr = nr;
     P.idx = idx; P.min_d = min_d;
@@ -320,8 +385,10 @@ int dsir_match_argmin(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, in
     if (algo == DSIR_MATCH_TC && !tc_ok) return DSIR_ERR_UNSUPPORTED;
     if (algo == DSIR_MATCH_TC || (algo == DSIR_MATCH_AUTO && tc_ok && match_tc_profitable(B, C, J, K))) {
         size_t used = W.off;
-        return launch_match_tc(P, (char *)ws + used, ws_bytes - used, st);
+        return launch_match_tc(P, (char *)ws + used, ws_bytes - used, st);   // fills ns / nr itself (norms + maxima fused)
     }
+    if ((rc = launch_sqnorm(fs, B, C, J, ns, st))) return rc;
+    if ((rc = launch_sqnorm(fr, B, C, K, nr, st))) return rc;
     return launch_match_fp32(P, MATCH_MODE_ARGMIN, st);
 }
 

@@ -20,10 +20,17 @@ void count_launch();  // every kernel this library enqueues is counted (dsir_lau
         }                                                 \
     } while (0)
 
-#define DSIR_LAUNCH_CHECK()                 \
-    do {                                    \
-        ::dsir::count_launch();             \
-        DSIR_CUDA_TRY(cudaGetLastError());  \
+// In-situ profiling (diagnostic, off by default): when enabled through dsir_profile_begin(), every launch site records
+// a CUDA event on its stream right after the launch; dsir_profile_report() turns consecutive events into per-site times.
+extern bool g_profile_on;
+void profile_mark(cudaStream_t st, const char *file, int line);
+
+// every launch site has the stream in a local named `st`
+#define DSIR_LAUNCH_CHECK()                                                  \
+    do {                                                                     \
+        ::dsir::count_launch();                                              \
+        DSIR_CUDA_TRY(cudaGetLastError());                                   \
+        if (::dsir::g_profile_on) ::dsir::profile_mark(st, __FILE__, __LINE__); \
     } while (0)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -21,6 +21,7 @@ struct MatchParams {
 enum { MATCH_MODE_ARGMIN = 0, MATCH_MODE_DENSE = 1, MATCH_MODE_SOFT = 2 };
 
 int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, cudaStream_t st);
+int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, int *max_a, int *max_b, cudaStream_t st);
 int launch_match_fp32(const MatchParams &P, int mode, cudaStream_t st);
 
 // the exact fp32 distance every path agrees on:  ((-2*dot) + ns) + nr,  dot = fma chain over c ascending

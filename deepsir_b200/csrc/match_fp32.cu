@@ -15,24 +15,39 @@ namespace dsir {
 constexpr int TM = 128, TN = 128, CK = 16, MT = 256;
 constexpr int PITCH = TM + 4;
 
-__global__ void sqnorm_kernel(dsir_feat f, int C, int N, float *__restrict__ out) {
+// squared norms (fma chain over channels ascending) and, optionally, the per-batch maximum (atomicMax on the float bits
+// of the non-negative norms; a NaN compares above every finite value) into max_a[b] and max_b[b]
+__global__ void sqnorm_kernel(dsir_feat f, int C, int N, float *__restrict__ out, int *__restrict__ max_a, int *__restrict__ max_b) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     int b = blockIdx.y;
-    if (n >= N) return;
-    const float *p = f.ptr + (size_t)b * f.batch_stride + (size_t)n * f.point_stride;
     float acc = 0.f;
-    for (int c = 0; c < C; ++c) {
-        float v = p[(size_t)c * f.chan_stride];
-        acc = __fmaf_rn(v, v, acc);
+    if (n < N) {
+        const float *p = f.ptr + (size_t)b * f.batch_stride + (size_t)n * f.point_stride;
+        for (int c = 0; c < C; ++c) {
+            float v = p[(size_t)c * f.chan_stride];
+            acc = __fmaf_rn(v, v, acc);
+        }
+        out[(size_t)b * N + n] = acc;
     }
-    out[(size_t)b * N + n] = acc;
+    if (max_a) {
+        int bits = __float_as_int(acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+        if ((threadIdx.x & 31) == 0) {
+            atomicMax(&max_a[b], bits);
+            if (max_b) atomicMax(&max_b[b], bits);
+        }
+    }
 }
 
-int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, cudaStream_t st) {
+int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, int *max_a, int *max_b, cudaStream_t st) {
     dim3 grid(cdiv(N, 256), B);
-    sqnorm_kernel<<<grid, 256, 0, st>>>(f, C, N, out);
+    sqnorm_kernel<<<grid, 256, 0, st>>>(f, C, N, out, max_a, max_b);
     DSIR_LAUNCH_CHECK();
     return DSIR_OK;
+}
+int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, cudaStream_t st) {
+    return launch_sqnorm(f, B, C, N, out, nullptr, nullptr, st);
 }
 
 // INNER: 0 = dot product, 1 = sum of squared differences, 2 = sum of absolute differences

@@ -44,8 +44,11 @@ constexpr int TC_RBS = 4;                     // 128-row blocks (accumulators) p
 constexpr int TC_BM = 128 * TC_RBS;           // source rows per work item
 constexpr int TC_BN = 128;                    // reference rows per unit (one N=128 MMA)
 constexpr int TC_STAGES = 5;                  // B ring depth
-constexpr int TC_EPI_WARPS = 4 * TC_RBS;      // warp 4+4i+q drains TMEM lane quadrant q of accumulator i
-constexpr int TC_THREADS = (4 + TC_EPI_WARPS) * 32;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle
+constexpr int TC_EPI_WARPS = 4 * TC_RBS;      // warp 4i+q drains TMEM lane quadrant q of accumulator i
+// The issue arbiter of an SM sub-partition prefers the HIGHEST warp id, so the three control warps sit above the 16
+// epilogue warps: the MMA issuer is never starved by epilogue math.
+constexpr int TC_WARP_TMA = TC_EPI_WARPS, TC_WARP_MMA = TC_EPI_WARPS + 1, TC_WARP_ALLOC = TC_EPI_WARPS + 2;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 3) * 32;
 constexpr int TC_MAX_SPLIT = 8;
 constexpr int TC_CH = 64;                     // fp16 channels per point in the tensor-core copy (one 128-byte swizzle row)
 constexpr int TC_AUG = 16;                    // folded-norm channels (one K=16 MMA)
@@ -139,11 +142,6 @@ __device__ __forceinline__ void tmem_wait32(uint32_t (&r)[32]) {
                  :
                  : "memory");
 }
-__device__ __forceinline__ float tmem_ld1_sync(uint32_t taddr) {
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
-    return __uint_as_float(r);
-}
 __device__ __forceinline__ float fmin3(float a, float b, float c) {   // FMNMX3 (sm_100+)
     float d;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -206,35 +204,66 @@ __device__ __forceinline__ void cand_insert(float (&cv)[T], int (&ci)[T], float 
     }
 }
 
-// 32 accumulator columns of one row.  Fast path: a 3-input-min tree (15 FMNMX3 + 1 FMNMX) and ONE vote.  Whenever
-// some lane of the warp sees a value within `margin` of its running minimum, the slow path re-reads exactly the
-// flagged columns from TMEM one at a time, so the hot loop stays small and carries no per-element branches.
+// One observed value enters a row's candidate list (sorted ascending, T entries).  The common event is a CLEAR
+// record low (x below the current minimum by more than the margin): every older entry is then outside the margin
+// of the new minimum and the list collapses to {x}.  Anything else (a near tie) takes the sorted insert.
+__device__ __forceinline__ void cand_update(float (&cv)[TC_T], int (&ci)[TC_T], float x, int col, float margin, float &thr) {
+    if (x < cv[0] - margin) {
+        cv[0] = x; ci[0] = col;
+#pragma unroll
+        for (int t = 1; t < TC_T; ++t) cv[t] = INFINITY;
+    } else {
+        cand_insert<TC_T>(cv, ci, x, col);
+    }
+    thr = cv[0] + margin;
+}
+
+__device__ __forceinline__ void tmem_ld4_sync(uint32_t taddr, float (&x)[4]) {
+    uint32_t r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+    x[0] = __uint_as_float(r0); x[1] = __uint_as_float(r1); x[2] = __uint_as_float(r2); x[3] = __uint_as_float(r3);
+}
+
+// 32 accumulator columns of one row.  Fast path: minima of the 8 aligned column quads, a 3-input-min tree over them
+// (20 FMNMX/FMNMX3) and ONE vote.  Whenever some lane of the warp sees a value within `margin` of its running minimum,
+// the slow path re-reads only the flagged QUADS from TMEM (four values in registers with static indices) and updates
+// the candidate list of the lanes concerned; the hot loop carries no per-element branches.
 __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint32_t taddr, float margin, float &thr,
                                          float (&cv)[TC_T], int (&ci)[TC_T]) {
 #define F(i) __uint_as_float(v[i])
-    const float a0 = fmin3(F(0), F(1), F(2)), a1 = fmin3(F(3), F(4), F(5)), a2 = fmin3(F(6), F(7), F(8));
-    const float a3 = fmin3(F(9), F(10), F(11)), a4 = fmin3(F(12), F(13), F(14)), a5 = fmin3(F(15), F(16), F(17));
-    const float a6 = fmin3(F(18), F(19), F(20)), a7 = fmin3(F(21), F(22), F(23)), a8 = fmin3(F(24), F(25), F(26));
-    const float a9 = fmin3(F(27), F(28), F(29));
-    const float b0 = fmin3(a0, a1, a2), b1 = fmin3(a3, a4, a5), b2 = fmin3(a6, a7, a8), b3 = fmin3(a9, F(30), F(31));
-    const float mm = fminf(fmin3(b0, b1, b2), b3);
-    if (__any_sync(0xffffffffu, mm < thr)) {
-        unsigned mask = 0;
+    float q[8];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) mask |= (F(e) < thr) ? (1u << e) : 0u;
-        unsigned um = __reduce_or_sync(0xffffffffu, mask);
+    for (int g = 0; g < 8; ++g) q[g] = fminf(fmin3(F(4 * g), F(4 * g + 1), F(4 * g + 2)), F(4 * g + 3));
+#undef F
+    const float mm = fmin3(fmin3(q[0], q[1], q[2]), fmin3(q[3], q[4], q[5]), fminf(q[6], q[7]));
+    if (__any_sync(0xffffffffu, mm < thr)) {
+        unsigned qm = 0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) qm |= (q[g] < thr) ? (1u << g) : 0u;
+        unsigned um = __reduce_or_sync(0xffffffffu, qm);
 #pragma unroll 1
         while (um) {
-            const int e = __ffs(um) - 1;
+            const int g = __ffs(um) - 1;
             um &= um - 1;
-            const float xe = tmem_ld1_sync(taddr + e);   // bit-identical to v[e]
-            if (xe < thr) {
-                cand_insert<TC_T>(cv, ci, xe, col0 + e);
-                thr = cv[0] + margin;
+            float x[4];
+            tmem_ld4_sync(taddr + 4 * g, x);   // bit-identical to v[4g .. 4g+3]
+            if ((qm >> g) & 1u) {
+                const float lo01 = fminf(x[0], x[1]), lo23 = fminf(x[2], x[3]);
+                const float m = fminf(lo01, lo23);
+                const int i = x[0] == m ? 0 : (x[1] == m ? 1 : (x[2] == m ? 2 : 3));   // first index of the quad minimum
+                cand_update(cv, ci, m, col0 + 4 * g + i, margin, thr);
+                // any OTHER element of the quad still below the (updated) threshold is a near tie: rare
+                const float hi01 = fmaxf(x[0], x[1]), hi23 = fmaxf(x[2], x[3]);
+                const float second = fminf(fmaxf(lo01, lo23), lo01 <= lo23 ? hi01 : hi23);
+                if (second < thr) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (e != i && x[e] < thr) cand_update(cv, ci, x[e], col0 + 4 * g + e, margin, thr);
+                }
             }
         }
     }
-#undef F
 }
 
 struct TcParams {
@@ -272,7 +301,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
     unsigned long long *dbg_s = (unsigned long long *)(tmem_slot + 2);   // start time / start clock, parked in smem
     if (threadIdx.x == 0) { dbg_s[0] = globaltimer_ns(); dbg_s[1] = clock64(); }
 
-    if (warp == 0 && lane == 0) {
+    if (warp == TC_WARP_TMA && lane == 0) {
         prefetch_tmap(&mapA);
         prefetch_tmap(&mapB);
         prefetch_tmap(&mapAaug);
@@ -283,13 +312,13 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
         mbar_init(empty_a, 1);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == TC_WARP_ALLOC) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == TC_WARP_TMA) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
             PipeState pb{0, 0};
@@ -315,7 +344,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                 iphase ^= 1u;
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == TC_WARP_MMA) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             PipeState pb{0, 0};
@@ -352,10 +381,10 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                 iphase ^= 1u;
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < TC_EPI_WARPS) {
         // =========================== epilogue: TMEM -> registers -> candidate lists ===========================
         const int q = warp & 3;                       // TMEM lane quadrant of this warp
-        const int a = (warp - 4) >> 2;                // accumulator (row block) of this warp
+        const int a = warp >> 2;                      // accumulator (row block) of this warp
         const int trow = q * 32 + lane;               // row inside the 128-row block
         uint32_t aphase = 0;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
@@ -397,7 +426,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == TC_WARP_ALLOC) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -413,44 +442,6 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// prep 1: [B,C,N] (any strides) -> K-major fp32 copy [B][N][Cp] * scale, channels C..Cp zero
-// ---------------------------------------------------------------------------------------------------------
-__global__ void tc_transpose_kernel(dsir_feat f, int C, int N, int Cp, float scale, float *__restrict__ out) {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z;
-    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const float *src = f.ptr + (size_t)b * f.batch_stride;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // i: channel, threadIdx.x: point
-        int c = c0 + i, n = n0 + threadIdx.x;
-        float v = 0.f;
-        if (c < C && n < N) v = src[(size_t)c * f.chan_stride + (size_t)n * f.point_stride];
-        tile[i][threadIdx.x] = v * scale;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // i: point, threadIdx.x: channel
-        int n = n0 + i, c = c0 + threadIdx.x;
-        if (n < N && c < Cp) out[((size_t)b * N + n) * Cp + c] = tile[threadIdx.x][i];
-    }
-}
-
-// per-batch maximum of non-negative norms (atomicMax on the float bits); a NaN compares above every finite value
-__global__ void tc_max_norm_kernel(const float *__restrict__ nrm, int N, int *__restrict__ out_a, int *__restrict__ out_b) {
-    const int b = blockIdx.y;
-    float m = 0.f;
-    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
-        const float v = nrm[(size_t)b * N + n];
-        m = (v > m || v != v) ? v : m;
-    }
-    int bits = __float_as_int(m);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(&out_a[b], bits);
-        if (out_b) atomicMax(&out_b[b], bits);
-    }
-}
-
 // sigma_b = 2^-e with 2^e > sqrt(max squared norm of the batch) (1 when the maximum is 0 or not finite)
 __device__ __forceinline__ float tc_sigma(float amax) {
     if (!(amax > 0.f) || !(amax < INFINITY)) return 1.f;
@@ -459,34 +450,43 @@ __device__ __forceinline__ float tc_sigma(float amax) {
     return exp2f((float)-e);
 }
 
-// prep 2: K-major fp32 copy (already scaled by `pre`: 1 or -2) -> fp16 tensor-core copy [B][N][64] * sigma, and for the
-// reference side the folded-norm channels [B][Npad][16] = {hi, lo, lolo, 0..} of sigma^2 |r|^2 (TC_PAD_NORM beyond N).
-// One thread = 8 channels of one point.  Block (0,0) also writes the constant source-side norm tile and sigma.
-__global__ void tc_convert_kernel(const float *__restrict__ in32, int N, int Npad, int Cp, const float *__restrict__ amax,
-                                  const float *__restrict__ nrm, __half *__restrict__ out16, __half *__restrict__ aug,
-                                  __half *__restrict__ aug_const, float *__restrict__ scale_out) {
+// prep: [B,C,N] fp32 (any strides) -> fp16 tensor-core copy [B][N][64] = mul * sigma * f (point-major, channels C..63
+// zero), and for the reference side the folded-norm channels [B][Npad][16] = {hi, lo, lolo, 0..} of sigma^2 |r|^2
+// (TC_PAD_NORM beyond N).  One block = 32 points x 64 channels through a shared-memory transpose.  Block (0,0) also
+// writes the constant source-side norm tile; the first block of every batch writes sigma.
+__global__ __launch_bounds__(256) void tc_prep_kernel(dsir_feat f, int C, int N, int Npad, const float *__restrict__ amax,
+                                                      const float *__restrict__ nrm, float mul, __half *__restrict__ out16,
+                                                      __half *__restrict__ aug, __half *__restrict__ aug_const,
+                                                      float *__restrict__ scale_out) {
+    __shared__ float tile[TC_CH][33];
     const int b = blockIdx.y;
+    const int n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float sigma = tc_sigma(amax[b]);
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = (int)(t >> 3), g = (int)(t & 7);
-    if (n < N) {
-        float v[8];
+    const float *src = f.ptr + (size_t)b * f.batch_stride;
+    if (n0 < N) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        if (g * 8 < Cp) {
-            const float4 *p = reinterpret_cast<const float4 *>(in32 + ((size_t)b * N + n) * Cp + g * 8);
-            const float4 x = p[0], y = p[1];
-            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+        for (int c = ty; c < TC_CH; c += 8) {   // c: channel, tx: point (coalesced when the point stride is 1)
+            const int n = n0 + tx;
+            float v = 0.f;
+            if (c < C && n < N) v = src[(size_t)c * f.chan_stride + (size_t)n * f.point_stride];
+            tile[c][tx] = v;
         }
+    }
+    __syncthreads();
+    const int i = threadIdx.x >> 3, g = threadIdx.x & 7;   // point inside the block, group of 8 channels
+    const int n = n0 + i;
+    if (n < N) {
+        const float m = mul * sigma;   // power of two (times -2): the scaling is exact
         __align__(16) __half h[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(v[i] * sigma);
+        for (int k = 0; k < 8; ++k) h[k] = __float2half_rn(tile[8 * g + k][i] * m);
         *reinterpret_cast<uint4 *>(out16 + ((size_t)b * N + n) * TC_CH + g * 8) = *reinterpret_cast<const uint4 *>(h);
     }
     if (aug && n < Npad && g < 2) {
         __align__(16) __half h[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(0.f);
+        for (int k = 0; k < 8; ++k) h[k] = __float2half_rn(0.f);
         if (g == 0) {
             if (n < N) {
                 const float x = nrm[(size_t)b * N + n] * sigma * sigma;
@@ -502,19 +502,21 @@ __global__ void tc_convert_kernel(const float *__restrict__ in32, int N, int Npa
         *reinterpret_cast<uint4 *>(aug + ((size_t)b * Npad + n) * TC_AUG + g * 8) = *reinterpret_cast<const uint4 *>(h);
     }
     if (aug_const && blockIdx.x == 0 && b == 0) {
-        for (int i = threadIdx.x; i < 128 * TC_AUG; i += blockDim.x)
-            aug_const[i] = __float2half_rn((i % TC_AUG) < 3 ? 1.f : 0.f);
+        for (int t = threadIdx.x; t < 128 * TC_AUG; t += blockDim.x)
+            aug_const[t] = __float2half_rn((t % TC_AUG) < 3 ? 1.f : 0.f);
     }
     if (scale_out && blockIdx.x == 0 && threadIdx.x == 0) scale_out[b] = sigma;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// refine: one warp per source row, one lane per candidate
+// refine: one thread per source row.  Candidates within margin of the row's approximate minimum are the only
+// columns that can hold the exact fp32 minimum.  A single such candidate IS the answer (no arithmetic needed unless
+// the caller wants the distance); several are re-scored with the exact fp32 op order of match_fp32.cu, reading the
+// caller's own feature tensors (consecutive rows -> coalesced source reads; the reference side is a gather).
 // ---------------------------------------------------------------------------------------------------------
 struct RefineParams {
-    int B, J, K, C, Cp, S, Jpad;
-    const float *a_copy;  // [B][J][Cp]
-    const float *b_copy;  // [B][K][Cp]  (= -2 r)
+    int B, J, K, C, S, Jpad;
+    dsir_feat fs, fr;
     const float *ns, *nr, *rmax, *scale;
     const float *cand_val;
     const int *cand_idx;
@@ -525,60 +527,81 @@ struct RefineParams {
     unsigned long long *rescue_keys;  // [B*J] (ordered distance bits << 32) | index, atomicMin target
 };
 
-__device__ __forceinline__ float exact_dist(const float *__restrict__ srow, const float *__restrict__ brow, int C, float nsj, float nrk) {
+// dot = fma chain over channels ascending, d = ((-2 dot) + ns) + nr: bit-identical to match_fp32_kernel
+__device__ __forceinline__ float exact_dist(const float *__restrict__ sp, int64_t s_cs, const float *__restrict__ rp, int64_t r_cs,
+                                            int C, float nsj, float nrk) {
     float dot = 0.f;
-    for (int c = 0; c < C; c += 4) {  // Cp is a multiple of 32 and channels >= C are zero: fma(0,0,dot) == dot
-        float4 s4 = *reinterpret_cast<const float4 *>(srow + c);
-        float4 b4 = *reinterpret_cast<const float4 *>(brow + c);
-        dot = __fmaf_rn(s4.x, __fmul_rn(-0.5f, b4.x), dot);
-        dot = __fmaf_rn(s4.y, __fmul_rn(-0.5f, b4.y), dot);
-        dot = __fmaf_rn(s4.z, __fmul_rn(-0.5f, b4.z), dot);
-        dot = __fmaf_rn(s4.w, __fmul_rn(-0.5f, b4.w), dot);
-    }
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) dot = __fmaf_rn(sp[(size_t)c * s_cs], rp[(size_t)c * r_cs], dot);
     return l2_from_dot(dot, nsj, nrk);
 }
 
-__global__ void match_tc_refine_kernel(RefineParams P) {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ __launch_bounds__(256) void match_tc_refine_kernel(RefineParams P) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (long long)P.B * P.J) return;
     const int b = (int)(row / P.J), j = (int)(row % P.J);
     const int ncand = P.S * TC_T;
-    const size_t cbase = ((size_t)b * P.Jpad + j) * ncand;
-    float v = INFINITY;
-    int k = -1;
-    if (lane < ncand) { v = P.cand_val[cbase + lane]; k = P.cand_idx[cbase + lane]; }
-    const bool valid = k >= 0 && k < P.K && v < 1e38f;
-    const float gmin = warp_min(valid ? v : INFINITY);
+    const float4 *cvp = reinterpret_cast<const float4 *>(P.cand_val + ((size_t)b * P.Jpad + j) * ncand);
+    const int4 *cip = reinterpret_cast<const int4 *>(P.cand_idx + ((size_t)b * P.Jpad + j) * ncand);
     const float nsj = P.ns[(size_t)b * P.J + j];
     const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C);   // candidate values are in scaled units
-    const bool take = valid && v <= gmin + margin;
-    // saturation: the last slot of some split is still within the margin -> something may have been dropped
-    const bool sat = valid && ((lane % TC_T) == TC_T - 1) && take;
-    const unsigned any_take = __ballot_sync(0xffffffffu, take);
-    const unsigned any_sat = __ballot_sync(0xffffffffu, sat);
-    float d = INFINITY;
-    int kk = 0x7fffffff;
-    if (take) {
-        d = exact_dist(P.a_copy + ((size_t)b * P.J + j) * P.Cp, P.b_copy + ((size_t)b * P.K + k) * P.Cp, P.Cp, nsj,
-                       P.nr[(size_t)b * P.K + k]);
-        kk = k;
-    }
+    // pass 1: approximate row minimum over the valid candidates
+    float gmin = INFINITY;
+    for (int s = 0; s < P.S; ++s) {
+        const float4 v = cvp[s];
+        const int4 k = cip[s];
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        const int kk[4] = {k.x, k.y, k.z, k.w};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        float d2 = __shfl_xor_sync(0xffffffffu, d, o);
-        int k2 = __shfl_xor_sync(0xffffffffu, kk, o);
-        if (d2 < d || (d2 == d && k2 < kk)) { d = d2; kk = k2; }
+        for (int t = 0; t < TC_T; ++t)
+            if (kk[t] >= 0 && kk[t] < P.K && vv[t] < 1e38f) gmin = fminf(gmin, vv[t]);
     }
-    const bool rescue = (any_take == 0u) || (any_sat != 0u) || !(d < INFINITY);
-    if (lane == 0) {
-        P.idx[row] = rescue ? 0 : (int64_t)kk;
-        if (P.min_d) P.min_d[row] = d;
-        if (rescue) {
-            int pos = atomicAdd(P.rescue_count, 1);
-            P.rescue_rows[pos] = (int)row;
-            P.rescue_keys[pos] = ~0ull;
+    // pass 2: who qualifies; a split whose LAST slot still qualifies may have dropped something -> rescue
+    const float lim = gmin + margin;
+    int ntake = 0, ksingle = 0;
+    bool sat = false;
+    for (int s = 0; s < P.S; ++s) {
+        const float4 v = cvp[s];
+        const int4 k = cip[s];
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        const int kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+        for (int t = 0; t < TC_T; ++t) {
+            const bool take = kk[t] >= 0 && kk[t] < P.K && vv[t] < 1e38f && vv[t] <= lim;
+            if (take) { ++ntake; ksingle = kk[t]; sat = sat || (t == TC_T - 1); }
         }
+    }
+    bool rescue = (ntake == 0) || sat;
+    float d = INFINITY;
+    int kbest = 0x7fffffff;
+    if (!rescue) {
+        if (ntake == 1 && P.min_d == nullptr) {
+            kbest = ksingle;
+        } else {
+            const float *sp = P.fs.ptr + (size_t)b * P.fs.batch_stride + (size_t)j * P.fs.point_stride;
+            const float *rb = P.fr.ptr + (size_t)b * P.fr.batch_stride;
+            for (int s = 0; s < P.S; ++s) {
+                const float4 v = cvp[s];
+                const int4 k = cip[s];
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+                const int kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll 1
+                for (int t = 0; t < TC_T; ++t) {
+                    if (!(kk[t] >= 0 && kk[t] < P.K && vv[t] < 1e38f && vv[t] <= lim)) continue;
+                    const float dd = exact_dist(sp, P.fs.chan_stride, rb + (size_t)kk[t] * P.fr.point_stride, P.fr.chan_stride,
+                                                P.C, nsj, P.nr[(size_t)b * P.K + kk[t]]);
+                    if (dd < d || (dd == d && kk[t] < kbest)) { d = dd; kbest = kk[t]; }
+                }
+            }
+            rescue = !(d < INFINITY);   // every qualifying distance was NaN/inf: let the exhaustive path decide
+        }
+    }
+    P.idx[row] = rescue ? 0 : (int64_t)kbest;
+    if (P.min_d) P.min_d[row] = d;
+    if (rescue) {
+        const int pos = atomicAdd(P.rescue_count, 1);
+        P.rescue_rows[pos] = (int)row;
+        P.rescue_keys[pos] = ~0ull;
     }
 }
 
@@ -593,9 +616,10 @@ __device__ __forceinline__ float float_from_order_bits(unsigned int u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 constexpr int RESCUE_CHUNK = 2048;
+constexpr int RESCUE_MAXC = 64;
 
 __global__ __launch_bounds__(256) void match_tc_rescue_kernel(RefineParams P, unsigned long long *keys) {
-    __shared__ float srow[128];
+    __shared__ float srow[RESCUE_MAXC];
     __shared__ unsigned long long red[8];
     const int count = *P.rescue_count;
     const int nchunk = (P.K + RESCUE_CHUNK - 1) / RESCUE_CHUNK;
@@ -605,13 +629,16 @@ __global__ __launch_bounds__(256) void match_tc_rescue_kernel(RefineParams P, un
         const int row = P.rescue_rows[i];
         const int b = row / P.J, j = row % P.J;
         __syncthreads();
-        for (int c = threadIdx.x; c < P.Cp; c += blockDim.x) srow[c] = P.a_copy[((size_t)b * P.J + j) * P.Cp + c];
+        for (int c = threadIdx.x; c < P.C; c += blockDim.x)
+            srow[c] = P.fs.ptr[(size_t)b * P.fs.batch_stride + (size_t)c * P.fs.chan_stride + (size_t)j * P.fs.point_stride];
         __syncthreads();
         const float nsj = P.ns[(size_t)b * P.J + j];
+        const float *rb = P.fr.ptr + (size_t)b * P.fr.batch_stride;
         unsigned long long best = ~0ull;
         const int kend = min(P.K, (ch + 1) * RESCUE_CHUNK);
-        for (int k = ch * RESCUE_CHUNK + threadIdx.x; k < kend; k += blockDim.x) {
-            float d = exact_dist(srow, P.b_copy + ((size_t)b * P.K + k) * P.Cp, P.Cp, nsj, P.nr[(size_t)b * P.K + k]);
+        for (int k = ch * RESCUE_CHUNK + threadIdx.x; k < kend; k += blockDim.x) {   // coalesced over k when point stride is 1
+            const float d = exact_dist(srow, 1, rb + (size_t)k * P.fr.point_stride, P.fr.chan_stride, P.C, nsj,
+                                       P.nr[(size_t)b * P.K + k]);
             if (d == d) {
                 unsigned long long key = ((unsigned long long)float_order_bits(d) << 32) | (unsigned int)k;
                 best = key < best ? key : best;
@@ -643,14 +670,13 @@ __global__ void match_tc_rescue_finalize_kernel(RefineParams P, const unsigned l
 }
 
 struct TcPlan {
-    int Cp, NKS, RB, U, S, Jpad, Kpad;
-    size_t off_a, off_b, off_a16, off_b16, off_baug, off_aaug, off_rmax, off_amax, off_scale, off_cval, off_cidx, off_count,
+    int NKS, RB, U, S, Jpad, Kpad;
+    size_t off_a16, off_b16, off_baug, off_aaug, off_rmax, off_amax, off_scale, off_cval, off_cidx, off_count,
         off_rows, off_keys, off_dbg, total;
 };
 
 TcPlan make_plan(int B, int C, int J, int K) {
     TcPlan p;
-    p.Cp = (C + 31) / 32 * 32;
     p.NKS = (C + 15) / 16;
     p.RB = (J + TC_BM - 1) / TC_BM;
     p.U = (K + TC_BN - 1) / TC_BN;
@@ -667,8 +693,6 @@ TcPlan make_plan(int B, int C, int J, int K) {
     p.S = S;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += ws_block(bytes); return o; };
-    p.off_a = take((size_t)B * J * p.Cp * 4);
-    p.off_b = take((size_t)B * K * p.Cp * 4);
     p.off_a16 = take((size_t)B * J * TC_CH * 2);
     p.off_b16 = take((size_t)B * K * TC_CH * 2);
     p.off_baug = take((size_t)B * p.Kpad * TC_AUG * 2);
@@ -713,7 +737,6 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     const TcPlan pl = make_plan(P.B, P.C, P.J, P.K);
     char *base = (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     if (ws == nullptr || (size_t)(base - (char *)ws) + pl.total - 1024 > ws_bytes) return DSIR_ERR_WORKSPACE;
-    float *a_copy = (float *)(base + pl.off_a), *b_copy = (float *)(base + pl.off_b);
     __half *a16 = (__half *)(base + pl.off_a16), *b16 = (__half *)(base + pl.off_b16);
     __half *baug = (__half *)(base + pl.off_baug), *aaug = (__half *)(base + pl.off_aaug);
     float *rmax = (float *)(base + pl.off_rmax), *amax = (float *)(base + pl.off_amax), *scale = (float *)(base + pl.off_scale);
@@ -723,24 +746,14 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     // rmax and amax are adjacent 256-byte blocks: one memset clears both
     DSIR_CUDA_TRY(cudaMemsetAsync(rmax, 0, pl.off_scale - pl.off_rmax, st));
     DSIR_CUDA_TRY(cudaMemsetAsync(count, 0, 4, st));
-    {
-        dim3 blk(32, 8);
-        dim3 ga(cdiv(P.J, 32), pl.Cp / 32, P.B), gb(cdiv(P.K, 32), pl.Cp / 32, P.B);
-        tc_transpose_kernel<<<ga, blk, 0, st>>>(P.fs, P.C, P.J, pl.Cp, 1.0f, a_copy);
-        DSIR_LAUNCH_CHECK();
-        tc_transpose_kernel<<<gb, blk, 0, st>>>(P.fr, P.C, P.K, pl.Cp, -2.0f, b_copy);
-        DSIR_LAUNCH_CHECK();
-        tc_max_norm_kernel<<<dim3(std::min(cdiv(P.K, 1024), 64), P.B), 256, 0, st>>>(P.nr, P.K, (int *)rmax, (int *)amax);
-        DSIR_LAUNCH_CHECK();
-        tc_max_norm_kernel<<<dim3(std::min(cdiv(P.J, 1024), 64), P.B), 256, 0, st>>>(P.ns, P.J, (int *)amax, nullptr);
-        DSIR_LAUNCH_CHECK();
-        tc_convert_kernel<<<dim3((unsigned)(((long long)P.J * 8 + 255) / 256), P.B), 256, 0, st>>>(
-            a_copy, P.J, P.J, pl.Cp, amax, nullptr, a16, nullptr, aaug, scale);
-        DSIR_LAUNCH_CHECK();
-        tc_convert_kernel<<<dim3((unsigned)(((long long)pl.Kpad * 8 + 255) / 256), P.B), 256, 0, st>>>(
-            b_copy, P.K, pl.Kpad, pl.Cp, amax, P.nr, b16, baug, nullptr, nullptr);
-        DSIR_LAUNCH_CHECK();
-    }
+    int rc;
+    // exact squared norms (fma chains, shared with the fp32 kernel) + per-batch maxima for sigma and the margin
+    if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, const_cast<float *>(P.nr), (int *)rmax, (int *)amax, st))) return rc;
+    if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, const_cast<float *>(P.ns), (int *)amax, nullptr, st))) return rc;
+    tc_prep_kernel<<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, amax, nullptr, 1.0f, a16, nullptr, aaug, scale);
+    DSIR_LAUNCH_CHECK();
+    tc_prep_kernel<<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, amax, P.nr, -2.0f, b16, baug, nullptr, nullptr);
+    DSIR_LAUNCH_CHECK();
     CUtensorMap mapA, mapB, mapAaug, mapBaug;
     if (!make_half_tmap(&mapA, a16, P.B, P.J, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
         !make_half_tmap(&mapB, b16, P.B, P.K, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
@@ -773,12 +786,12 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     DSIR_LAUNCH_CHECK();
 
     RefineParams R{};
-    R.B = P.B; R.J = P.J; R.K = P.K; R.C = P.C; R.Cp = pl.Cp; R.S = pl.S; R.Jpad = pl.Jpad;
-    R.a_copy = a_copy; R.b_copy = b_copy; R.ns = P.ns; R.nr = P.nr; R.rmax = rmax; R.scale = scale; R.cand_val = cval; R.cand_idx = cidx;
+    R.B = P.B; R.J = P.J; R.K = P.K; R.C = P.C; R.S = pl.S; R.Jpad = pl.Jpad;
+    R.fs = P.fs; R.fr = P.fr; R.ns = P.ns; R.nr = P.nr; R.rmax = rmax; R.scale = scale; R.cand_val = cval; R.cand_idx = cidx;
     R.idx = P.idx; R.min_d = P.min_d; R.rescue_count = count; R.rescue_rows = rows;
     R.rescue_keys = (unsigned long long *)(base + pl.off_keys);
     const long long nrows = (long long)P.B * P.J;
-    match_tc_refine_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(R);
+    match_tc_refine_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(R);
     DSIR_LAUNCH_CHECK();
     match_tc_rescue_kernel<<<sms * 4, 256, 0, st>>>(R, R.rescue_keys);
     DSIR_LAUNCH_CHECK();

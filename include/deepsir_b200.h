@@ -49,6 +49,13 @@ int dsir_device_check(void);
 /* number of kernels this library has enqueued since it was loaded (all threads) */
 uint64_t dsir_launch_count(void);
 
+/* In-situ profiler (diagnostic; not for production timing): between dsir_profile_begin(stream) and
+ * dsir_profile_report() every kernel launch site of the library records a CUDA event right after its launch;
+ * the report (text, one line per launch site "file:line launches total_us share") is written to buf.
+ * dsir_profile_report synchronises the device. */
+int dsir_profile_begin(dsir_stream_t stream);
+int dsir_profile_report(char *buf, size_t buf_bytes);
+
 /* ------------------------------------------------------------------------------------------------
  * xyz k-nearest neighbours.  Replaces torch_points_kernels.knn(pos_support, pos, k) as called at
  * dataloader/data_base.py:165,170.  d2 = fma(dz,dz, fma(dy,dy, dx*dx)) in fp32; results ascending in
