@@ -408,6 +408,14 @@ int dsir_match_argmin_filter_timing(const void *ws, size_t ws_bytes, int B, int 
     return match_tc_filter_timing((const char *)ws + used, B, C, J, K, host_out, (cudaStream_t)stream);
 }
 
+int dsir_match_argmin_filter_trace(const void *ws, size_t ws_bytes, int B, int C, int J, int K, uint32_t *host_out,
+                                   dsir_stream_t stream) {
+    if (!ws || !host_out || B <= 0 || C <= 0 || J <= 0 || K <= 0) return DSIR_ERR_BAD_ARG;
+    size_t used = ws_block((size_t)B * J * sizeof(float)) + ws_block((size_t)B * K * sizeof(float));
+    if (used >= ws_bytes) return DSIR_ERR_WORKSPACE;
+    return match_tc_filter_trace((const char *)ws + used, B, C, J, K, host_out, (cudaStream_t)stream);
+}
+
 size_t dsir_match_soft_workspace_bytes(int B, int C, int J, int K) {
     (void)C;
     if (B <= 0 || J <= 0 || K <= 0) return 256;

@@ -9,6 +9,7 @@ bool match_tc_profitable(int B, int C, int J, int K);
 size_t match_tc_workspace_bytes(int B, int C, int J, int K);
 int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_t st);
 int match_tc_rescued_rows(const void *ws, int B, int C, int J, int K, int *out, cudaStream_t st);
+int match_tc_filter_trace(const void *ws, int B, int C, int J, int K, unsigned int *out, cudaStream_t st);
 int match_tc_filter_timing(const void *ws, int B, int C, int J, int K, double *out, cudaStream_t st);
 
 }  // namespace dsir

@@ -109,6 +109,11 @@ int dsir_match_argmin_rescued_rows(const void *ws, size_t ws_bytes, int B, int C
 int dsir_match_argmin_filter_timing(const void *ws, size_t ws_bytes, int B, int C, int J, int K, double *host_out,
                                     dsir_stream_t stream);
 
+/* diagnostic (only filled when the environment variable DSIR_TC_DEBUG has bit 1 set): SM-clock stamps of CTA 0's first
+ * 256 units of the last filter launch; host_out[4096] u32, layout documented at match_tc_filter_trace (match_tc.cu). */
+int dsir_match_argmin_filter_trace(const void *ws, size_t ws_bytes, int B, int C, int J, int K, uint32_t *host_out,
+                                   dsir_stream_t stream);
+
 /* fused distance + affinity + row softmax + soft target (never materialises [J,K]):
  *   a_jk = -beta_b (d_jk - alpha_b) (+ col_bias[b,k])           compute_affinity, matchnet.py:195-208
  *   lse_j = log sum_k exp(a_jk);  w_jk = exp(a_jk - lse_j)      row pass of sinkhorn, matchnet.py:259
