@@ -42,7 +42,7 @@ tm = {}
 _, n_resc = D.match_argmin(b["feat_src"], b["feat_ref"], algo=D.MATCH_TC, return_rescued=True, timing=tm)
 print("rescued rows:", n_resc, "of", a.batch * a.n)
 print("filter kernel (device timers, steady state): span %.1f us = %.1f us/pair, %.0f cycles/CTA (%.2f GHz), %.0f cycles per "
-      "256x128 unit (tensor floor 640)" % (tm["span_ns"] / 1e3, tm["span_ns"] / 1e3 / a.batch, tm["cycles_per_cta"],
+      "item-unit (tensor floor 320 per 128x128 tile)" % (tm["span_ns"] / 1e3, tm["span_ns"] / 1e3 / a.batch, tm["cycles_per_cta"],
                                             tm["cycles_per_cta"] / tm["span_ns"], tm["cycles_per_unit"]))
 for name, algo in (("grid", D.KNN_AUTO), ("brute", D.KNN_BRUTE)):
     if name == "brute" and a.batch > 8:

@@ -32,20 +32,18 @@ torch.cuda.synchronize()
 out = (ctypes.c_uint32 * 4096)()
 L.check(lib.dsir_match_argmin_filter_trace(ws.data_ptr(), ws.numel(), B, C, J, K, ctypes.addressof(out), L.stream_ptr(dev)), "trace")
 t = np.frombuffer(out, dtype=np.uint32).astype(np.int64)
-mma = t[:2048].reshape(256, 4, 2)      # [useq][a][free seen, issued]
-epi = t[2048:].reshape(4, 256, 2)      # [a][useq][full seen, drained]
+mma = t[:1024].reshape(256, 2, 2)      # [useq][row block][free seen, issued]
+epi = t[1024:1024 + 2048].reshape(256, 8)   # [useq][k]
 t0 = mma[0, 0, 0]
 d = lambda x: (x - t0) & 0xffffffff
-sl = slice(40, 200)                    # steady state, inside the first item (128 units) and into the second
-per_unit = np.diff(d(mma[sl, 0, 0])).mean()
-print(f"period per unit (MMA thread, accumulator 0): {per_unit:.0f} clk")
-for acc in range(4):                   # acc = 2 * row block + column half
-    r = acc >> 1
-    free_seen, issued = d(mma[sl, r, 0]), d(mma[sl, r, 1])
-    full_seen, drained = d(epi[acc, sl, 0]), d(epi[acc, sl, 1])
-    print(f"rb {r} half {acc & 1}: issue {np.mean(issued - free_seen):6.0f} | issued->full seen {np.mean(full_seen - issued):6.0f} | "
-          f"drain {np.mean(drained - full_seen):6.0f} | drained->free seen(same stage, 2 units later) "
-          f"{np.mean(d(mma[sl, r, 0])[2:] - drained[:-2]):6.0f}")
-print("first units of acc 0 (free seen, issued, full seen, drained), clk from start:")
-for u in list(range(0, 3)) + list(range(100, 103)):
-    print(u, d(mma[u, 0, 0]), d(mma[u, 0, 1]), d(epi[0, u, 0]), d(epi[0, u, 1]))
+sl = slice(40, 200)
+print(f"period per unit (issuer of row block 0): {np.diff(d(mma[sl, 0, 0])).mean():.0f} clk")
+for r in range(2):
+    print(f"issuer {r}: free seen -> issued {np.mean(d(mma[sl, r, 1]) - d(mma[sl, r, 0])):6.0f}")
+e = d(epi[sl])
+names = ["full seen -> 32 cols in regs", "step 1 (tree, vote, slow path)", "wait second 32 cols", "step 2", "fence + arrive"]
+print(f"epilogue warp 0: issued -> full seen {np.mean(e[:, 0] - d(mma[sl, 0, 1])):6.0f}")
+for k, n in enumerate(names):
+    print(f"   {n:34s} {np.mean(e[:, k + 1] - e[:, k]):6.0f}")
+print(f"   drain total {np.mean(e[:, 5] - e[:, 0]):6.0f};  released -> issuer sees it free (2 units later) "
+      f"{np.mean(d(mma[sl, 0, 0])[2:] - e[:-2, 5]):6.0f}")

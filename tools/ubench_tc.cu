@@ -95,7 +95,7 @@ __global__ __launch_bounds__(640, 1) void ubench(int mode, int variant, int read
     long long t0 = clock64();
     if (warp == 0) {
         if (lane == 0 && (mode & 1)) {
-            auto issue = [&](auto NV, auto F16V, auto KSV, auto TSV) {
+            auto issue = [&](auto NV, auto F16V, auto KSV, auto TSV, int special) {
                 constexpr int N = decltype(NV)::value;
                 constexpr bool f16 = decltype(F16V)::value;
                 constexpr int ksteps = decltype(KSV)::value;
@@ -111,7 +111,11 @@ __global__ __launch_bounds__(640, 1) void ubench(int mode, int variant, int read
                         const int kb = (ks >> 2) & 1, kk = ks & 3;
                         const uint64_t db = db0 + (uint64_t)((kb * (N * 128) + kk * 32) >> 4);
                         const uint64_t da = da0 + (uint64_t)((kb * 16384 + kk * 32) >> 4);
-                        if (ts) mma_ts(d, tbase + 384 + ks * 8, db, idesc, ks > 0);
+                        if (special == 1 && ks == 4) {   // fifth k-step from a SWIZZLE_32B tile (SBO 256, layout 6)
+                            mma_ss_f16(d, make_desc(smem_u32(smem + 80 * 1024), 256, 6), make_desc(smem_u32(smem + 84 * 1024), 256, 6), idesc, 1);
+                        } else if (special == 2) {       // alternate between two accumulators MMA by MMA
+                            mma_ss_f16(tbase + (uint32_t)((ks & 1) * 128), da, db, idesc, ks > 1);
+                        } else if (ts) mma_ts(d, tbase + 384 + ks * 8, db, idesc, ks > 0);
                         else if (f16) mma_ss_f16(d, da, db, idesc, ks > 0);
                         else mma_ss(d, da, db, idesc, ks > 0);
                     }
@@ -119,13 +123,15 @@ __global__ __launch_bounds__(640, 1) void ubench(int mode, int variant, int read
             };
             using std::integral_constant;
             switch (variant) {
-                case 0: issue(integral_constant<int, 128>{}, integral_constant<bool, false>{}, integral_constant<int, 8>{}, integral_constant<bool, false>{}); break;
-                case 1: issue(integral_constant<int, 256>{}, integral_constant<bool, false>{}, integral_constant<int, 8>{}, integral_constant<bool, false>{}); break;
-                case 2: issue(integral_constant<int, 128>{}, integral_constant<bool, false>{}, integral_constant<int, 8>{}, integral_constant<bool, true>{}); break;
-                case 3: issue(integral_constant<int, 128>{}, integral_constant<bool, false>{}, integral_constant<int, 9>{}, integral_constant<bool, false>{}); break;
-                case 4: issue(integral_constant<int, 128>{}, integral_constant<bool, true>{}, integral_constant<int, 4>{}, integral_constant<bool, false>{}); break;
-                case 5: issue(integral_constant<int, 256>{}, integral_constant<bool, true>{}, integral_constant<int, 4>{}, integral_constant<bool, false>{}); break;
-                default: issue(integral_constant<int, 128>{}, integral_constant<bool, true>{}, integral_constant<int, 5>{}, integral_constant<bool, false>{}); break;
+                case 0: issue(integral_constant<int, 128>{}, integral_constant<bool, false>{}, integral_constant<int, 8>{}, integral_constant<bool, false>{}, 0); break;
+                case 1: issue(integral_constant<int, 256>{}, integral_constant<bool, false>{}, integral_constant<int, 8>{}, integral_constant<bool, false>{}, 0); break;
+                case 2: issue(integral_constant<int, 128>{}, integral_constant<bool, false>{}, integral_constant<int, 8>{}, integral_constant<bool, true>{}, 0); break;
+                case 3: issue(integral_constant<int, 128>{}, integral_constant<bool, false>{}, integral_constant<int, 9>{}, integral_constant<bool, false>{}, 0); break;
+                case 4: issue(integral_constant<int, 128>{}, integral_constant<bool, true>{}, integral_constant<int, 4>{}, integral_constant<bool, false>{}, 0); break;
+                case 5: issue(integral_constant<int, 256>{}, integral_constant<bool, true>{}, integral_constant<int, 4>{}, integral_constant<bool, false>{}, 0); break;
+                case 7: issue(integral_constant<int, 128>{}, integral_constant<bool, true>{}, integral_constant<int, 5>{}, integral_constant<bool, false>{}, 1); break;
+                case 8: issue(integral_constant<int, 128>{}, integral_constant<bool, true>{}, integral_constant<int, 5>{}, integral_constant<bool, false>{}, 2); break;
+                default: issue(integral_constant<int, 128>{}, integral_constant<bool, true>{}, integral_constant<int, 5>{}, integral_constant<bool, false>{}, 0); break;
             }
             tc_commit(&bar);
             while (!mbar_try_wait(&bar, 0)) {}
@@ -188,7 +194,7 @@ int main() {
         CK(cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost));
         printf("%-44s grid=%3d  %.3f ms", name, grid, ms);
         if (mode & 1) {
-            const int ksteps = variant == 3 ? 9 : (variant == 6 ? 5 : (variant >= 4 ? 4 : 8));
+            const int ksteps = variant == 3 ? 9 : (variant >= 6 ? 5 : (variant >= 4 ? 4 : 8));
             printf("  mma: %lld clk, %.1f clk per MMA", h[0], (double)h[0] / ((double)iters * ksteps));
         }
         if (mode & 2) {
@@ -212,6 +218,8 @@ int main() {
         run("mma f16 SS M128 N128 K64", 1, 4, 0, 8000, 0, 0, grid);
         run("mma f16 SS M128 N256 K64", 1, 5, 0, 4000, 0, 0, grid);
         run("mma f16 SS M128 N128 K80", 1, 6, 0, 8000, 0, 0, grid);
+        run("mma f16 K80, 5th step SW32 tile", 1, 7, 0, 8000, 0, 0, grid);
+        run("mma f16 K80, alternating accumulators", 1, 8, 0, 8000, 0, 0, grid);
         run("mma f16 N128 K80 + ld+min3 16 warps", 3, 6, 16, 8000, 700, 1, grid);
         run("mma f16 N128 K80 + ld+min3 8 warps", 3, 6, 8, 8000, 1400, 1, grid);
         run("mma f16 N256 K64 + ld+min3 16 warps", 3, 5, 16, 4000, 700, 1, grid);
