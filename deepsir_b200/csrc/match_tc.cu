@@ -248,19 +248,22 @@ __device__ __forceinline__ void tmem_ld4_sync(uint32_t taddr, float (&x)[4]) {
 __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint32_t taddr, float margin, float &thr,
                                          float (&cv)[TC_T], int (&ci)[TC_T], bool sample, float &best) {
 #define F(i) __uint_as_float(v[i])
-    float q[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) q[g] = fminf(fmin3(F(4 * g), F(4 * g + 1), F(4 * g + 2)), F(4 * g + 3));
-#undef F
-    const float mm = fmin3(fmin3(q[0], q[1], q[2]), fmin3(q[3], q[4], q[5]), fminf(q[6], q[7]));
+    const float a0 = fmin3(F(0), F(1), F(2)), a1 = fmin3(F(3), F(4), F(5)), a2 = fmin3(F(6), F(7), F(8));
+    const float a3 = fmin3(F(9), F(10), F(11)), a4 = fmin3(F(12), F(13), F(14)), a5 = fmin3(F(15), F(16), F(17));
+    const float a6 = fmin3(F(18), F(19), F(20)), a7 = fmin3(F(21), F(22), F(23)), a8 = fmin3(F(24), F(25), F(26));
+    const float a9 = fmin3(F(27), F(28), F(29));
+    const float b0 = fmin3(a0, a1, a2), b1 = fmin3(a3, a4, a5), b2 = fmin3(a6, a7, a8), b3 = fmin3(a9, F(30), F(31));
+    const float mm = fminf(fmin3(b0, b1, b2), b3);
     if (sample) {              // priming pass: only the value of the running minimum, no candidates, no branches
         best = fminf(best, mm);
         return;
     }
     if (__any_sync(0xffffffffu, mm < thr)) {
-        unsigned qm = 0;
+        unsigned qm = 0;       // which aligned column quads hold a value below the threshold
 #pragma unroll
-        for (int g = 0; g < 8; ++g) qm |= (q[g] < thr) ? (1u << g) : 0u;
+        for (int g = 0; g < 8; ++g)
+            qm |= (fminf(fmin3(F(4 * g), F(4 * g + 1), F(4 * g + 2)), F(4 * g + 3)) < thr) ? (1u << g) : 0u;
+#undef F
         unsigned um = __reduce_or_sync(0xffffffffu, qm);
 #pragma unroll 1
         while (um) {
@@ -269,18 +272,9 @@ __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint
             float x[4];
             tmem_ld4_sync(taddr + 4 * g, x);   // bit-identical to v[4g .. 4g+3]
             if ((qm >> g) & 1u) {
-                const float lo01 = fminf(x[0], x[1]), lo23 = fminf(x[2], x[3]);
-                const float m = fminf(lo01, lo23);
-                const int i = x[0] == m ? 0 : (x[1] == m ? 1 : (x[2] == m ? 2 : 3));   // first index of the quad minimum
-                cand_update(cv, ci, m, col0 + 4 * g + i, margin, thr);
-                // any OTHER element of the quad still below the (updated) threshold is a near tie: rare
-                const float hi01 = fmaxf(x[0], x[1]), hi23 = fmaxf(x[2], x[3]);
-                const float second = fminf(fmaxf(lo01, lo23), lo01 <= lo23 ? hi01 : hi23);
-                if (second < thr) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (e != i && x[e] < thr) cand_update(cv, ci, x[e], col0 + 4 * g + e, margin, thr);
-                }
+                for (int e = 0; e < 4; ++e)
+                    if (x[e] < thr) cand_update(cv, ci, x[e], col0 + 4 * g + e, margin, thr);
             }
         }
     }
@@ -291,10 +285,10 @@ __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint
 // instead of ~ln(32 nu)), then all `nu` units of the range.  The three roles walk the same schedule.
 struct UnitSched {
     int u0, nu, ns, stride;
-    __device__ __forceinline__ UnitSched(int sp, int S, int U) {
+    __device__ __forceinline__ UnitSched(int sp, int S, int U, int prime_div) {
         u0 = (int)((long long)sp * U / S);
         nu = (int)((long long)(sp + 1) * U / S) - u0;
-        ns = nu >= 16 ? nu / 8 : 0;
+        ns = (prime_div > 0 && nu >= 2 * prime_div) ? nu / prime_div : 0;
         stride = ns > 0 ? nu / ns : 1;
     }
     __device__ __forceinline__ int total() const { return ns + nu; }
@@ -310,6 +304,7 @@ struct TcParams {
     const float *scale;     // [B] sigma (power of two)
     float *cand_val;        // [B][Jpad][S][T]  (scaled units)
     int *cand_idx;
+    int prime_div;            // priming pass over every prime_div-th unit (0 = none)
     int dbg_flags;            // experiments only (DSIR_TC_DEBUG): bit 0 = never take the slow path (wrong results)
     unsigned int *trace;      // DSIR_TC_DEBUG bit 1: block 0 logs clock stamps of its first 256 units (see match_tc_filter_trace)
     unsigned long long *dbg;  // [grid][4]: start ns, end ns, cycles, units (diagnostic, always written)
@@ -364,7 +359,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
             bool first = true;
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
                 const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
-                const UnitSched us(sp, P.S, P.U);
+                const UnitSched us(sp, P.S, P.U, P.prime_div);
                 mbar_wait(empty_a, iphase ^ 1u);
                 mbar_expect_tx(full_a, TC_RBS * MAIN_TILE + (first ? AUG_TILE : 0u));
 #pragma unroll
@@ -396,7 +391,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
             const uint64_t descB0 = make_kmajor_desc(smem_u32(sB), 1024, 2);
             const uint64_t descBaug0 = make_kmajor_desc(smem_u32(sBaug), 256, 6);
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-                const UnitSched us(it % P.S, P.S, P.U);
+                const UnitSched us(it % P.S, P.S, P.U, P.prime_div);
                 mbar_wait(full_a, iphase);
                 for (int t = 0; t < us.total(); ++t) {
                     mbar_wait(&full_b[pb.stage], pb.phase);
@@ -436,7 +431,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
         int useq = 0;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
-            const UnitSched us(sp, P.S, P.U);
+            const UnitSched us(sp, P.S, P.U, P.prime_div);
             float best = INFINITY;
             float cv[TC_T];
             int ci[TC_T];
@@ -494,7 +489,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
         d[0] = dbg_s[0]; d[1] = globaltimer_ns(); d[2] = clock64() - dbg_s[1];
         unsigned long long units = 0;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-            units += (unsigned long long)UnitSched(it % P.S, P.S, P.U).nu;
+            units += (unsigned long long)UnitSched(it % P.S, P.S, P.U, P.prime_div).nu;
         }
         d[3] = units;
     }
@@ -580,8 +575,9 @@ struct RefineParams {
     const int *cand_idx;
     int64_t *idx;
     float *min_d;
-    int *rescue_count;
+    int *rescue_count, *exact_count;   // adjacent ints
     int *rescue_rows;  // [B*J] flat row ids
+    int *exact_rows;   // [B*J]
     unsigned long long *rescue_keys;  // [B*J] (ordered distance bits << 32) | index, atomicMin target
 };
 
@@ -589,11 +585,12 @@ struct RefineParams {
 __device__ __forceinline__ float exact_dist(const float *__restrict__ sp, int64_t s_cs, const float *__restrict__ rp, int64_t r_cs,
                                             int C, float nsj, float nrk) {
     float dot = 0.f;
-#pragma unroll 8
+#pragma unroll 32
     for (int c = 0; c < C; ++c) dot = __fmaf_rn(sp[(size_t)c * s_cs], rp[(size_t)c * r_cs], dot);
     return l2_from_dot(dot, nsj, nrk);
 }
 
+// classify: one thread per source row
 __global__ __launch_bounds__(256) void match_tc_refine_kernel(RefineParams P) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (long long)P.B * P.J) return;
@@ -615,7 +612,7 @@ __global__ __launch_bounds__(256) void match_tc_refine_kernel(RefineParams P) {
         for (int t = 0; t < TC_T; ++t)
             if (kk[t] >= 0 && kk[t] < P.K && vv[t] < 1e38f) gmin = fminf(gmin, vv[t]);
     }
-    // pass 2: who qualifies; a split whose LAST slot still qualifies may have dropped something -> rescue
+    // pass 2: who qualifies; a list whose LAST slot still qualifies may have dropped something -> rescue
     const float lim = gmin + margin;
     int ntake = 0, ksingle = 0;
     bool sat = false;
@@ -630,37 +627,63 @@ __global__ __launch_bounds__(256) void match_tc_refine_kernel(RefineParams P) {
             if (take) { ++ntake; ksingle = kk[t]; sat = sat || (t == TC_T - 1); }
         }
     }
-    bool rescue = (ntake == 0) || sat;
-    float d = INFINITY;
-    int kbest = 0x7fffffff;
-    if (!rescue) {
-        if (ntake == 1 && P.min_d == nullptr) {
-            kbest = ksingle;
-        } else {
-            const float *sp = P.fs.ptr + (size_t)b * P.fs.batch_stride + (size_t)j * P.fs.point_stride;
-            const float *rb = P.fr.ptr + (size_t)b * P.fr.batch_stride;
-            for (int s = 0; s < nlist; ++s) {
-                const float4 v = cvp[s];
-                const int4 k = cip[s];
-                const float vv[4] = {v.x, v.y, v.z, v.w};
-                const int kk[4] = {k.x, k.y, k.z, k.w};
-#pragma unroll 1
-                for (int t = 0; t < TC_T; ++t) {
-                    if (!(kk[t] >= 0 && kk[t] < P.K && vv[t] < 1e38f && vv[t] <= lim)) continue;
-                    const float dd = exact_dist(sp, P.fs.chan_stride, rb + (size_t)kk[t] * P.fr.point_stride, P.fr.chan_stride,
-                                                P.C, nsj, P.nr[(size_t)b * P.K + kk[t]]);
-                    if (dd < d || (dd == d && kk[t] < kbest)) { d = dd; kbest = kk[t]; }
-                }
-            }
-            rescue = !(d < INFINITY);   // every qualifying distance was NaN/inf: let the exhaustive path decide
-        }
-    }
-    P.idx[row] = rescue ? 0 : (int64_t)kbest;
-    if (P.min_d) P.min_d[row] = d;
-    if (rescue) {
+    if (ntake == 0 || sat) {                       // exhaustive fp32 scan
+        P.idx[row] = 0;
+        if (P.min_d) P.min_d[row] = INFINITY;
         const int pos = atomicAdd(P.rescue_count, 1);
         P.rescue_rows[pos] = (int)row;
         P.rescue_keys[pos] = ~0ull;
+    } else if (ntake == 1 && P.min_d == nullptr) {  // the only possible argmin: no arithmetic needed
+        P.idx[row] = (int64_t)ksingle;
+    } else {                                        // several candidates (or the distance is wanted): exact re-scoring
+        P.idx[row] = 0;
+        const int pos = atomicAdd(P.exact_count, 1);
+        P.exact_rows[pos] = (int)row;
+    }
+}
+
+// exact re-scoring of the listed rows: one warp per row, one lane per candidate slot (<= 32), every qualifying lane
+// walks its own fma chain; the (value, index) lexicographic minimum wins, exactly like match_fp32_kernel.
+__global__ __launch_bounds__(256) void match_tc_exact_kernel(RefineParams P) {
+    const int lane = threadIdx.x & 31;
+    const int count = *P.exact_count;
+    const int nlist = P.S * TC_LISTS, ncand = nlist * TC_T;
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += gridDim.x * (blockDim.x >> 5)) {
+        const int row = P.exact_rows[i];
+        const int b = row / P.J, j = row % P.J;
+        const size_t cbase = ((size_t)b * P.Jpad + j) * ncand;
+        float v = INFINITY;
+        int k = -1;
+        if (lane < ncand) { v = P.cand_val[cbase + lane]; k = P.cand_idx[cbase + lane]; }
+        const bool valid = k >= 0 && k < P.K && v < 1e38f;
+        const float gmin = warp_min(valid ? v : INFINITY);
+        const float nsj = P.ns[(size_t)b * P.J + j];
+        const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C);
+        const bool take = valid && v <= gmin + margin;
+        float d = INFINITY;
+        int kk = 0x7fffffff;
+        if (take) {
+            d = exact_dist(P.fs.ptr + (size_t)b * P.fs.batch_stride + (size_t)j * P.fs.point_stride, P.fs.chan_stride,
+                           P.fr.ptr + (size_t)b * P.fr.batch_stride + (size_t)k * P.fr.point_stride, P.fr.chan_stride, P.C, nsj,
+                           P.nr[(size_t)b * P.K + k]);
+            kk = k;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float d2 = __shfl_xor_sync(0xffffffffu, d, o);
+            const int k2 = __shfl_xor_sync(0xffffffffu, kk, o);
+            if (d2 < d || (d2 == d && k2 < kk)) { d = d2; kk = k2; }
+        }
+        if (lane == 0) {
+            const bool rescue = !(d < INFINITY);   // every qualifying distance was NaN/inf: let the exhaustive path decide
+            P.idx[row] = rescue ? 0 : (int64_t)kk;
+            if (P.min_d) P.min_d[row] = d;
+            if (rescue) {
+                const int pos = atomicAdd(P.rescue_count, 1);
+                P.rescue_rows[pos] = row;
+                P.rescue_keys[pos] = ~0ull;
+            }
+        }
     }
 }
 
@@ -674,7 +697,7 @@ __device__ __forceinline__ unsigned int float_order_bits(float f) {
 __device__ __forceinline__ float float_from_order_bits(unsigned int u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
-constexpr int RESCUE_CHUNK = 2048;
+constexpr int RESCUE_CHUNK = 256;    // one column per thread: the 64 strided loads of a thread are independent
 constexpr int RESCUE_MAXC = 64;
 
 __global__ __launch_bounds__(256) void match_tc_rescue_kernel(RefineParams P, unsigned long long *keys) {
@@ -731,7 +754,7 @@ __global__ void match_tc_rescue_finalize_kernel(RefineParams P, const unsigned l
 struct TcPlan {
     int NKS, RB, U, S, Jpad, Kpad;
     size_t off_a16, off_b16, off_baug, off_aaug, off_rmax, off_amax, off_scale, off_cval, off_cidx, off_count,
-        off_rows, off_keys, off_dbg, off_trace, total;
+        off_rows, off_erows, off_keys, off_dbg, off_trace, total;
 };
 
 TcPlan make_plan(int B, int C, int J, int K) {
@@ -763,6 +786,7 @@ TcPlan make_plan(int B, int C, int J, int K) {
     p.off_cidx = take((size_t)B * p.Jpad * S * TC_LISTS * TC_T * 4);
     p.off_count = take(256);
     p.off_rows = take((size_t)B * J * 4);
+    p.off_erows = take((size_t)B * J * 4);
     p.off_keys = take((size_t)B * J * 8);
     p.off_dbg = take((size_t)256 * 4 * 8);
     p.off_trace = take((size_t)4096 * 4);
@@ -805,7 +829,7 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
 
     // rmax and amax are adjacent 256-byte blocks: one memset clears both
     DSIR_CUDA_TRY(cudaMemsetAsync(rmax, 0, pl.off_scale - pl.off_rmax, st));
-    DSIR_CUDA_TRY(cudaMemsetAsync(count, 0, 4, st));
+    DSIR_CUDA_TRY(cudaMemsetAsync(count, 0, 8, st));
     int rc;
     // exact squared norms (fma chains, shared with the fp32 kernel) + per-batch maxima for sigma and the margin
     if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, const_cast<float *>(P.nr), (int *)rmax, (int *)amax, st))) return rc;
@@ -827,6 +851,7 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     T.dbg = (unsigned long long *)(base + pl.off_dbg);
     T.trace = (unsigned int *)(base + pl.off_trace);
     { const char *e = getenv("DSIR_TC_DEBUG"); T.dbg_flags = e ? atoi(e) : 0; }
+    { const char *e = getenv("DSIR_TC_PRIME"); T.prime_div = e ? atoi(e) : 8; }
     const int items = P.B * pl.RB * pl.S;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -850,10 +875,13 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     RefineParams R{};
     R.B = P.B; R.J = P.J; R.K = P.K; R.C = P.C; R.S = pl.S; R.Jpad = pl.Jpad;
     R.fs = P.fs; R.fr = P.fr; R.ns = P.ns; R.nr = P.nr; R.rmax = rmax; R.scale = scale; R.cand_val = cval; R.cand_idx = cidx;
-    R.idx = P.idx; R.min_d = P.min_d; R.rescue_count = count; R.rescue_rows = rows;
+    R.idx = P.idx; R.min_d = P.min_d; R.rescue_count = count; R.exact_count = count + 1; R.rescue_rows = rows;
+    R.exact_rows = (int *)(base + pl.off_erows);
     R.rescue_keys = (unsigned long long *)(base + pl.off_keys);
     const long long nrows = (long long)P.B * P.J;
     match_tc_refine_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(R);
+    DSIR_LAUNCH_CHECK();
+    match_tc_exact_kernel<<<sms * 8, 256, 0, st>>>(R);
     DSIR_LAUNCH_CHECK();
     match_tc_rescue_kernel<<<sms * 4, 256, 0, st>>>(R, R.rescue_keys);
     DSIR_LAUNCH_CHECK();
