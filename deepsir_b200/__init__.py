@@ -12,6 +12,7 @@ from .kabsch import (compute_rigid_transform, compute_rigid_transform_2, kabsch_
                      kabsch_from_moments, kabsch_soft)
 from .knn import knn, nn_search, nn_search_cloud  # noqa: F401
 from .loop import align_loop, pred_pairs  # noqa: F401
+from .pipeline import RegistrationPipeline  # noqa: F401
 from . import se3 as se3_torch  # noqa: F401
 from . import se3, synth  # noqa: F401
 

@@ -1,0 +1,93 @@
+"""Host-side pipeline over the C-ABI path: pinned host batches in, poses and correspondences out.
+
+The reference moves a collated batch to the device (`dict_all_to_device`, test.py:391), runs the forward pass and reads
+the pose back, strictly in sequence.  Here the upload of batch i+1 (copy stream) overlaps the kernels of batch i
+(compute stream) and the small result download, so a stream of batches runs at max(PCIe time, kernel time) per batch
+instead of their sum.  Everything on the device goes through libdeepsir_b200.so; torch only provides streams, events
+and memory.
+"""
+from __future__ import annotations
+
+from collections import deque
+
+import torch
+
+from . import _lib as L
+from .knn import nn_search_cloud
+from .loop import align_loop
+
+
+class RegistrationPipeline:
+    """KNN pyramid of both clouds + `iters` x (match -> Kabsch -> transform) per batch, double buffered.
+
+    A batch is a dict of PINNED host tensors: points_src/points_ref [B,N,>=3], feat_src/feat_ref [B,C,N],
+    weights [B,N].  `run(batches)` yields, in order, dicts with host tensors
+    T [B,3,4] (final cumulative transform), pred [B,N] int32 (last correspondences, the `pred_pairs` of
+    network/model.py:599-601) and status [iters,B]; with keep_graph=True also the device KNN tensors of the batch.
+    """
+
+    def __init__(self, device=None, num_knn=16, sub_sampling_ratio=(4, 4, 4, 4), iters=1, depth=2, keep_graph=False):
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.dev.type != "cuda":
+            raise L.DeepSIRError("RegistrationPipeline runs on a CUDA device only")
+        self.k, self.ratios, self.iters, self.depth, self.keep_graph = num_knn, tuple(sub_sampling_ratio), iters, depth, keep_graph
+        self.copy_stream = torch.cuda.Stream(self.dev)
+
+    def _upload(self, host, compute):
+        with torch.cuda.stream(self.copy_stream):
+            d = {k: v.to(self.dev, non_blocking=True) for k, v in host.items()}
+            up = torch.cuda.Event()
+            up.record(self.copy_stream)
+        for v in d.values():
+            v.record_stream(compute)   # the compute stream reads them: keep the allocator from recycling early
+        return d, up
+
+    def _compute(self, d, up, compute):
+        compute.wait_event(up)
+        g_src = nn_search_cloud(d["points_src"], self.k, self.ratios)
+        g_ref = nn_search_cloud(d["points_ref"], self.k, self.ratios)
+        xs = d["points_src"][:, :, :3].permute(0, 2, 1).contiguous()   # the loop's [B,3,N] layout (model.py:541-549)
+        xr = d["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
+        tr, pred, _, status = align_loop(d["feat_src"], d["feat_ref"], xs, xr, d["weights"], self.iters)
+        B, N = pred[-1].shape
+        out = dict(T=torch.empty(B, 3, 4, dtype=torch.float32, pin_memory=True),
+                   pred=torch.empty(B, N, dtype=torch.int32, pin_memory=True),
+                   status=torch.empty(self.iters, B, dtype=torch.int32, pin_memory=True))
+        out["T"].copy_(tr[-1], non_blocking=True)
+        out["pred"].copy_(pred[-1].to(torch.int32), non_blocking=True)
+        out["status"].copy_(status, non_blocking=True)
+        if self.keep_graph:
+            out["graph_src"], out["graph_ref"] = g_src, g_ref
+        done = torch.cuda.Event()
+        done.record(compute)
+        return out, done
+
+    def run(self, batches):
+        compute = torch.cuda.current_stream(self.dev)
+        self.copy_stream.wait_stream(compute)        # uploads start after whatever the caller enqueued before
+        uploaded, inflight = deque(), deque()
+        it = iter(batches)
+
+        def feed():
+            try:
+                uploaded.append(self._upload(next(it), compute))
+                return True
+            except StopIteration:
+                return False
+
+        for _ in range(self.depth):
+            if not feed():
+                break
+        while uploaded:
+            d, up = uploaded.popleft()
+            inflight.append(self._compute(d, up, compute))
+            del d
+            feed()                                   # the next upload is enqueued while this batch computes
+            if len(inflight) >= self.depth:
+                out, done = inflight.popleft()
+                done.synchronize()
+                yield out
+        while inflight:
+            out, done = inflight.popleft()
+            done.synchronize()
+            yield out

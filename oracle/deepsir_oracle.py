@@ -259,6 +259,16 @@ def kabsch_moments_fp64(src, tgt, weights):
     return out
 
 
+def kabsch_from_moments_fp64(mom):
+    """Kabsch from (summed) raw moments [B,17] fp64: the centred covariance of network/model.py:33-45 rewritten as
+    H = Sxy/S - (2 - Sw/S) c_s c_t^T with S = S|w| + eps, c_s = Sx/S, c_t = Sy/S; then :47-58 (fp64 SVD, det fix)."""
+    S = mom[:, 0] + _EPS
+    c_s, c_t = mom[:, 2:5] / S[:, None], mom[:, 5:8] / S[:, None]
+    H = mom[:, 8:17].reshape(-1, 3, 3) / S[:, None, None] - (2.0 - mom[:, 1] / S)[:, None, None] * c_s[:, :, None] * c_t[:, None, :]
+    T, _ = _kabsch_from_cov(H, c_s, c_t, keep_double=True)
+    return T, torch.zeros(mom.shape[0], dtype=torch.int32)
+
+
 def rotation_angle_deg(Ra, Rb):
     """geodesic distance between rotations in degrees (same formula as network/loss.py:266 pose_error)."""
     R = Ra.double() @ Rb.double().transpose(-1, -2)

@@ -368,3 +368,86 @@ def test_loop_ten_iterations_converges():
     # transforms[i] is the running composition (model.py:595)
     moved = D.se3_torch.transform_V2(tr[-1], cu(xs))
     assert torch.allclose(moved, xyz, atol=5e-4)
+
+
+# ------------------------------------------------------------------------------------------- fp16 filter edge cases
+def test_match_tc_extreme_scales_and_non_finite_rows():
+    """The tensor-core stage rounds sigma-scaled features to fp16; the answer must not depend on the scale of the
+    inputs, on rows of zeros, or on non-finite rows (those fall through to the exhaustive fp32 path)."""
+    fs0, fr0 = synth.random_features(1, 64, 1500, 21), synth.random_features(1, 64, 2100, 22)
+    for scale_s, scale_r in [(1e-6, 1e-6), (1e4, 1e4), (1e-3, 1e2), (37.0, 0.01)]:
+        fs, fr = cu(fs0 * scale_s), cu(fr0 * scale_r)
+        i_tc, d_tc = D.match_argmin(fs, fr, return_min=True, algo=D.MATCH_TC)
+        i_32, d_32 = D.match_argmin(fs, fr, return_min=True, algo=D.MATCH_FP32)
+        assert torch.equal(i_tc, i_32) and torch.equal(d_tc, d_32), (scale_s, scale_r)
+    fs, fr = cu(fs0.clone()), cu(fr0.clone())
+    fs[0, :, 7] = 0.0                      # a zero source row
+    fr[0, :, 11] = 0.0                     # a zero reference row
+    fs[0, 3, 100] = float("nan")           # a NaN source row: every distance NaN -> index 0 like the fp32 kernel
+    fr[0, 5, 200] = float("inf")           # a non-finite reference row never wins
+    i_tc = D.match_argmin(fs, fr, algo=D.MATCH_TC)
+    i_32 = D.match_argmin(fs, fr, algo=D.MATCH_FP32)
+    assert torch.equal(i_tc, i_32)
+    assert (i_tc != 200).all()
+
+
+def test_filter_timing_diagnostic():
+    b = synth.make_batch(2, 4096, 64, "kitti", config=2, first_pair=50)
+    tm = {}
+    D.match_argmin(cu(b["feat_src"]), cu(b["feat_ref"]), algo=D.MATCH_TC, timing=tm)
+    assert tm["span_ns"] > 0 and tm["cycles_per_unit"] > 0
+
+
+# ------------------------------------------------------------------------------------------- host pipeline
+def test_pipeline_equals_direct_calls():
+    """RegistrationPipeline (pinned host in -> host out, upload overlapped with compute) returns exactly what the
+    individual library calls return on device-resident copies of the same batches."""
+    batches = [synth.make_batch(2, 3000, 64, "kitti", config=2, first_pair=10 * i) for i in range(3)]
+    host = [dict(points_src=b["points_src"].pin_memory(), points_ref=b["points_ref"].pin_memory(),
+                 feat_src=b["feat_src"].pin_memory(), feat_ref=b["feat_ref"].pin_memory(),
+                 weights=b["weights"][:, :, 0].contiguous().pin_memory()) for b in batches]
+    pipe = D.RegistrationPipeline(DEV, 16, (4, 4, 4, 4), iters=2, depth=2, keep_graph=True)
+    outs = list(pipe.run(iter(host)))
+    assert len(outs) == 3
+    for b, o in zip(batches, outs):
+        xs = b["points_src"][:, :, :3].permute(0, 2, 1).contiguous()
+        xr = b["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
+        tr, pred, _, st = D.align_loop(cu(b["feat_src"]), cu(b["feat_ref"]), cu(xs), cu(xr), cu(b["weights"]), 2)
+        assert torch.equal(o["T"], tr[-1].cpu())
+        assert o["pred"].dtype == torch.int32 and torch.equal(o["pred"].long(), pred[-1].cpu())
+        assert torch.equal(o["status"], st.cpu())
+        g = D.nn_search_cloud(cu(b["points_ref"]), 16, (4, 4, 4, 4))
+        for k in g:
+            assert torch.equal(o["graph_ref"][k], g[k])
+
+
+# ------------------------------------------------------------------------------------------- row-block sharding
+def test_rowblock_sharding_on_one_device():
+    """raw fp64 moments of source-row blocks add up to the moments of the whole pair, and the Kabsch solve
+    from the summed moments equals the unsharded solve (ranks emulated as row blocks on one GPU; the collective itself is
+    covered by the world-size-2 gloo test)."""
+    from deepsir_b200 import dist as DD
+    b = synth.make_batch(2, 5000, 64, "kitti", config=4, first_pair=3)
+    xs = cu(b["points_src"][:, :, :3].permute(0, 2, 1).contiguous())
+    xr = cu(b["points_ref"][:, :, :3].permute(0, 2, 1).contiguous())
+    fs, fr, w = cu(b["feat_src"]), cu(b["feat_ref"]), cu(b["weights"][:, :, 0].contiguous())
+    idx = D.match_argmin(fs, fr)
+    T_full, st = D.kabsch_gather(xs, xr, idx, w)
+    mom = torch.zeros(2, 17, dtype=torch.float64, device=DEV)
+    parts = []
+    for r in range(3):
+        lo, hi = DD.row_block(5000, 3, r)
+        i_r = D.match_argmin(fs[:, :, lo:hi], fr)                 # a rank matches only its own rows
+        parts.append(i_r)
+        mom += DD.LibraryOps.moments(xs[:, :, lo:hi].contiguous(), xr, i_r, w[:, lo:hi].contiguous())
+    assert torch.equal(torch.cat(parts, 1), idx)
+    T_sh, st2 = D.kabsch_from_moments(mom)
+    assert (st == 0).all() and (st2 == 0).all()
+    assert O.rotation_angle_deg(T_sh.cpu()[:, :, :3], T_full.cpu()[:, :, :3]).max() < 1e-5
+    assert (T_sh - T_full).abs().max() < 1e-5
+    # the sharded loop with one rank is the fused loop
+    tr_a, pred_a, xyz_a, _ = DD.align_rowblock(fs, fr, xs, xr, w, 3)
+    tr_b, pred_b, xyz_b, _ = D.align_loop(fs, fr, xs, xr, w, 3)
+    assert torch.equal(torch.stack(pred_a), torch.stack(pred_b))
+    for a, c in zip(tr_a, tr_b):
+        assert_pose_close(a, c.cpu())
