@@ -94,12 +94,12 @@ def make_inputs(batch, first_pair):
 
 
 def cpu_step(host, n_pairs):
-    """The reference path on the CPU (oracle port): nn_search on both clouds + match/argmin (6000-row chunks) +
-    gather + Kabsch (fp64 LAPACK SVD) + transform + compose, for the first n_pairs pairs."""
+    """The reference path on the CPU (oracle port): nn_search on both clouds (kd-tree, all cores) + match/argmin
+    (6000-row chunks, MKL sgemm) + gather + Kabsch (fp64 LAPACK SVD) + transform + compose, for the first n_pairs pairs."""
     from oracle import deepsir_oracle as O
     s = slice(0, n_pairs)
-    O.nn_search_c(host["points_src"][s], KNN_K, RATIOS)
-    O.nn_search_c(host["points_ref"][s], KNN_K, RATIOS)
+    O.nn_search_kdtree(host["points_src"][s], KNN_K, RATIOS)      # kd-tree like the reference's torch_points_kernels.knn
+    O.nn_search_kdtree(host["points_ref"][s], KNN_K, RATIOS)
     xs = host["points_src"][s, :, :3].permute(0, 2, 1).contiguous()
     xr = host["points_ref"][s, :, :3].permute(0, 2, 1).contiguous()
     O.align_loop(host["feat_src"][s], host["feat_ref"][s], xs, xr, host["weights"][s, :, None], 1)
@@ -125,7 +125,7 @@ def run_reference(args, rank, world):
            "config": {"workload": WORKLOAD, "sample": f"{n_pairs} pair per step on the host CPU"},
            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
                             "sample": f"{n_pairs} pair/step x {args.steps} steps of the C2 workload, oracle port "
-                                      f"(torch-CPU MKL + OpenMP C KNN), {cores} threads"},
+                                      f"(torch-CPU MKL + scipy cKDTree KNN), {cores} threads"},
            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -267,7 +267,7 @@ def main():
         cores = os.cpu_count() or 1
         out["cpu_baseline"] = {"value": n_pairs * reps / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
                                "sample": f"{reps} x {n_pairs} pair of the C2 workload on the host: oracle port "
-                                         f"(torch-CPU MKL sgemm/LAPACK + OpenMP C brute-force KNN), {cores} threads"}
+                                         f"(torch-CPU MKL sgemm/LAPACK + scipy cKDTree KNN), {cores} threads"}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

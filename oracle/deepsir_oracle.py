@@ -372,6 +372,29 @@ def nn_search(points, num_knn=16, ratios=(4, 4, 4, 4)):
     return dict(xyz=torch.cat(xs, 1), neigh_idx=torch.cat(nb, 1), sub_idx=torch.cat(pool, 1), interp_idx=torch.cat(up, 1))
 
 
+def nn_search_kdtree(points, num_knn=16, ratios=(4, 4, 4, 4), workers=-1):
+    """DataBase.nn_search (dataloader/data_base.py:153-183) with scipy's cKDTree standing in for torch_points_kernels.knn
+    (C++/nanoflann kd-tree, absent here): the SAME algorithm class as the reference's CPU path, used for the TIMED CPU
+    baseline (the brute-force C oracle above defines the exact answer but is ~7x slower than a kd-tree at 16k points).
+    Results agree with the exact oracle except at fp32 distance ties (tests/test_oracle_golden.py)."""
+    from scipy.spatial import cKDTree
+    pc_all = points[:, :, :3].contiguous().numpy()
+    out = dict(xyz=[], neigh_idx=[], sub_idx=[], interp_idx=[])
+    for b in range(pc_all.shape[0]):
+        pc = pc_all[b]
+        xs, nb, pool, up = [], [], [], []
+        for r in ratios:
+            _, idx = cKDTree(pc).query(pc, k=num_knn, workers=workers)
+            m = pc.shape[0] // r
+            sub = pc[:m]
+            _, u = cKDTree(sub).query(pc, k=1, workers=workers)
+            xs.append(pc); nb.append(idx.reshape(pc.shape[0], num_knn)); pool.append(idx.reshape(pc.shape[0], num_knn)[:m]); up.append(u.reshape(-1, 1))
+            pc = sub
+        out["xyz"].append(np.concatenate(xs)); out["neigh_idx"].append(np.concatenate(nb))
+        out["sub_idx"].append(np.concatenate(pool)); out["interp_idx"].append(np.concatenate(up))
+    return {k: torch.from_numpy(np.stack(v).astype(np.int64 if k != "xyz" else np.float32)) for k, v in out.items()}
+
+
 def nn_search_c(points, num_knn=16, ratios=(4, 4, 4, 4)):
     """Same as nn_search but through the C pyramid driver (used as the timed cpu_baseline leg)."""
     p = np.ascontiguousarray(points.detach().cpu().numpy(), dtype=np.float32)

@@ -153,3 +153,16 @@ def test_nn_search_pyramid_shapes_and_c_driver():
     for k in a:
         assert torch.equal(a[k], c[k]), k
     assert a["interp_idx"].max() < 256 and a["neigh_idx"][:, 1024:1280].max() < 256
+
+
+def test_kdtree_baseline_agrees_with_exact_oracle():
+    """The kd-tree stand-in that bench.py TIMES as the CPU baseline computes the same pyramid as the exact oracle
+    (identical except at fp32 distance ties)."""
+    from deepsir_b200 import synth
+    b = synth.make_batch(1, 2048, 8, "kitti", config=1, first_pair=77)
+    a = O.nn_search_c(b["points_src"], 16, (4, 4, 4, 4))
+    k = O.nn_search_kdtree(b["points_src"], 16, (4, 4, 4, 4), workers=1)
+    assert torch.equal(a["xyz"], k["xyz"])
+    for key in ("neigh_idx", "sub_idx", "interp_idx"):
+        assert a[key].shape == k[key].shape
+        assert (a[key] == k[key]).float().mean() > 0.999, key
