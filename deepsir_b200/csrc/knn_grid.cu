@@ -12,6 +12,8 @@
 //           cube is ONE contiguous run of sorted points.
 //   query   one thread per query, queries taken in the cell order of their own grid so that the lanes of a warp
 //           are spatial neighbours (same cells -> L1 hits, little divergence); sorted top-k in registers.
+#include <cstdlib>
+
 #include "knn.cuh"
 
 namespace dsir {
@@ -176,6 +178,71 @@ __device__ __forceinline__ void topk_insert_lex(float (&bd)[KMAX], int (&bi)[KMA
     }
 }
 
+// Per-thread max-heap of the k best (d, idx) pairs in SHARED memory, column layout [slot][thread]: the bank of an
+// access is thread % 32 whatever the slot, so lanes that touch different slots never conflict.  A sorted register list
+// costs ~100 compare/select instructions per insertion on the ALU pipe, which bounded the kernel; the heap needs
+// <= log2(k) levels of two loads + two stores and keeps 2k registers free (higher occupancy).  Order is lexicographic
+// (d, idx); the root is the current k-th best and is mirrored in registers.
+template <int KMAX>
+struct SmemHeap {
+    float *d;   // [KMAX][128]
+    int *i;
+    int K;      // heap size (= k)
+    float rd;   // root
+    int ri;
+    __device__ __forceinline__ static bool gt(float da, int ia, float db, int ib) { return da > db || (da == db && ia > ib); }
+    __device__ __forceinline__ void init(float *dcol, int *icol, int k) {
+        d = dcol; i = icol; K = k;
+        for (int p = 0; p < k; ++p) { d[p * 128] = INFINITY; i[p * 128] = 0x7fffffff; }
+        rd = INFINITY; ri = 0x7fffffff;
+    }
+    // precondition: (x, s) < root.  Replace the root and sift down.
+    __device__ __forceinline__ void replace_root(float x, int s) {
+        int pos = 0;
+        while (true) {
+            const int l = 2 * pos + 1;
+            if (l >= K) break;
+            float cd = d[l * 128];
+            int ci = i[l * 128], c = l;
+            if (l + 1 < K) {
+                const float d2 = d[(l + 1) * 128];
+                const int i2 = i[(l + 1) * 128];
+                if (gt(d2, i2, cd, ci)) { cd = d2; ci = i2; c = l + 1; }
+            }
+            if (!gt(cd, ci, x, s)) break;
+            d[pos * 128] = cd; i[pos * 128] = ci;
+            pos = c;
+        }
+        d[pos * 128] = x; i[pos * 128] = s;
+        rd = d[0]; ri = i[0];
+    }
+    // remove and return the root (largest); heap shrinks by one
+    __device__ __forceinline__ void pop(float &od, int &oi) {
+        od = d[0]; oi = i[0];
+        --K;
+        if (K > 0) {
+            const float x = d[K * 128];
+            const int s = i[K * 128];
+            int pos = 0;
+            while (true) {
+                const int l = 2 * pos + 1;
+                if (l >= K) break;
+                float cd = d[l * 128];
+                int ci = i[l * 128], c = l;
+                if (l + 1 < K) {
+                    const float d2 = d[(l + 1) * 128];
+                    const int i2 = i[(l + 1) * 128];
+                    if (gt(d2, i2, cd, ci)) { cd = d2; ci = i2; c = l + 1; }
+                }
+                if (!gt(cd, ci, x, s)) break;
+                d[pos * 128] = cd; i[pos * 128] = ci;
+                pos = c;
+            }
+            d[pos * 128] = x; i[pos * 128] = s;
+        }
+    }
+};
+
 template <int KMAX>
 __global__ __launch_bounds__(128) void knn_grid_query_kernel(KnnGridQueryParams P) {
     const int b = blockIdx.y;
@@ -280,6 +347,105 @@ __global__ __launch_bounds__(128) void knn_grid_query_kernel(KnnGridQueryParams 
     }
 }
 
+template <int KMAX>
+__global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryParams P) {
+    __shared__ float s_hd[KMAX * 128];
+    __shared__ int s_hi[KMAX * 128];
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.Nq) return;
+    const KnnGridHeader H = P.hdr[b];
+    const int *__restrict__ cs = P.cell_start + (size_t)b * (P.gmax + 1);
+    const float4 *__restrict__ S = P.sorted + (size_t)b * P.Ns;
+
+    // query t of this block: in cell order of the query grid when one is given, else in natural order
+    float qx, qy, qz;
+    int qi;
+    if (P.q_sorted != nullptr) {
+        float4 q = P.q_sorted[(size_t)b * P.q_sorted_bs + t];
+        qx = q.x; qy = q.y; qz = q.z; qi = __float_as_int(q.w);
+    } else {
+        const float *qp = P.query + (size_t)b * P.qry_bs + (size_t)t * P.qry_stride;
+        qx = qp[0]; qy = qp[1]; qz = qp[2]; qi = t;
+    }
+
+    SmemHeap<KMAX> hp;
+    hp.init(s_hd + threadIdx.x, s_hi + threadIdx.x, P.k);
+
+    int px0 = 1, px1 = 0, py0 = 1, py1 = 0, pz0 = 1, pz1 = 0;  // cells already scanned (empty box)
+    float R = P.r0_cells * H.h;
+    const bool q_ok = (qx == qx) && (qy == qy) && (qz == qz);   // NaN query: nothing compares, scan everything once
+    for (int pass = 0; pass < 64; ++pass) {
+        const float Rb = __fmaf_rn(R, 1.0001f, H.slack);
+        int x0 = cell_of(qx - Rb, H.lo[0], H.inv_h, H.gx), x1 = cell_of(qx + Rb, H.lo[0], H.inv_h, H.gx);
+        int y0 = cell_of(qy - Rb, H.lo[1], H.inv_h, H.gy), y1 = cell_of(qy + Rb, H.lo[1], H.inv_h, H.gy);
+        int z0 = cell_of(qz - Rb, H.lo[2], H.inv_h, H.gz), z1 = cell_of(qz + Rb, H.lo[2], H.inv_h, H.gz);
+        if (!q_ok || !(Rb < INFINITY)) { x0 = 0; x1 = H.gx - 1; y0 = 0; y1 = H.gy - 1; z0 = 0; z1 = H.gz - 1; }
+        // never shrink (R only grows, but keep the invariant explicit)
+        if (px0 <= px1) { x0 = min(x0, px0); x1 = max(x1, px1); y0 = min(y0, py0); y1 = max(y1, py1); z0 = min(z0, pz0); z1 = max(z1, pz1); }
+        for (int z = z0; z <= z1; ++z) {
+            for (int y = y0; y <= y1; ++y) {
+                const int row = (z * H.gy + y) * H.gx;
+                const bool inner = (px0 <= px1) && y >= py0 && y <= py1 && z >= pz0 && z <= pz1;
+                // run A: [x0, inner ? px0-1 : x1]   run B: inner ? [px1+1, x1] : empty
+                int a0 = x0, a1 = inner ? px0 - 1 : x1;
+                int b0 = inner ? px1 + 1 : 1, b1 = inner ? x1 : 0;
+#pragma unroll 1
+                for (int run = 0; run < 2; ++run) {
+                    const int r0 = run == 0 ? a0 : b0, r1 = run == 0 ? a1 : b1;
+                    if (r0 > r1) continue;
+                    const int s = cs[row + r0], e = cs[row + r1 + 1];
+                    // four candidates per trip: four independent load->distance chains hide the load latency
+                    for (int i = s; i < e; i += 4) {
+                        float d4[4];
+                        int p4[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const bool ok = i + u < e;
+                            const float4 p = S[ok ? i + u : s];
+                            const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+                            float d = __fmul_rn(dx, dx);
+                            d = __fmaf_rn(dy, dy, d);
+                            d = __fmaf_rn(dz, dz, d);
+                            d4[u] = ok ? d : INFINITY;
+                            p4[u] = ok ? __float_as_int(p.w) : 0x7fffffff;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (d4[u] < hp.rd || (d4[u] == hp.rd && p4[u] < hp.ri)) hp.replace_root(d4[u], p4[u]);
+                    }
+                }
+            }
+        }
+        px0 = x0; px1 = x1; py0 = y0; py1 = y1; pz0 = z0; pz1 = z1;
+        const bool all = x0 == 0 && y0 == 0 && z0 == 0 && x1 == H.gx - 1 && y1 == H.gy - 1 && z1 == H.gz - 1;
+        const float kth = hp.rd;
+        if (all) break;
+        if (kth < __fmul_rn(R, R)) break;   // strict: every unscanned point is farther than R along some axis
+        if (kth < INFINITY) {
+            // k points known: the k-th distance bounds the answer; make R^2 strictly exceed it
+            float Rn = fmaxf(__fmul_rn(sqrtf(kth), 1.000001f), 1e-18f);
+            while (!(kth < __fmul_rn(Rn, Rn))) Rn = __fmul_rn(Rn, 1.0001f);
+            R = fmaxf(Rn, __fmul_rn(R, 1.0001f));
+        } else {
+            R = __fmul_rn(R, 2.f);
+        }
+    }
+
+    int64_t *o = P.idx + (size_t)b * P.idx_bs + (size_t)qi * P.k;
+    int64_t *o2 = (P.idx2 != nullptr && qi < P.idx2_rows) ? P.idx2 + (size_t)b * P.idx2_bs + (size_t)qi * P.k : nullptr;
+    float *od = P.dist2 != nullptr ? P.dist2 + (size_t)b * P.idx_bs + (size_t)qi * P.k : nullptr;
+    for (int p = P.k - 1; p >= 0; --p) {     // the heap yields the k best in descending order
+        float dd;
+        int ii;
+        hp.pop(dd, ii);
+        const int64_t v = ii == 0x7fffffff ? (int64_t)-1 : (int64_t)ii;
+        o[p] = v;
+        if (o2) o2[p] = v;
+        if (od) od[p] = dd;
+    }
+}
+
 }  // namespace
 
 size_t knn_grid_smem_bytes(int gmax) { return (size_t)(gmax + 1) * sizeof(int); }
@@ -299,11 +465,16 @@ int launch_knn_grid_query(const KnnGridQueryParams &P, int B, cudaStream_t st) {
     if (P.Ns < P.k) return DSIR_ERR_KNN_TOO_FEW;
     if (P.Nq <= 0 || B <= 0) return DSIR_OK;
     dim3 grid((P.Nq + 127) / 128, B);
+    static const bool reg_list = getenv("DSIR_KNN_REGLIST") != nullptr;   // experiments: sorted register list for every k
     if (P.k == 1) knn_grid_query_kernel<1><<<grid, 128, 0, st>>>(P);
     else if (P.k <= 4) knn_grid_query_kernel<4><<<grid, 128, 0, st>>>(P);
-    else if (P.k <= 8) knn_grid_query_kernel<8><<<grid, 128, 0, st>>>(P);
-    else if (P.k <= 16) knn_grid_query_kernel<16><<<grid, 128, 0, st>>>(P);
-    else knn_grid_query_kernel<32><<<grid, 128, 0, st>>>(P);
+    else if (reg_list) {
+        if (P.k <= 8) knn_grid_query_kernel<8><<<grid, 128, 0, st>>>(P);
+        else if (P.k <= 16) knn_grid_query_kernel<16><<<grid, 128, 0, st>>>(P);
+        else knn_grid_query_kernel<32><<<grid, 128, 0, st>>>(P);
+    } else if (P.k <= 8) knn_grid_query_heap_kernel<8><<<grid, 128, 0, st>>>(P);
+    else if (P.k <= 16) knn_grid_query_heap_kernel<16><<<grid, 128, 0, st>>>(P);
+    else knn_grid_query_heap_kernel<32><<<grid, 128, 0, st>>>(P);
     DSIR_LAUNCH_CHECK();
     return DSIR_OK;
 }
