@@ -13,6 +13,8 @@ from .kabsch import (compute_rigid_transform, compute_rigid_transform_2, kabsch_
 from .knn import knn, nn_search, nn_search_cloud  # noqa: F401
 from .loop import align_loop, pred_pairs  # noqa: F401
 from .pipeline import RegistrationPipeline  # noqa: F401
+from .graph import (gather_neighbour, gather_neighbour_V2, gather_neighbour_V4, relative_pos_encoding, random_sample,  # noqa: F401
+                    nearest_interpolation, sinkhorn)
 from . import se3 as se3_torch  # noqa: F401
 from . import se3, synth  # noqa: F401
 

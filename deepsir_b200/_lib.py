@@ -16,7 +16,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libdeepsir_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
-SOURCES = ["api.cu", "knn.cu", "knn_grid.cu", "match_fp32.cu", "match_tc.cu", "kabsch.cu"]
+SOURCES = ["api.cu", "knn.cu", "knn_grid.cu", "match_fp32.cu", "match_tc.cu", "kabsch.cu", "graph.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -92,6 +92,14 @@ _SIGS = {
                                    _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "dsir_gather_points": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
                                       _c.c_void_p]),
+    "dsir_gather_neighbours": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int,
+                                          _c.c_void_p, _c.c_void_p]),
+    "dsir_rel_pos_encoding": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "dsir_pool_max": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
+                                 _c.c_void_p]),
+    "dsir_sinkhorn_workspace_bytes": (_c.c_size_t, [_c.c_int] * 3),
+    "dsir_sinkhorn": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                 _c.c_size_t, _c.c_void_p]),
     "dsir_kabsch_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int]),
     "dsir_kabsch": (_c.c_int, [Points, Points, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
                                _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "graph.cuh"
 #include "kabsch.cuh"
 #include "knn.cuh"
 #include "match.cuh"
@@ -446,6 +447,38 @@ int dsir_gather_points(const float *in, int B, int C, int N, const int64_t *idx,
                        dsir_stream_t stream) {
     if (!in || !idx || !out || B <= 0 || C <= 0 || N <= 0 || M < 0) return DSIR_ERR_BAD_ARG;
     return launch_gather_points(in, B, C, N, idx, M, out, (cudaStream_t)stream);
+}
+
+/* ------------------------------------------------------------------ KNN consumers / Sinkhorn --- */
+int dsir_gather_neighbours(const float *in, int B, int C, int N, const int64_t *idx, int M, int k, float *out,
+                           dsir_stream_t stream) {
+    if (!in || !idx || !out || B <= 0 || C <= 0 || N <= 0 || M < 0 || k <= 0) return DSIR_ERR_BAD_ARG;
+    return launch_gather_neighbours(in, B, C, N, idx, M, k, out, (cudaStream_t)stream);
+}
+
+int dsir_rel_pos_encoding(const float *xyz, int B, int N, const int64_t *idx, int k, float *out, dsir_stream_t stream) {
+    if (!xyz || !idx || !out || B <= 0 || N <= 0 || k <= 0) return DSIR_ERR_BAD_ARG;
+    return launch_rel_pos_encoding(xyz, B, N, idx, k, out, (cudaStream_t)stream);
+}
+
+int dsir_pool_max(const float *in, int B, int C, int N, const int64_t *idx, int M, int k, float *out, dsir_stream_t stream) {
+    if (!in || !idx || !out || B <= 0 || C <= 0 || N <= 0 || M < 0 || k <= 0) return DSIR_ERR_BAD_ARG;
+    return launch_pool_max(in, B, C, N, idx, M, k, out, (cudaStream_t)stream);
+}
+
+size_t dsir_sinkhorn_workspace_bytes(int B, int J, int K) {
+    if (B <= 0 || J <= 0 || K <= 0) return 256;
+    return ws_block((size_t)B * J * sizeof(float)) + ws_block((size_t)B * K * sizeof(float)) + 256;
+}
+
+int dsir_sinkhorn(const float *log_alpha, int B, int J, int K, int n_iters, int slack, float *out, void *ws, size_t ws_bytes,
+                  dsir_stream_t stream) {
+    if (!log_alpha || !out || B <= 0 || J <= 0 || K <= 0 || n_iters < 0) return DSIR_ERR_BAD_ARG;
+    Workspace W(ws, ws_bytes);
+    float *u = W.take<float>((size_t)B * J);
+    float *v = W.take<float>((size_t)B * K);
+    if (!W.ok()) return DSIR_ERR_WORKSPACE;
+    return launch_sinkhorn(log_alpha, B, J, K, n_iters, slack ? 1 : 0, out, u, v, (cudaStream_t)stream);
 }
 
 /* ------------------------------------------------------------------ Kabsch --------------------- */

@@ -130,6 +130,25 @@ int dsir_gather_points(const float *in, int B, int C, int N, const int64_t *idx,
                        dsir_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * KNN consumers of the RandLA-Net local aggregation (the stage right after the KNN pyramid) and Sinkhorn.
+ * All tensors contiguous.  Indices outside [0,N) (the -1 padding of a short neighbour list) read as 0 / are skipped.
+ * ---------------------------------------------------------------------------------------------- */
+/* gather_neighbour_V2 (network/tools.py:197-209): in [B,C,N], idx [B,M,k] int64 -> out [B,C,M,k] */
+int dsir_gather_neighbours(const float *in, int B, int C, int N, const int64_t *idx, int M, int k, float *out,
+                           dsir_stream_t stream);
+/* Building_block.relative_pos_encoding (network/RandLANet.py:197-212): xyz [B,3,N], idx [B,N,k] -> out [B,10,N,k] =
+ * { |rel|, rel(3) = neighbour - centre, centre(3), neighbour(3) } */
+int dsir_rel_pos_encoding(const float *xyz, int B, int N, const int64_t *idx, int k, float *out, dsir_stream_t stream);
+/* RandLA.random_sample (network/RandLANet.py:374-391): in [B,C,N], pool_idx [B,M,k] -> out [B,C,M] = max over the k
+ * gathered neighbours; the [B,C,M,k] intermediate is never written.  k <= 32. */
+int dsir_pool_max(const float *in, int B, int C, int N, const int64_t *idx, int M, int k, float *out, dsir_stream_t stream);
+/* sinkhorn (network/matchnet.py:211-271): log_alpha [B,J,K] -> out [B,J,K] after n_iters row/column normalisations in
+ * the log domain, with or without the slack row/column; out may alias log_alpha.  ws >= dsir_sinkhorn_workspace_bytes. */
+size_t dsir_sinkhorn_workspace_bytes(int B, int J, int K);
+int dsir_sinkhorn(const float *log_alpha, int B, int J, int K, int n_iters, int slack, float *out, void *ws, size_t ws_bytes,
+                  dsir_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Weighted Kabsch.  Replaces compute_rigid_transform_2 (network/model.py:22-66) including its host
  * round trip (fp64 LAPACK SVD at :47).  Points are addressed as p[b,m,i] = base[b*bs + m*ps + i*cs]
  * so both [B,M,3] (model.py:586) and [B,3,M] (the loop's layout) work without a transpose copy.

@@ -133,6 +133,33 @@ def gather_neighbour_V3(inputs, idx):
 # --------------------------------------------------------------------------------------
 # soft correspondence (network/matchnet.py)
 # --------------------------------------------------------------------------------------
+def gather_neighbour_V2(inputs, idx):
+    """network/tools.py:197-209.  inputs [B,C,N], idx [B,M,k] -> [B,C,M,k]."""
+    B, C, N = inputs.shape
+    k = idx.shape[-1]
+    flat = idx.reshape(B, -1)[:, None, :].expand(B, C, -1)
+    return torch.gather(inputs, 2, flat).reshape(B, C, -1, k)
+
+
+def relative_pos_encoding(xyz, idx):
+    """network/RandLANet.py:197-212.  xyz [B,3,N], idx [B,N,k] -> [B,10,N,k] = {|rel|, rel, centre, neighbour}."""
+    nb = gather_neighbour_V2(xyz, idx)
+    tile = xyz[:, :, :, None].expand(-1, -1, -1, idx.shape[-1])
+    rel = nb - tile
+    dis = torch.sqrt(torch.sum(torch.pow(rel, 2), dim=1, keepdim=True))
+    return torch.cat([dis, rel, tile, nb], dim=1)
+
+
+def random_sample(feature, pool_idx):
+    """network/RandLANet.py:374-391.  feature [B,C,N,1], pool_idx [B,M,k] -> [B,C,M,1]."""
+    return gather_neighbour_V2(feature.squeeze(3), pool_idx).max(dim=3, keepdim=True)[0]
+
+
+def nearest_interpolation(feature, interp_idx):
+    """network/RandLANet.py:393-408.  feature [B,C,N,1], interp_idx [B,M,1] -> [B,C,M,1]."""
+    return gather_neighbour_V3(feature.squeeze(3), interp_idx.reshape(interp_idx.shape[0], -1)).unsqueeze(3)
+
+
 def compute_affinity(beta, feat_distance, alpha=0.5):
     """network/matchnet.py:195-208:  -beta_b * (d - alpha_b)."""
     if isinstance(alpha, float):
@@ -153,8 +180,9 @@ def soft_correspondence(feat_src, feat_ref, xyz_ref, beta, alpha):
     return w, y, s[:, :, 0], lse[:, :, 0]
 
 
-def sinkhorn(log_alpha, n_iters=5, slack=True):
-    """network/matchnet.py:211-271 (eps early-exit disabled, as in every call site)."""
+def sinkhorn(log_alpha, n_iters=5, slack=True, eps=-1):
+    """network/matchnet.py:211-271 including the eps early exit (:246-251, :262-267)."""
+    prev = None
     if slack:
         la = torch.nn.functional.pad(log_alpha, (0, 1, 0, 1))
         for _ in range(n_iters):
@@ -162,11 +190,21 @@ def sinkhorn(log_alpha, n_iters=5, slack=True):
             la = torch.cat((top, la[:, -1:, :]), dim=1)
             left = la[:, :, :-1] - torch.logsumexp(la[:, :, :-1], dim=1, keepdim=True)
             la = torch.cat((left, la[:, :, -1:]), dim=2)
+            if eps > 0:
+                cur = torch.exp(la[:, :-1, :-1])
+                if prev is not None and torch.max(torch.sum(torch.abs(cur - prev), dim=[1, 2])) < eps:
+                    break
+                prev = cur.clone()
         return la[:, :-1, :-1]
     la = log_alpha
     for _ in range(n_iters):
         la = la - torch.logsumexp(la, dim=2, keepdim=True)
         la = la - torch.logsumexp(la, dim=1, keepdim=True)
+        if eps > 0:
+            cur = torch.exp(la)
+            if prev is not None and torch.max(torch.sum(torch.abs(cur - prev), dim=[1, 2])) < eps:
+                break
+            prev = cur.clone()
     return la
 
 

@@ -138,5 +138,35 @@ def main():
          transform_gt=b["transform_gt"])
 
 
+def graph():
+    """KNN consumers (network/tools.py, network/RandLANet.py) and larger Sinkhorn cases from the reference itself."""
+    from network import RandLANet as R_rla  # noqa: E402  (reference)
+    os.makedirs(OUT, exist_ok=True)
+    g = torch.Generator().manual_seed(11)
+    B, C, N, k = 2, 5, 300, 16
+    xyz = torch.randn(B, 3, N, generator=g) * 10
+    feat = torch.randn(B, C, N, generator=g)
+    idx = torch.randint(0, N, (B, N, k), generator=g)
+    pool = idx[:, :N // 4, :].contiguous()
+    interp = torch.randint(0, N // 4, (B, N, 1), generator=g)
+    sub_feat = torch.randn(B, C, N // 4, generator=g)
+    la = torch.randn(2, 37, 53, generator=g) * 3
+    save("graph_ops", xyz=xyz, feat=feat, idx=idx, pool=pool, interp=interp, sub_feat=sub_feat,
+         gather_v2=R_tools.gather_neighbour_V2(feat, idx),
+         gather_v1=R_tools.gather_neighbour(feat.permute(0, 2, 1).contiguous(), idx),
+         gather_v4=R_tools.gather_neighbour_V4(feat.permute(0, 2, 1).contiguous(), idx[:, :, 0].contiguous()),
+         rel_pos=R_rla.Building_block.relative_pos_encoding(xyz, idx),
+         pooled=R_rla.RandLA.random_sample(feat[:, :, :, None], pool),
+         interpolated=R_rla.RandLA.nearest_interpolation(sub_feat[:, :, :, None], interp),
+         log_alpha=la,
+         sinkhorn_slack_5=R_match.sinkhorn(la, n_iters=5, slack=True),
+         sinkhorn_noslack_3=R_match.sinkhorn(la, n_iters=3, slack=False),
+         sinkhorn_slack_eps=R_match.sinkhorn(la, n_iters=50, slack=True, eps=1e-2))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "graph":
+        graph()
+    else:
+        main()
+        graph()

@@ -451,3 +451,54 @@ def test_rowblock_sharding_on_one_device():
     assert torch.equal(torch.stack(pred_a), torch.stack(pred_b))
     for a, c in zip(tr_a, tr_b):
         assert_pose_close(a, c.cpu())
+
+
+# ------------------------------------------------------------------------------------------- KNN consumers / Sinkhorn
+def test_graph_ops_golden(golden):
+    """gather_neighbour[_V2/_V4], relative_pos_encoding, random_sample, nearest_interpolation against the reference's
+    own outputs: pure data movement and one subtraction/sqrt -> bit-exact."""
+    g = golden("graph_ops")
+    feat, idx, xyz = cu(g["feat"]), cu(g["idx"]), cu(g["xyz"])
+    assert torch.equal(D.gather_neighbour_V2(feat, idx).cpu(), g["gather_v2"])
+    assert torch.equal(D.gather_neighbour(feat.permute(0, 2, 1).contiguous(), idx).cpu(), g["gather_v1"])
+    assert torch.equal(D.gather_neighbour_V4(feat.permute(0, 2, 1).contiguous(), idx[:, :, 0].contiguous()).cpu(), g["gather_v4"])
+    rp = D.relative_pos_encoding(xyz, idx).cpu()
+    assert torch.equal(rp[:, 1:], g["rel_pos"][:, 1:])
+    assert torch.allclose(rp[:, 0], g["rel_pos"][:, 0], rtol=2e-7, atol=0)     # sqrt of a 3-term sum
+    assert torch.equal(D.random_sample(feat[:, :, :, None], cu(g["pool"])).cpu(), g["pooled"])
+    assert torch.equal(D.nearest_interpolation(cu(g["sub_feat"])[:, :, :, None], cu(g["interp"])).cpu(), g["interpolated"])
+
+
+def test_graph_ops_on_a_real_pyramid():
+    """The KNN pyramid's own index tensors feed the consumers (level-local indices, int64)."""
+    b = synth.make_batch(2, 4096, 8, "kitti", config=2, first_pair=5)
+    gph = D.nn_search_cloud(cu(b["points_src"]), 16, (4, 4, 4, 4))
+    n0 = 4096
+    xyz0 = gph["xyz"][:, :n0].permute(0, 2, 1).contiguous()
+    nb0 = gph["neigh_idx"][:, :n0]
+    rp = D.relative_pos_encoding(xyz0, nb0)
+    ref = O.relative_pos_encoding(xyz0.cpu(), nb0.cpu())
+    assert torch.equal(rp.cpu()[:, 1:], ref[:, 1:]) and torch.allclose(rp.cpu()[:, 0], ref[:, 0], rtol=2e-7, atol=0)
+    assert (rp[:, 0, :, 0] == 0).all()                      # the first neighbour of a point is the point itself
+    feat = cu(torch.randn(2, 32, n0, generator=torch.Generator().manual_seed(3)))
+    pooled = D.random_sample(feat[:, :, :, None], gph["sub_idx"][:, :n0 // 4])
+    assert torch.equal(pooled.cpu(), O.random_sample(feat.cpu()[:, :, :, None], gph["sub_idx"][:, :n0 // 4].cpu()))
+    up = D.nearest_interpolation(pooled, gph["interp_idx"][:, :n0])
+    assert up.shape == (2, 32, n0, 1)
+
+
+@pytest.mark.parametrize("shape", [(2, 37, 53), (1, 700, 650), (2, 5, 2000)])
+def test_sinkhorn_vs_oracle(golden, shape):
+    g = golden("graph_ops")
+    la = cu(g["log_alpha"])
+    assert torch.allclose(D.sinkhorn(la, 5, True).cpu(), g["sinkhorn_slack_5"], atol=1e-4, rtol=SOFT_RTOL)
+    assert torch.allclose(D.sinkhorn(la, 3, False).cpu(), g["sinkhorn_noslack_3"], atol=1e-4, rtol=SOFT_RTOL)
+    assert torch.allclose(D.sinkhorn(la, 50, True, eps=1e-2).cpu(), g["sinkhorn_slack_eps"], atol=1e-4, rtol=SOFT_RTOL)
+    B, J, K = shape
+    a = torch.randn(B, J, K, generator=torch.Generator().manual_seed(J)) * 4
+    for slack in (True, False):
+        out = D.sinkhorn(cu(a), 5, slack).cpu()
+        assert torch.allclose(out, O.sinkhorn(a, 5, slack), atol=1e-4, rtol=SOFT_RTOL)
+        # after the last column step every column of exp(out) (+ slack row) sums to 1: <= 1 without the slack entry
+        col = torch.exp(out).sum(dim=1)
+        assert (col <= 1 + 1e-4).all() and (slack or torch.allclose(col, torch.ones_like(col), atol=1e-4))

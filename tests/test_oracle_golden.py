@@ -166,3 +166,16 @@ def test_kdtree_baseline_agrees_with_exact_oracle():
     for key in ("neigh_idx", "sub_idx", "interp_idx"):
         assert a[key].shape == k[key].shape
         assert (a[key] == k[key]).float().mean() > 0.999, key
+
+
+def test_graph_ops_oracle_matches_reference_fixture(golden):
+    """KNN consumers (tools.py / RandLANet.py) and Sinkhorn incl. the eps early exit: oracle == reference output."""
+    g = golden("graph_ops")
+    assert torch.equal(O.gather_neighbour_V2(g["feat"], g["idx"]), g["gather_v2"])
+    assert torch.equal(O.gather_neighbour_V2(g["feat"], g["idx"]).permute(0, 2, 3, 1), g["gather_v1"])
+    assert torch.equal(O.relative_pos_encoding(g["xyz"], g["idx"]), g["rel_pos"])
+    assert torch.equal(O.random_sample(g["feat"][:, :, :, None], g["pool"]), g["pooled"])
+    assert torch.equal(O.nearest_interpolation(g["sub_feat"][:, :, :, None], g["interp"]), g["interpolated"])
+    assert torch.allclose(O.sinkhorn(g["log_alpha"], 5, True), g["sinkhorn_slack_5"], atol=2e-6, rtol=0)
+    assert torch.allclose(O.sinkhorn(g["log_alpha"], 3, False), g["sinkhorn_noslack_3"], atol=2e-6, rtol=0)
+    assert torch.allclose(O.sinkhorn(g["log_alpha"], 50, True, eps=1e-2), g["sinkhorn_slack_eps"], atol=2e-6, rtol=0)
