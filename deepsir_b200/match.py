@@ -131,16 +131,39 @@ def match_soft(feat_src, feat_ref, xyz_ref, beta, alpha=0.5, col_bias=None):
     beta = beta.to(torch.float32).contiguous()
     alpha_t = torch.full((B,), float(alpha), dtype=torch.float32, device=dev) if isinstance(alpha, float) \
         else alpha.to(torch.float32).contiguous()
-    xyz_ref = xyz_ref.contiguous()
+    xyz_ref = xyz_ref.contiguous() if xyz_ref is not None else None
     cb = col_bias.contiguous() if col_bias is not None else None
-    y = torch.empty(B, J, 3, dtype=torch.float32, device=dev)
+    y = torch.empty(B, J, 3, dtype=torch.float32, device=dev) if xyz_ref is not None else None
     lse = torch.empty(B, J, dtype=torch.float32, device=dev)
     lib = L.lib()
     ws = L.workspace(lib.dsir_match_soft_workspace_bytes(B, C, J, K), dev)
-    L.check(lib.dsir_match_soft(fs, fr, B, C, J, K, beta.data_ptr(), alpha_t.data_ptr(), L.ptr(cb), xyz_ref.data_ptr(),
-                                y.data_ptr(), lse.data_ptr(), 0, None, None, ws.data_ptr(), ws.numel(),
+    L.check(lib.dsir_match_soft(fs, fr, B, C, J, K, beta.data_ptr(), alpha_t.data_ptr(), L.ptr(cb), L.ptr(xyz_ref),
+                                L.ptr(y), lse.data_ptr(), 0, None, None, ws.data_ptr(), ws.numel(),
                                 L.stream_ptr(dev)), "dsir_match_soft")
     return y, torch.ones(B, J, dtype=torch.float32, device=dev), lse
+
+
+def sinkhorn_implicit(feat_src, feat_ref, xyz_ref, beta, alpha=0.5, n_iters=5, slack=True):
+    """Sinkhorn (network/matchnet.py:211-271) on the NEVER-MATERIALISED affinity a_jk = -beta (d_jk - alpha)
+    (matchnet.py:195-208) in its dual form: log P_jk = a_jk - u_j - v_k with
+        u_j = LSE_k(a_jk - v_k (, 0 with slack)),   v_k = LSE_j(a_jk - u_j (, 0 with slack)).
+    Every half-step is one fused distance + log-sum-exp sweep (dsir_match_soft with a column bias; the column step is
+    the same kernel with the roles of the two clouds swapped, since d_jk is symmetric).  Returns
+    (y_soft [B,J,3] = sum_k P_jk r_k / sum_k P_jk, rowmass [B,J] = sum_k P_jk, u [B,J], v [B,K]) -- the inputs of
+    kabsch_soft / compute_rigid_transform (network/model.py:68-116) -- without ever forming [B,J,K]."""
+    dev = L.require_cuda(feat_src, feat_ref, xyz_ref, beta)
+    B, C, J = feat_src.shape
+    K = feat_ref.shape[2]
+    u = torch.zeros(B, J, dtype=torch.float32, device=dev)
+    v = torch.zeros(B, K, dtype=torch.float32, device=dev)
+    zero = torch.zeros((), dtype=torch.float32, device=dev)
+    for _ in range(n_iters):
+        _, _, lse_r = match_soft(feat_src, feat_ref, None, beta, alpha, col_bias=-v)       # [B,J]
+        u = torch.logaddexp(lse_r, zero) if slack else lse_r
+        _, _, lse_c = match_soft(feat_ref, feat_src, None, beta, alpha, col_bias=-u)       # [B,K]
+        v = torch.logaddexp(lse_c, zero) if slack else lse_c
+    y, _, lse_r = match_soft(feat_src, feat_ref, xyz_ref, beta, alpha, col_bias=-v)
+    return y, torch.exp(lse_r - u), u, v
 
 
 def gather_neighbour_V3(inputs, neigh_idx):

@@ -502,3 +502,25 @@ def test_sinkhorn_vs_oracle(golden, shape):
         # after the last column step every column of exp(out) (+ slack row) sums to 1: <= 1 without the slack entry
         col = torch.exp(out).sum(dim=1)
         assert (col <= 1 + 1e-4).all() and (slack or torch.allclose(col, torch.ones_like(col), atol=1e-4))
+
+
+def test_sinkhorn_on_the_implicit_matrix():
+    """Sinkhorn over the never-materialised affinity equals the reference's sinkhorn() on the materialised
+    compute_affinity(match_features_V2()) matrix, and the soft targets / row masses feed the soft Kabsch."""
+    b = synth.make_batch(2, 600, 32, "3dmatch", config=3, first_pair=2)
+    fs, fr = b["feat_src"], b["feat_ref"][:, :, :500].contiguous()
+    xr = b["points_ref"][:, :500, :3].contiguous()
+    beta, alpha = torch.tensor([10.0, 6.0]), torch.tensor([0.5, 0.4])
+    for slack in (True, False):
+        logp = O.sinkhorn(O.compute_affinity(beta, O.match_features_V2(fs, fr), alpha), 5, slack)     # [B,J,K]
+        P = torch.exp(logp)
+        y, mass, u, v = D.sinkhorn_implicit(cu(fs), cu(fr), cu(xr), cu(beta), cu(alpha), n_iters=5, slack=slack)
+        mass_ref = P.sum(dim=2)
+        y_ref = (P @ xr) / (mass_ref[:, :, None] + 1e-16)
+        assert torch.allclose(mass.cpu(), mass_ref, rtol=5e-4, atol=1e-6)
+        assert torch.allclose(y.cpu(), y_ref, rtol=5e-4, atol=1e-4)
+        # duals reproduce the matrix itself
+        a = O.compute_affinity(beta, O.match_features_V2(fs, fr), alpha)
+        assert torch.allclose(a - u.cpu()[:, :, None] - v.cpu()[:, None, :], logp, atol=2e-3, rtol=0)
+    T, inv = D.kabsch_soft(cu(b["points_src"][:, :, :3].contiguous()), y, mass)
+    assert not bool(inv) and T.shape == (2, 3, 4)
