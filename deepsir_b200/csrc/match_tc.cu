@@ -245,8 +245,17 @@ __device__ __forceinline__ void tmem_ld4_sync(uint32_t taddr, float (&x)[4]) {
 // (20 FMNMX/FMNMX3) and ONE vote.  Whenever some lane of the warp sees a value within `margin` of its running minimum,
 // the slow path re-reads only the flagged QUADS from TMEM (four values in registers with static indices) and updates
 // the candidate list of the lanes concerned; the hot loop carries no per-element branches.
+// LAST: this is the unit's final step, every tcgen05.ld of the accumulator has completed -> the accumulator goes back to
+// the MMA issuer as soon as the vote says that nothing has to be re-read from TMEM (or right after the re-reads).
+__device__ __forceinline__ void release_acc(uint64_t *empty_bar, int lane) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar);
+}
+template <bool LAST>
 __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint32_t taddr, float margin, float &thr,
-                                         float (&cv)[TC_T], int (&ci)[TC_T], bool sample, float &best) {
+                                         float (&cv)[TC_T], int (&ci)[TC_T], bool sample, float &best,
+                                         uint64_t *empty_bar = nullptr, int lane = 0) {
 #define F(i) __uint_as_float(v[i])
     const float a0 = fmin3(F(0), F(1), F(2)), a1 = fmin3(F(3), F(4), F(5)), a2 = fmin3(F(6), F(7), F(8));
     const float a3 = fmin3(F(9), F(10), F(11)), a4 = fmin3(F(12), F(13), F(14)), a5 = fmin3(F(15), F(16), F(17));
@@ -255,10 +264,13 @@ __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint
     const float b0 = fmin3(a0, a1, a2), b1 = fmin3(a3, a4, a5), b2 = fmin3(a6, a7, a8), b3 = fmin3(a9, F(30), F(31));
     const float mm = fminf(fmin3(b0, b1, b2), b3);
     if (sample) {              // priming pass: only the value of the running minimum, no candidates, no branches
+        if (LAST) release_acc(empty_bar, lane);
         best = fminf(best, mm);
         return;
     }
-    if (__any_sync(0xffffffffu, mm < thr)) {
+    const bool slow = __any_sync(0xffffffffu, mm < thr);
+    if (LAST && !slow) release_acc(empty_bar, lane);
+    if (slow) {
         unsigned qm = 0;       // which aligned column quads hold a value below the threshold
 #pragma unroll
         for (int g = 0; g < 8; ++g)
@@ -277,6 +289,7 @@ __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint
                     if (x[e] < thr) cand_update(cv, ci, x[e], col0 + 4 * g + e, margin, thr);
             }
         }
+        if (LAST) release_acc(empty_bar, lane);
     }
 }
 
@@ -457,18 +470,19 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                     tmem_wait32(va);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 1] = (unsigned int)clock64();
                     tmem_ld32(tbase + (g + 1) * 32, vb);
-                    filter32(va, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci, sample, best);
+                    filter32<false>(va, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci, sample, best);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 2] = (unsigned int)clock64();
                     tmem_wait32(vb);
                     if (g + 2 < TC_STEPS) tmem_ld32(tbase + (g + 2) * 32, va);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 3] = (unsigned int)clock64();
-                    filter32(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best);
+                    if (g + 2 < TC_STEPS)
+                        filter32<false>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best);
+                    else   // last step: the accumulator is handed back from inside (right after the vote)
+                        filter32<true>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best,
+                                       &tmem_empty[pa.stage * TC_RBS + r], lane);
                 }
                 if (tracing && useq < 256) P.trace[1024 + useq * 8 + 4] = (unsigned int)clock64();
                 if (t == us.ns - 1 && !(P.dbg_flags & 1)) thr = best + margin;   // primed: every row has seen a value <= best
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[pa.stage * TC_RBS + r]);
                 if (tracing && useq < 256) P.trace[1024 + useq * 8 + 5] = (unsigned int)clock64();
                 ++useq;
                 pa.advance(TC_ACC_STAGES);

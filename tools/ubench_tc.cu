@@ -131,6 +131,8 @@ __global__ __launch_bounds__(640, 1) void ubench(int mode, int variant, int read
                 case 5: issue(integral_constant<int, 256>{}, integral_constant<bool, true>{}, integral_constant<int, 4>{}, integral_constant<bool, false>{}, 0); break;
                 case 7: issue(integral_constant<int, 128>{}, integral_constant<bool, true>{}, integral_constant<int, 5>{}, integral_constant<bool, false>{}, 1); break;
                 case 8: issue(integral_constant<int, 128>{}, integral_constant<bool, true>{}, integral_constant<int, 5>{}, integral_constant<bool, false>{}, 2); break;
+                case 9: issue(integral_constant<int, 64>{}, integral_constant<bool, true>{}, integral_constant<int, 5>{}, integral_constant<bool, false>{}, 0); break;
+                case 10: issue(integral_constant<int, 32>{}, integral_constant<bool, true>{}, integral_constant<int, 5>{}, integral_constant<bool, false>{}, 0); break;
                 default: issue(integral_constant<int, 128>{}, integral_constant<bool, true>{}, integral_constant<int, 5>{}, integral_constant<bool, false>{}, 0); break;
             }
             tc_commit(&bar);
@@ -220,6 +222,9 @@ int main() {
         run("mma f16 SS M128 N128 K80", 1, 6, 0, 8000, 0, 0, grid);
         run("mma f16 K80, 5th step SW32 tile", 1, 7, 0, 8000, 0, 0, grid);
         run("mma f16 K80, alternating accumulators", 1, 8, 0, 8000, 0, 0, grid);
+        run("mma f16 SS M128 N64 K80", 1, 9, 0, 8000, 0, 0, grid);
+        run("mma f16 SS M128 N32 K80", 1, 10, 0, 8000, 0, 0, grid);
+        run("mma f16 N64 K80 + ld+min3 16 warps", 3, 9, 16, 8000, 350, 1, grid);
         run("mma f16 N128 K80 + ld+min3 16 warps", 3, 6, 16, 8000, 700, 1, grid);
         run("mma f16 N128 K80 + ld+min3 8 warps", 3, 6, 8, 8000, 1400, 1, grid);
         run("mma f16 N256 K64 + ld+min3 16 warps", 3, 5, 16, 4000, 700, 1, grid);
