@@ -10,7 +10,7 @@ from .match import (square_distance, square_distance_V2, match_features, match_f
                     match_argmin, match_soft, sinkhorn_implicit, compute_affinity, gather_neighbour_V3)
 from .kabsch import (compute_rigid_transform, compute_rigid_transform_2, kabsch_gather, kabsch_moments,  # noqa: F401
                      kabsch_from_moments, kabsch_soft)
-from .knn import knn, nn_search, nn_search_cloud  # noqa: F401
+from .knn import knn, nn_search, nn_search_cloud, nn_search_pair  # noqa: F401
 from .loop import align_loop, pred_pairs  # noqa: F401
 from .pipeline import RegistrationPipeline  # noqa: F401
 from .graph import (gather_neighbour, gather_neighbour_V2, gather_neighbour_V4, relative_pos_encoding, random_sample,  # noqa: F401

@@ -28,7 +28,7 @@ def knn(pos_support, pos, k, algo=L.KNN_AUTO):
     return idx, d2
 
 
-def nn_search_cloud(points, num_knn=16, sub_sampling_ratio=(4, 4, 4, 4), algo=L.KNN_AUTO):
+def nn_search_cloud(points, num_knn=16, sub_sampling_ratio=(4, 4, 4, 4), algo=L.KNN_AUTO, _stream=None, _keep=None):
     """One cloud tensor [B,N,C>=3] -> dict(xyz, neigh_idx, sub_idx, interp_idx), the four tensors
     DataBase.nn_search (data_base.py:179-182) attaches per cloud.  One library call for the whole pyramid."""
     dev = L.require_cuda(points)
@@ -52,15 +52,41 @@ def nn_search_cloud(points, num_knn=16, sub_sampling_ratio=(4, 4, 4, 4), algo=L.
     ws = L.workspace(lib.dsir_knn_pyramid_workspace_bytes(B, N, num_knn, ctypes.addressof(rat), Lv, algo), dev)
     L.check(lib.dsir_knn_pyramid(p.data_ptr(), S, B, N, ctypes.addressof(rat), Lv, num_knn, xyz.data_ptr(),
                                  neigh.data_ptr(), sub.data_ptr(), interp.data_ptr(), ws.data_ptr(), ws.numel(), algo,
-                                 L.stream_ptr(dev)), "dsir_knn_pyramid")
+                                 L.stream_ptr(dev) if _stream is None else _stream.cuda_stream), "dsir_knn_pyramid")
+    if _keep is not None:
+        _keep += [ws, p]   # the caller frees them after it has joined `_stream`
     return dict(xyz=xyz, neigh_idx=neigh, sub_idx=sub, interp_idx=interp)
+
+
+_side_streams = {}
+
+
+def nn_search_pair(points_src, points_ref, num_knn=16, sub_sampling_ratio=(4, 4, 4, 4), algo=L.KNN_AUTO):
+    """Both pyramids of a pair batch at once: the source pyramid on the caller's stream, the reference pyramid on a side
+    stream that forks from and joins back into it.  The two are independent (data_base.py:157 loops over the two keys), and
+    the small launches of the coarse levels of one fill the tail of the other.  Returns (graph_src, graph_ref)."""
+    dev = L.require_cuda(points_src, points_ref)
+    cur = torch.cuda.current_stream(dev)
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(dev)
+    # Outputs and workspace of BOTH pyramids are allocated on the caller's stream (no cross-stream ownership for the
+    # caching allocator to track); only the kernels of the reference pyramid run on the side stream, between a fork
+    # (side waits for everything enqueued so far) and a join (the caller's stream waits for the side stream).
+    keep = []
+    side.wait_stream(cur)                                                       # fork
+    g_ref = nn_search_cloud(points_ref, num_knn, sub_sampling_ratio, algo, _stream=side, _keep=keep)
+    g_src = nn_search_cloud(points_src, num_knn, sub_sampling_ratio, algo)
+    cur.wait_stream(side)                                                       # join
+    del keep   # workspace of the side pyramid: released only now, so its next user on `cur` is ordered after the join
+    return g_src, g_ref
 
 
 def nn_search(data_list_stack, num_knn=16, sub_sampling_ratio=(4, 4, 4, 4), algo=L.KNN_AUTO):
     """DataBase.nn_search (data_base.py:153-183) on a dict already moved to the device: adds
     '<k>_xyz', '<k>_neigh_idx', '<k>_sub_idx', '<k>_interp_idx' for k in points_src, points_ref."""
-    for k in ["points_src", "points_ref"]:
-        r = nn_search_cloud(data_list_stack[k], num_knn, sub_sampling_ratio, algo)
+    pair = nn_search_pair(data_list_stack["points_src"], data_list_stack["points_ref"], num_knn, sub_sampling_ratio, algo)
+    for k, r in zip(["points_src", "points_ref"], pair):
         data_list_stack[k + "_xyz"] = r["xyz"]
         data_list_stack[k + "_neigh_idx"] = r["neigh_idx"]
         data_list_stack[k + "_sub_idx"] = r["sub_idx"]

@@ -13,7 +13,7 @@ from collections import deque
 import torch
 
 from . import _lib as L
-from .knn import nn_search_cloud
+from .knn import nn_search_pair
 from .loop import align_loop
 
 
@@ -44,8 +44,7 @@ class RegistrationPipeline:
 
     def _compute(self, d, up, compute):
         compute.wait_event(up)
-        g_src = nn_search_cloud(d["points_src"], self.k, self.ratios)
-        g_ref = nn_search_cloud(d["points_ref"], self.k, self.ratios)
+        g_src, g_ref = nn_search_pair(d["points_src"], d["points_ref"], self.k, self.ratios)
         xs = d["points_src"][:, :, :3].permute(0, 2, 1).contiguous()   # the loop's [B,3,N] layout (model.py:541-549)
         xr = d["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
         tr, pred, _, status = align_loop(d["feat_src"], d["feat_ref"], xs, xr, d["weights"], self.iters)
