@@ -122,6 +122,34 @@ int dsir_profile_report(char *buf, size_t buf_bytes) {
 /* ------------------------------------------------------------------ KNN ------------------------ */
 namespace {
 
+// Fork/join helper for the independent query launches of one pyramid.  The levels of a pyramid only share the grids
+// (built first, on the caller's stream); the big level-0 self-kNN stays on the caller's stream, the coarse levels and
+// the 1-NN up-sampling queries go to library-owned auxiliary streams so that their small grids fill the tail of the big
+// launch instead of running one after the other.  Per host thread and device: 4 non-blocking streams used round-robin
+// and a ring of timing-less events.  Everything forked is joined back before the entry point returns, so the caller
+// still sees ONE stream (also under CUDA-graph capture, where fork/join by events is the supported pattern).
+struct AuxStreams {
+    static constexpr int NS = 4, NE = 32;
+    int dev = -1;
+    cudaStream_t s[NS] = {};
+    cudaEvent_t e[NE] = {};
+    int next_s = 0, next_e = 0;
+    bool ready(int device) {
+        if (dev == device) return true;
+        if (dev != -1) return false;   // one device per host thread (one process per GPU); otherwise stay single-stream
+        for (int i = 0; i < NS; ++i)
+            if (cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+        for (int i = 0; i < NE; ++i)
+            if (cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+        dev = device;
+        return true;
+    }
+    cudaStream_t stream() { cudaStream_t r = s[next_s]; next_s = (next_s + 1) % NS; return r; }
+    cudaEvent_t event() { cudaEvent_t r = e[next_e]; next_e = (next_e + 1) % NE; return r; }
+};
+thread_local AuxStreams g_aux;
+const bool KNN_FORK = getenv("DSIR_KNN_NOFORK") == nullptr;
+
 struct GridSlot {
     KnnGridHeader *hdr;
     int *cell_start;
@@ -289,9 +317,33 @@ int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *r
         return nullptr;
     };
 
+    // fork: level-0 self-kNN stays on `st`; coarser self-kNNs -> aux stream A, every 1-NN up-sampling -> aux stream B
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool fork = KNN_FORK && L > 1 && g_aux.ready(dev);
+    cudaStream_t st_main = st, st_self = st, st_up = st;
+    if (fork) {
+        cudaEvent_t ev = g_aux.event();
+        st_self = g_aux.stream();
+        st_up = g_aux.stream();
+        DSIR_CUDA_TRY(cudaEventRecord(ev, st_main));
+        DSIR_CUDA_TRY(cudaStreamWaitEvent(st_self, ev, 0));
+        DSIR_CUDA_TRY(cudaStreamWaitEvent(st_up, ev, 0));
+    }
+    auto join = [&]() -> int {
+        if (!fork) return DSIR_OK;
+        cudaEvent_t e1 = g_aux.event(), e2 = g_aux.event();
+        DSIR_CUDA_TRY(cudaEventRecord(e1, st_self));
+        DSIR_CUDA_TRY(cudaEventRecord(e2, st_up));
+        DSIR_CUDA_TRY(cudaStreamWaitEvent(st_main, e1, 0));
+        DSIR_CUDA_TRY(cudaStreamWaitEvent(st_main, e2, 0));
+        return DSIR_OK;
+    };
+
     for (int l = 0; l < L; ++l) {
         const GridSlot *gl = find_slot(lv.n[l]);   // grid over the level cloud (support of the self-kNN, query order)
         const GridSlot *gm = find_slot(lv.m[l]);   // grid over the sub-cloud (support of the 1-NN up-sampling)
+        st = l == 0 ? st_main : st_self;
         int64_t *nb = neigh + (size_t)lv.off[l] * k;
         int64_t *pool = sub + (size_t)lv.offsub[l] * k;
         int64_t *up = interp + lv.off[l];
@@ -303,7 +355,7 @@ int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *r
             Q.Nq = lv.n[l]; Q.k = k; Q.r0_cells = GRID_R0_CELLS;
             Q.idx = nb; Q.idx_bs = (long long)lv.sumN * k;
             Q.idx2 = pool; Q.idx2_bs = (long long)lv.sumSub * k; Q.idx2_rows = lv.m[l];
-            if ((rc = launch_knn_grid_query(Q, B, st))) return rc;
+            if ((rc = launch_knn_grid_query(Q, B, st))) { join(); return rc; }
         } else {
             KnnBruteParams P{};
             P.sup4 = pts4; P.sup_bs = N;
@@ -311,9 +363,10 @@ int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *r
             P.Ns = lv.n[l]; P.Nq = lv.n[l]; P.k = k;
             P.idx = nb; P.idx_bs = (long long)lv.sumN * k;
             P.idx2 = pool; P.idx2_bs = (long long)lv.sumSub * k; P.idx2_rows = lv.m[l];
-            if ((rc = launch_knn_brute(P, B, st))) return rc;
+            if ((rc = launch_knn_brute(P, B, st))) { join(); return rc; }
         }
         // ---- 1-NN of every level point into the sub-cloud (data_base.py:170) ----
+        st = st_up;
         if (gm) {
             KnnGridQueryParams Q{};
             Q.hdr = gm->hdr; Q.cell_start = gm->cell_start; Q.sorted = gm->sorted; Q.gmax = KNN_GRID_GMAX; Q.Ns = lv.m[l];
@@ -321,17 +374,17 @@ int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *r
             else { Q.query = (const float *)pts4; Q.qry_bs = (long long)N * 4; Q.qry_stride = 4; }
             Q.Nq = lv.n[l]; Q.k = 1; Q.r0_cells = GRID_R0_CELLS;
             Q.idx = up; Q.idx_bs = lv.sumN;
-            if ((rc = launch_knn_grid_query(Q, B, st))) return rc;
+            if ((rc = launch_knn_grid_query(Q, B, st))) { join(); return rc; }
         } else {
             KnnBruteParams U{};
             U.sup4 = pts4; U.sup_bs = N;
             U.query = (const float *)pts4; U.qry_bs = (long long)N * 4; U.qry_stride = 4;
             U.Ns = lv.m[l]; U.Nq = lv.n[l]; U.k = 1;
             U.idx = up; U.idx_bs = lv.sumN;
-            if ((rc = launch_knn_brute(U, B, st))) return rc;
+            if ((rc = launch_knn_brute(U, B, st))) { join(); return rc; }
         }
     }
-    return DSIR_OK;
+    return join();
 }
 
 /* ------------------------------------------------------------------ match ---------------------- */
