@@ -15,6 +15,8 @@ from .loop import align_loop, pred_pairs  # noqa: F401
 from .pipeline import RegistrationPipeline  # noqa: F401
 from .graph import (gather_neighbour, gather_neighbour_V2, gather_neighbour_V4, relative_pos_encoding, random_sample,  # noqa: F401
                     nearest_interpolation, sinkhorn)
+from .keypoint import score_fun, feat_score, topk  # noqa: F401
+from . import metrics  # noqa: F401
 from . import se3 as se3_torch  # noqa: F401
 from . import se3, synth  # noqa: F401
 

@@ -16,7 +16,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libdeepsir_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
-SOURCES = ["api.cu", "knn.cu", "knn_grid.cu", "match_fp32.cu", "match_tc.cu", "kabsch.cu", "graph.cu"]
+SOURCES = ["api.cu", "knn.cu", "knn_grid.cu", "match_fp32.cu", "match_tc.cu", "kabsch.cu", "graph.cu", "keypoint.cu", "metrics.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -117,6 +117,19 @@ _SIGS = {
     "dsir_align_loop": (_c.c_int, [Feat, Feat, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                    _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                    _c.c_size_t, _c.c_int, _c.c_void_p]),
+    "dsir_keypoint_score_workspace_bytes": (_c.c_size_t, [_c.c_int] * 3),
+    "dsir_keypoint_score": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,
+                                       _c.c_int, _c.c_int, _c.c_float, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                       _c.c_size_t, _c.c_void_p]),
+    "dsir_topk_rows": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "dsir_pose_errors": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p,
+                                    _c.c_void_p]),
+    "dsir_correspondence_check_workspace_bytes": (_c.c_size_t, [_c.c_int64]),
+    "dsir_correspondence_check": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
+                                             _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "dsir_nn_sqdist_workspace_bytes": (_c.c_size_t, [_c.c_int]),
+    "dsir_nn_sqdist_mean": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                       _c.c_void_p, _c.c_size_t, _c.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
 

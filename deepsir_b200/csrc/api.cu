@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "graph.cuh"
 #include "kabsch.cuh"
+#include "keypoint.cuh"
+#include "metrics.cuh"
 #include "knn.cuh"
 #include "match.cuh"
 #include "match_tc.cuh"
@@ -652,6 +654,55 @@ int dsir_align_loop(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, floa
         if (rc) return rc;
     }
     return DSIR_OK;
+}
+
+/* ------------------------------------------------------------------ key points, evaluation ---- */
+size_t dsir_keypoint_score_workspace_bytes(int B, int C, int N) {
+    if (B <= 0 || C <= 0 || N <= 0) return 0;
+    return keypoint_score_workspace_bytes(B, C, N);
+}
+
+int dsir_keypoint_score(const float *feat, const float *xyz, const float *prob, const int64_t *label,
+                        const float *label_weights, int num_class, const int64_t *neigh_idx, int idx_stride, int k,
+                        float ball_r, int B, int C, int N, float *score, void *ws, size_t ws_bytes, dsir_stream_t stream) {
+    if (!feat || !xyz || !neigh_idx || !score || B <= 0 || C <= 0 || N <= 0 || k <= 0 || idx_stride < k) return DSIR_ERR_BAD_ARG;
+    if (label && (!label_weights || num_class <= 0)) return DSIR_ERR_BAD_ARG;
+    if (k > 32) return DSIR_ERR_UNSUPPORTED;
+    return launch_keypoint_score(feat, xyz, prob, label, label_weights, num_class, neigh_idx, idx_stride, k, ball_r, B, C, N,
+                                 score, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int dsir_topk_rows(const float *score, int B, int N, int k, float *values, int64_t *index, dsir_stream_t stream) {
+    if (!score || !values || !index || B <= 0 || N <= 0 || k <= 0 || k > N) return DSIR_ERR_BAD_ARG;
+    if (k > 16384 || N >= (1 << 30)) return DSIR_ERR_UNSUPPORTED;
+    return launch_topk_rows(score, B, N, k, values, index, (cudaStream_t)stream);
+}
+
+int dsir_pose_errors(const float *T_pred, const float *T_gt, int B, float rte_thresh, float rre_thresh, float *out,
+                     int32_t *success, dsir_stream_t stream) {
+    if (!T_pred || !T_gt || !out || B <= 0) return DSIR_ERR_BAD_ARG;
+    return launch_pose_errors(T_pred, T_gt, B, rte_thresh, rre_thresh, out, success, (cudaStream_t)stream);
+}
+
+size_t dsir_correspondence_check_workspace_bytes(int64_t total_pos) {
+    return total_pos < 0 ? 0 : correspondence_check_workspace_bytes(total_pos);
+}
+
+int dsir_correspondence_check(const int32_t *pos_pairs, const int64_t *pos_offsets, int64_t total_pos,
+                              const int32_t *pred_pairs, int B, int N, const int64_t *hash_seed, uint8_t *correct, void *ws,
+                              size_t ws_bytes, dsir_stream_t stream) {
+    if (!pos_offsets || !pred_pairs || !hash_seed || !correct || B <= 0 || N <= 0 || total_pos < 0 || (total_pos > 0 && !pos_pairs))
+        return DSIR_ERR_BAD_ARG;
+    return launch_correspondence_check(pos_pairs, pos_offsets, total_pos, pred_pairs, B, N, hash_seed, correct, ws, ws_bytes,
+                                       (cudaStream_t)stream);
+}
+
+size_t dsir_nn_sqdist_workspace_bytes(int B) { return B <= 0 ? 0 : nn_sqdist_workspace_bytes(B); }
+
+int dsir_nn_sqdist_mean(const float *a, const float *b, int B, int N, int M, float *min_d, float *mean, void *ws,
+                        size_t ws_bytes, dsir_stream_t stream) {
+    if (!a || !b || B <= 0 || N <= 0 || M <= 0 || (!min_d && !mean)) return DSIR_ERR_BAD_ARG;
+    return launch_nn_sqdist_mean(a, b, B, N, M, min_d, mean, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -202,6 +202,43 @@ int dsir_align_loop(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, floa
                     const float *weights, int iters, float *transforms, int64_t *pred_idx, int32_t *status,
                     void *ws, size_t ws_bytes, int algo, dsir_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Key-point scoring and selection on the KNN graph.
+ * dsir_keypoint_score = Network.score_fun (network/model.py:700-757):
+ *   feat [B,C,N], xyz [B,3,N], prob [B,N] (NULL: no probability gate), label [B,N] int64 (NULL: semantic score 1),
+ *   label_weights [num_class] (model.py:146-150), neigh_idx [B,N,idx_stride] int64 of which the first k (<= 32; the
+ *   reference uses 16) are read, ball_r (2.0 in the reference)  ->  score [B,N]
+ * dsir_topk_rows = torch.topk(score, k, dim=-1, largest=True) (model.py:692): values/index [B,k], descending, ties to the
+ *   LOWER index, NaN first.  k <= 16384.
+ * ---------------------------------------------------------------------------------------------- */
+size_t dsir_keypoint_score_workspace_bytes(int B, int C, int N);
+int dsir_keypoint_score(const float *feat, const float *xyz, const float *prob, const int64_t *label,
+                        const float *label_weights, int num_class, const int64_t *neigh_idx, int idx_stride, int k,
+                        float ball_r, int B, int C, int N, float *score, void *ws, size_t ws_bytes, dsir_stream_t stream);
+int dsir_topk_rows(const float *score, int B, int N, int k, float *values, int64_t *index, dsir_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * On-device evaluation of a registration result.
+ * dsir_pose_errors: T_pred, T_gt [B,3,4] -> out [B,4] = { err_r_deg, err_t  (common/metrics_util.py:55-61: residual of
+ *   inverse(gt) o pred), rre_deg, rte (metrics_util.py:27-33 rte_rre) }, success [B] int32 (may be NULL) =
+ *   err_t < rte_thresh && err_r_deg < rre_thresh (metrics_util.py:63).
+ * dsir_correspondence_check = Loss.find_correct_correspondence (network/loss.py:723-749): pos_pairs = the ground-truth
+ *   pair lists of the batch concatenated [total,2] int32 with pos_offsets [B+1] int64 (device), pred_pairs [B,N,2] int32
+ *   (model.py:599-601), hash_seed [B] int64 (device; loss.py:738-742)  ->  correct [B,N] uint8 = np.isin(key(pred),
+ *   key(pos)) with key = a0 + a1 * seed (loss.py:280-294).
+ * dsir_nn_sqdist_mean: a [B,N,3], b [B,M,3] -> min_d [B,N] (may be NULL) = min_k |a_j - b_k|^2 by direct differences and
+ *   mean [B] (may be NULL): one side of the modified chamfer distance (metrics_util.py:38-40, 72-74).
+ * ---------------------------------------------------------------------------------------------- */
+int dsir_pose_errors(const float *T_pred, const float *T_gt, int B, float rte_thresh, float rre_thresh, float *out,
+                     int32_t *success, dsir_stream_t stream);
+size_t dsir_correspondence_check_workspace_bytes(int64_t total_pos);
+int dsir_correspondence_check(const int32_t *pos_pairs, const int64_t *pos_offsets, int64_t total_pos,
+                              const int32_t *pred_pairs, int B, int N, const int64_t *hash_seed, uint8_t *correct, void *ws,
+                              size_t ws_bytes, dsir_stream_t stream);
+size_t dsir_nn_sqdist_workspace_bytes(int B);
+int dsir_nn_sqdist_mean(const float *a, const float *b, int B, int N, int M, float *min_d, float *mean, void *ws,
+                        size_t ws_bytes, dsir_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

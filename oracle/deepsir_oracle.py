@@ -211,6 +211,92 @@ def sinkhorn(log_alpha, n_iters=5, slack=True, eps=-1):
 # --------------------------------------------------------------------------------------
 # SE(3) (common/math/se3_torch.py)
 # --------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------------------
+# key-point scoring / selection (network/model.py:668-757) and evaluation (loss.py:723-749, metrics_util.py:27-85)
+# ---------------------------------------------------------------------------------------------------------
+_EPS = 1e-16   # network/model.py:18
+
+
+def score_fun(feat, xyz, prob, label, neigh_idx, label_weights, k_neighbors=16, ball_r=2.0):
+    """network/model.py:700-757, statement by statement."""
+    batch = feat.shape[0]
+    neigh_idx = neigh_idx[:, :, :k_neighbors]
+    max_per_sample = torch.max(feat.reshape(batch, -1), dim=1, keepdim=True)[0]
+    feat_norm = feat / (max_per_sample.view(batch, 1, 1) + _EPS)
+    neighbor_feat = torch.mean(gather_neighbour_V2(feat_norm, neigh_idx), dim=3)
+    local_max_score = torch.nn.functional.softplus(feat_norm - neighbor_feat)
+    neighbor_xyz = gather_neighbour_V2(xyz, neigh_idx)
+    relative_xyz = torch.norm(neighbor_xyz - xyz.unsqueeze(-1), dim=1, keepdim=True)
+    relative_xyz = torch.mean(relative_xyz, dim=-1)
+    aggregation_score = (relative_xyz < ball_r).float()
+    depth_wise_max = torch.max(feat_norm, dim=1, keepdim=True)[0]
+    depth_wise_max_score = feat_norm / (depth_wise_max + _EPS)
+    lw = torch.as_tensor(label_weights, dtype=torch.float32)
+    label_score = lw[label.reshape(-1).long()].view(batch, 1, xyz.shape[-1])
+    label_score = label_score / (torch.max(label_score, dim=-1, keepdim=True)[0] + _EPS)
+    prob = prob / (torch.max(prob, dim=-1, keepdim=True)[0] + _EPS)
+    label_score = label_score * torch.gt(prob, 0.2)
+    score = local_max_score * aggregation_score * depth_wise_max_score * label_score
+    return torch.max(score, dim=1)[0]
+
+
+def topk_lower_index(score, k):
+    """torch.topk(score, k, largest=True) (model.py:692) with the tie order fixed: equal values by ascending index."""
+    B, N = score.shape
+    vals, idxs = [], []
+    for b in range(B):
+        s = score[b].numpy()
+        order = np.lexsort((np.arange(N), -s))     # primary: value descending, secondary: index ascending
+        idxs.append(torch.from_numpy(order[:k].astype(np.int64)))
+        vals.append(score[b][idxs[-1]])
+    return torch.stack(vals), torch.stack(idxs)
+
+
+def pair_hash(arr, M):
+    """network/loss.py:280-294 for an [N,2] array."""
+    arr = np.asarray(arr).astype(np.int64)
+    return arr[:, 0] + arr[:, 1] * int(M)
+
+
+def find_correct_correspondence(pos_pairs, pred_pairs, hash_seed=None, len_batch=None):
+    """network/loss.py:723-749."""
+    out = []
+    for i in range(len(pos_pairs)):
+        seed = max(len_batch[i]) if hash_seed is None else hash_seed
+        out.append(np.isin(pair_hash(pred_pairs[i], seed), pair_hash(pos_pairs[i], seed), assume_unique=False))
+    return np.stack(out, axis=0)
+
+
+def rte_rre(T_pred, T_gt, eps=1e-16):
+    """common/metrics_util.py:27-33 (numpy, in the dtype of the inputs like the reference: test.py:432-433 passes fp32)."""
+    T_pred, T_gt = np.asarray(T_pred), np.asarray(T_gt)
+    rte = np.linalg.norm(T_pred[:3, 3] - T_gt[:3, 3])
+    rre = np.arccos(np.clip((np.trace(T_pred[:3, :3].T @ T_gt[:3, :3]) - 1) / 2, -1 + eps, 1 - eps)) * 180 / np.pi
+    return rte, rre
+
+
+def pose_residuals(pred, gt, eps=1e-16):
+    """common/metrics_util.py:55-61."""
+    c = se3_concatenate(se3_inverse(gt), pred)
+    tr = c[:, 0, 0] + c[:, 1, 1] + c[:, 2, 2]
+    deg = torch.acos(torch.clamp(0.5 * (tr - 1), min=-1 + eps, max=1 - eps)) * 180.0 / np.pi
+    return deg, c[:, :, 3].norm(dim=-1)
+
+
+def nn_sqdist(a, b):
+    """common/metrics_util.py:38-40 + the row minimum of :72-73."""
+    d = torch.sum((a[:, :, None, :] - b[:, None, :, :]) ** 2, dim=-1)
+    return torch.min(d, dim=-1)[0]
+
+
+def chamfer(points_src, points_ref, points_raw, pred, gt):
+    """common/metrics_util.py:66-74."""
+    src_transformed = se3_transform(pred, points_src)
+    inter = se3_concatenate(pred, se3_inverse(gt))
+    src_clean = se3_transform(inter, points_raw)
+    return torch.mean(nn_sqdist(src_transformed, points_raw), dim=1) + torch.mean(nn_sqdist(points_ref, src_clean), dim=1)
+
+
 def se3_identity(batch):
     """se3_torch.py:6-7."""
     return torch.eye(3, 4)[None].repeat(batch, 1, 1)

@@ -164,9 +164,60 @@ def graph():
          sinkhorn_slack_eps=R_match.sinkhorn(la, n_iters=50, slack=True, eps=1e-2))
 
 
+def keypoint_eval():
+    """score_fun / feat_score (model.py:668-757), find_correct_correspondence (loss.py:723-749), compute_metrics and rte_rre
+    (metrics_util.py:27-85) run from the reference on seeded inputs."""
+    import types
+    from network import loss as R_loss
+    from common import metrics_util as R_met
+    from oracle import deepsir_oracle as O
+    from scipy.spatial.transform import Rotation
+    if not hasattr(Rotation, "from_dcm"):      # removed from scipy >= 1.6; only the Euler-angle r_mse/r_mae (not on the
+        Rotation.from_dcm = Rotation.from_matrix   # path) of compute_metrics go through it (common/math/so3.py:23)
+    g = torch.Generator().manual_seed(23)
+    B, C, N, k = 2, 32, 1024, 16
+    b = synth.make_batch(B, N, C, "kitti", config=1, first_pair=40)
+    xyz = b["points_src"][:, :, :3].permute(0, 2, 1).contiguous()
+    feat = torch.rand(B, C, N, generator=g) * 3 - 0.5
+    prob = torch.rand(B, 1, N, generator=g)
+    label = torch.randint(0, 19, (B, 1, N), generator=g)
+    neigh = O.nn_search_c(b["points_src"], k, (4, 4, 4, 4))["neigh_idx"][:, :N]
+    lw = torch.tensor(R_model_label_weights()).float()
+    fake = types.SimpleNamespace(num_knn=16, label_weights=lw)
+    score = R_model.Network.score_fun(fake, feat, xyz, prob, label, neigh)
+    fake2 = types.SimpleNamespace(num_knn=16, label_weights=lw, sub_selection=True,
+                                  score_fun=lambda *a: R_model.Network.score_fun(fake, *a))
+    f_sub, x_sub, l_sub, s_sub = R_model.Network.feat_score(fake2, feat, xyz, prob, label, neigh, num_sub=200)
+    # correspondence check
+    pos = [torch.stack([torch.arange(N), torch.randperm(N, generator=g)], 1)[: N - 100 * i].int() for i in range(B)]
+    pred = torch.stack([torch.stack([torch.arange(N), torch.where(torch.rand(N, generator=g) < 0.6, pos[i][:, 1].long()[torch.arange(N) % pos[i].shape[0]],
+                                                                   torch.randint(0, N, (N,), generator=g))], 1) for i in range(B)]).int()
+    corr_seed = R_loss.ScanAlignmentLoss.find_correct_correspondence(None, [p.numpy() for p in pos], pred.numpy(), hash_seed=N)
+    # pose metrics
+    gt = b["transform_gt"][:, :3, :]
+    gn = torch.Generator().manual_seed(5)
+    noise = torch.stack([synth.random_pose(gn, 3.0 * (i + 1), 1.0, 0.3 * (i + 1), any_axis=True) for i in range(B)])
+    pred_T = R_se3.concatenate(noise, gt)
+    data = dict(transform_gt=gt, points_src=b["points_src"], points_ref=b["points_ref"])
+    m = R_met.compute_metrics(data, pred_T, 2.0, 5.0)
+    rr = np.stack([R_met.rte_rre(pred_T[i].numpy(), gt[i].numpy(), 2.0, 5.0) for i in range(B)])
+    save("keypoint_eval", feat=feat, xyz=xyz, prob=prob, label=label, neigh=neigh, label_weights=lw, score=score,
+         sub_feat=f_sub, sub_xyz=x_sub, sub_label=l_sub, sub_score=s_sub,
+         pos0=pos[0], pos1=pos[1], pred_pairs=pred, correct=corr_seed,
+         transform_gt=gt, transform_pred=pred_T, points_src=b["points_src"], points_ref=b["points_ref"],
+         err_r_deg=m["err_r_deg"], err_t=m["err_t"], succ=m["succ"], chamfer_dist=m["chamfer_dist"], rte_rre=rr)
+
+
+def R_model_label_weights():
+    return [3, 1, 1, 3, 2, 0, 0, 0, 6, 5, 6, 4, 7, 7, 6, 8, 4, 9, 9]   # network/model.py:146-149
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "graph":
         graph()
+    elif len(sys.argv) > 1 and sys.argv[1] == "keypoint":
+        keypoint_eval()
     else:
         main()
         graph()
+        keypoint_eval()

@@ -524,3 +524,96 @@ def test_sinkhorn_on_the_implicit_matrix():
         assert torch.allclose(a - u.cpu()[:, :, None] - v.cpu()[:, None, :], logp, atol=2e-3, rtol=0)
     T, inv = D.kabsch_soft(cu(b["points_src"][:, :, :3].contiguous()), y, mass)
     assert not bool(inv) and T.shape == (2, 3, 4)
+
+
+# ------------------------------------------------------------------------------------------- f-1 key points
+def test_keypoint_score_and_topk_golden(golden):
+    """score_fun / feat_score against the reference's own outputs (fp32 gather-reduce: 1e-5 relative; selection exact
+    where the scores are distinct)."""
+    g = golden("keypoint_eval")
+    feat, xyz, prob, label, neigh = (cu(g[k]) for k in ("feat", "xyz", "prob", "label", "neigh"))
+    s = D.score_fun(feat, xyz, prob, label, neigh, label_weights=g["label_weights"].tolist())
+    assert torch.allclose(s.cpu(), g["score"], rtol=1e-5, atol=1e-7)
+    v, i = D.topk(cu(g["score"]), 200)
+    vo, io = O.topk_lower_index(g["score"], 200)
+    assert torch.equal(v.cpu(), vo) and torch.equal(i.cpu(), io)
+    assert torch.equal(v.cpu(), g["sub_score"])
+    f2, x2, l2, s2 = D.feat_score(cu(g["feat"]), xyz, prob, label, neigh, num_sub=200, label_weights=g["label_weights"].tolist())
+    assert f2.shape == g["sub_feat"].shape and x2.shape == g["sub_xyz"].shape and l2.shape == g["sub_label"].shape
+    assert torch.allclose(s2.cpu(), g["sub_score"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("n,k", [(1000, 1), (1000, 1000), (20000, 4096), (333, 17)])
+def test_topk_ties_nan_and_sizes(n, k):
+    g = torch.Generator().manual_seed(n + k)
+    s = torch.randint(0, 7, (3, n), generator=g).float()          # heavy ties: equal values go to the lower index
+    s[1, ::5] = 0.0
+    s[2, n // 2] = float("nan")                                    # NaN ranks first like torch.topk
+    v, i = D.topk(cu(s), k)
+    vo, io = O.topk_lower_index(torch.nan_to_num(s, nan=float("inf")), k)
+    assert torch.equal(i.cpu(), io)
+    assert torch.equal(torch.nan_to_num(v.cpu(), nan=float("inf")), vo)
+    tv, _ = torch.topk(s, k, dim=-1, largest=True)
+    assert torch.equal(torch.nan_to_num(v.cpu(), nan=-1.0), torch.nan_to_num(tv, nan=-1.0))
+
+
+def test_keypoint_score_c2_level0_properties():
+    """Full C2 cloud size: scores are finite, zero wherever the gate closes, invariant to a permutation of the neighbours."""
+    b = synth.make_batch(1, 16384, 8, "kitti", config=2, first_pair=9)
+    gph = D.nn_search_cloud(cu(b["points_src"]), 16, (4, 4, 4, 4))
+    xyz = cu(b["points_src"][:, :, :3].permute(0, 2, 1).contiguous())
+    gen = torch.Generator().manual_seed(1)
+    feat = cu(torch.rand(1, 64, 16384, generator=gen))
+    prob = cu(torch.rand(1, 1, 16384, generator=gen))
+    label = cu(torch.randint(0, 19, (1, 1, 16384), generator=gen))
+    nb = gph["neigh_idx"][:, :16384]
+    s = D.score_fun(feat, xyz, prob, label, nb)
+    assert torch.isfinite(s).all() and (s >= 0).all()
+    so = O.score_fun(feat.cpu(), xyz.cpu(), prob.cpu(), label.cpu(), nb.cpu(), D.keypoint.KITTI_LABEL_WEIGHTS)
+    assert torch.allclose(s.cpu(), so, rtol=1e-5, atol=1e-7)
+    s2 = D.score_fun(feat, xyz, prob, label, nb.flip(-1).contiguous())
+    assert torch.allclose(s, s2, rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------- f-4 evaluation
+def test_eval_golden(golden):
+    g = golden("keypoint_eval")
+    c = D.metrics.find_correct_correspondence([cu(g["pos0"]), cu(g["pos1"])], cu(g["pred_pairs"]), hash_seed=1024)
+    assert torch.equal(c.cpu(), g["correct"].bool())
+    c2 = D.metrics.find_correct_correspondence([cu(g["pos0"]), cu(g["pos1"])], cu(g["pred_pairs"]), len_batch=[(1024, 1024), (1024, 900)])
+    assert torch.equal(c2.cpu(), g["correct"].bool())
+    pe = D.metrics.pose_errors(cu(g["transform_pred"]), cu(g["transform_gt"]), 2.0, 5.0)
+    assert torch.allclose(pe["err_r_deg"].cpu(), g["err_r_deg"], atol=ROT_TOL_DEG)
+    assert torch.allclose(pe["err_t"].cpu(), g["err_t"], atol=TRANS_TOL_M)
+    assert torch.equal(pe["succ"].cpu(), g["succ"].bool())
+    assert torch.allclose(pe["rte"].cpu().double(), g["rte_rre"][:, 1].double(), atol=TRANS_TOL_M)
+    assert torch.allclose(pe["rre"].cpu().double(), g["rte_rre"][:, 2].double(), atol=ROT_TOL_DEG)
+    data = dict(transform_gt=cu(g["transform_gt"]), points_src=cu(g["points_src"]), points_ref=cu(g["points_ref"]))
+    m = D.metrics.compute_metrics(data, cu(g["transform_pred"]), 2.0, 5.0)
+    assert torch.allclose(m["chamfer_dist"].cpu(), g["chamfer_dist"], rtol=1e-5, atol=1e-8)
+
+
+def test_correspondence_check_empty_and_collisions():
+    """np.isin semantics: an empty positive list gives all-false; keys collide exactly like _hash when an index exceeds
+    the seed (loss.py:280-294)."""
+    pred = torch.tensor([[[0, 5], [1, 2], [7, 0]]], dtype=torch.int32)
+    pos = [torch.tensor([[5, 4], [1, 2]], dtype=torch.int32)]       # seed 5: key(0,5) = 25 = key(5,4)
+    c = D.metrics.find_correct_correspondence([cu(pos[0])], cu(pred), hash_seed=5)
+    assert c.cpu().tolist() == O.find_correct_correspondence([pos[0].numpy()], pred.numpy(), hash_seed=5).tolist() == [[True, True, False]]
+    c = D.metrics.find_correct_correspondence([torch.zeros(0, 2, dtype=torch.int32, device=DEV)], cu(pred), hash_seed=5)
+    assert not c.any()
+
+
+def test_loop_to_metrics_without_host_sync():
+    """The loop's last pose and correspondences feed the evaluation entirely on the device: ground-truth matches are found,
+    the pose error of a planted pair is small."""
+    b = synth.make_batch(2, 4096, 64, "kitti", config=2, first_pair=21)
+    xs = b["points_src"][:, :, :3].permute(0, 2, 1).contiguous()
+    xr = b["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
+    tr, pred, _, _ = D.align_loop(cu(b["feat_src"]), cu(b["feat_ref"]), cu(xs), cu(xr), cu(b["weights"]), 2)
+    pairs = torch.stack([torch.arange(4096, device=DEV).expand(2, -1), pred[-1]], dim=-1).int()
+    pos = [torch.stack([torch.arange(4096), b["perm"][i]], 1).int() for i in range(2)]
+    corr = D.metrics.find_correct_correspondence([cu(p) for p in pos], pairs, hash_seed=4096)
+    assert corr.float().mean().item() > 0.85                       # 10 % planted outliers
+    pe = D.metrics.pose_errors(tr[-1], cu(b["transform_gt"]), 2.0, 5.0)
+    assert pe["succ"].all() and pe["err_r_deg"].max().item() < 0.5 and pe["err_t"].max().item() < 0.3

@@ -179,3 +179,28 @@ def test_graph_ops_oracle_matches_reference_fixture(golden):
     assert torch.allclose(O.sinkhorn(g["log_alpha"], 5, True), g["sinkhorn_slack_5"], atol=2e-6, rtol=0)
     assert torch.allclose(O.sinkhorn(g["log_alpha"], 3, False), g["sinkhorn_noslack_3"], atol=2e-6, rtol=0)
     assert torch.allclose(O.sinkhorn(g["log_alpha"], 50, True, eps=1e-2), g["sinkhorn_slack_eps"], atol=2e-6, rtol=0)
+
+
+def test_keypoint_and_eval_oracle_matches_reference_fixture(golden):
+    """score_fun / feat_score (model.py:668-757), find_correct_correspondence (loss.py:723-749), compute_metrics and
+    rte_rre (metrics_util.py:27-85): oracle == the reference's own outputs."""
+    g = golden("keypoint_eval")
+    s = O.score_fun(g["feat"], g["xyz"], g["prob"], g["label"], g["neigh"], g["label_weights"])
+    assert torch.allclose(s, g["score"], rtol=1e-6, atol=1e-7)
+    v, i = O.topk_lower_index(g["score"], 200)
+    assert torch.equal(v, g["sub_score"])                       # torch.topk values are order-independent
+    tie_free = (v[:, 1:] != v[:, :-1]).all(dim=1)               # indices too wherever the values are distinct
+    for b in range(v.shape[0]):
+        if tie_free[b]:
+            assert torch.equal(O.gather_neighbour_V3(g["xyz"], i)[b], g["sub_xyz"][b])
+    c = O.find_correct_correspondence([g["pos0"].numpy(), g["pos1"].numpy()], g["pred_pairs"].numpy(), hash_seed=1024)
+    assert np.array_equal(c, g["correct"].numpy().astype(bool))
+    deg, mag = O.pose_residuals(g["transform_pred"], g["transform_gt"])
+    assert torch.allclose(deg, g["err_r_deg"], atol=1e-5) and torch.allclose(mag, g["err_t"], atol=1e-6)
+    for b in range(2):
+        rte, rre = O.rte_rre(g["transform_pred"][b].numpy(), g["transform_gt"][b].numpy())
+        assert abs(rte - g["rte_rre"][b, 1].item()) < 1e-7 and abs(rre - g["rte_rre"][b, 2].item()) < 1e-5
+    src, ref = g["points_src"][:, :2048, :3], g["points_ref"][:, :2048, :3]
+    raw = torch.cat([O.se3_transform(g["transform_gt"], src), ref], dim=1)
+    ch = O.chamfer(src, ref, raw, g["transform_pred"], g["transform_gt"])
+    assert torch.allclose(ch, g["chamfer_dist"], rtol=1e-6, atol=1e-8)
