@@ -450,8 +450,11 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
             int ci[TC_T];
 #pragma unroll
             for (int t = 0; t < TC_T; ++t) { cv[t] = INFINITY; ci[t] = -1; }
-            float thr = (P.dbg_flags & 1) ? -INFINITY : INFINITY;
             const int j = rb * TC_BM + r * 128 + trow;
+            // Rows beyond J (zero-filled by the TMA) would tie on EVERY column (x = sigma^2 |r_k|^2) and drag their warp
+            // through the slow path at every step; their lists are never read, so they never look at anything.
+            const bool dead = j >= P.J || (P.dbg_flags & 1);
+            float thr = dead ? -INFINITY : INFINITY;
             const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
             const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C);
             for (int t = 0; t < us.total(); ++t) {
@@ -482,7 +485,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                                        &tmem_empty[pa.stage * TC_RBS + r], lane);
                 }
                 if (tracing && useq < 256) P.trace[1024 + useq * 8 + 4] = (unsigned int)clock64();
-                if (t == us.ns - 1 && !(P.dbg_flags & 1)) thr = best + margin;   // primed: every row has seen a value <= best
+                if (t == us.ns - 1 && !dead) thr = best + margin;   // primed: every row has seen a value <= best
                 if (tracing && useq < 256) P.trace[1024 + useq * 8 + 5] = (unsigned int)clock64();
                 ++useq;
                 pa.advance(TC_ACC_STAGES);
@@ -786,7 +789,7 @@ TcPlan make_plan(int B, int C, int J, int K) {
         if (S > p.U) S = p.U;
         if (S < 1) S = 1;
     }
-    p.S = S;
+    p.S = S;   // (splitting further to fill the last wave was measured slower: every split re-primes and re-discovers its minima)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += ws_block(bytes); return o; };
     p.off_a16 = take((size_t)B * J * TC_CH * 2);
