@@ -183,22 +183,27 @@ __device__ __forceinline__ void topk_insert_lex(float (&bd)[KMAX], int (&bi)[KMA
 // costs ~100 compare/select instructions per insertion on the ALU pipe, which bounded the kernel; the heap needs
 // <= log2(k) levels of two loads + two stores and keeps 2k registers free (higher occupancy).  Order is lexicographic
 // (d, idx); the root is the current k-th best and is mirrored in registers.
+#ifndef DSIR_KNN_SORTNET
+#define DSIR_KNN_SORTNET 0
+#endif
+constexpr bool KNN_SORTNET = DSIR_KNN_SORTNET != 0;
+
 template <int KMAX>
 struct SmemHeap {
     float *d;   // [KMAX][128]
     int *i;
     int K;      // heap size (= k)
-    float rd;   // root
+    int cnt;    // filled slots; the heap property holds once cnt == K
+    float rd;   // filter: the root (k-th best) once the heap is built, (+inf, max) while it fills
     int ri;
     __device__ __forceinline__ static bool gt(float da, int ia, float db, int ib) { return da > db || (da == db && ia > ib); }
     __device__ __forceinline__ void init(float *dcol, int *icol, int k) {
-        d = dcol; i = icol; K = k;
+        d = dcol; i = icol; K = k; cnt = 0;
         for (int p = 0; p < k; ++p) { d[p * 128] = INFINITY; i[p * 128] = 0x7fffffff; }
         rd = INFINITY; ri = 0x7fffffff;
     }
-    // precondition: (x, s) < root.  Replace the root and sift down.
-    __device__ __forceinline__ void replace_root(float x, int s) {
-        int pos = 0;
+    // place (x, s) at `pos` and sift it down
+    __device__ __forceinline__ void sift(int pos, float x, int s) {
         while (true) {
             const int l = 2 * pos + 1;
             if (l >= K) break;
@@ -214,32 +219,24 @@ struct SmemHeap {
             pos = c;
         }
         d[pos * 128] = x; i[pos * 128] = s;
+    }
+    __device__ __forceinline__ void heapify() {
+        for (int p = K / 2 - 1; p >= 0; --p) sift(p, d[p * 128], i[p * 128]);
         rd = d[0]; ri = i[0];
     }
+    // precondition: (x, s) < root.  Replace the root and sift down.  (Filling the first k slots directly and heapifying
+    // once was measured slower: the extra branch splits the warp between lanes that still fill and lanes that sift.)
+    __device__ __forceinline__ void replace_root(float x, int s) {
+        sift(0, x, s);
+        rd = d[0]; ri = i[0];
+    }
+    // fewer than k candidates were ever offered (placeholders (+inf, max) fill the rest): make it a heap for pop()
+    __device__ __forceinline__ void finish() {}
     // remove and return the root (largest); heap shrinks by one
     __device__ __forceinline__ void pop(float &od, int &oi) {
         od = d[0]; oi = i[0];
         --K;
-        if (K > 0) {
-            const float x = d[K * 128];
-            const int s = i[K * 128];
-            int pos = 0;
-            while (true) {
-                const int l = 2 * pos + 1;
-                if (l >= K) break;
-                float cd = d[l * 128];
-                int ci = i[l * 128], c = l;
-                if (l + 1 < K) {
-                    const float d2 = d[(l + 1) * 128];
-                    const int i2 = i[(l + 1) * 128];
-                    if (gt(d2, i2, cd, ci)) { cd = d2; ci = i2; c = l + 1; }
-                }
-                if (!gt(cd, ci, x, s)) break;
-                d[pos * 128] = cd; i[pos * 128] = ci;
-                pos = c;
-            }
-            d[pos * 128] = x; i[pos * 128] = s;
-        }
+        if (K > 0) sift(0, d[K * 128], i[K * 128]);
     }
 };
 
@@ -347,6 +344,18 @@ __global__ __launch_bounds__(128) void knn_grid_query_kernel(KnnGridQueryParams 
     }
 }
 
+// zig-zag offset sequence 0, -1, +1, -2, +2, ...: the rows of a search box are visited centre first, so that the k-th
+// distance is tight before the far rows come up - most of which are then skipped by the row bound below
+__device__ __forceinline__ int zigzag(int i) { return (i & 1) ? -((i + 1) >> 1) : (i >> 1); }
+
+// conservative distance from coordinate v to the slab of cell c along one axis (0 inside): every point of the cell is
+// at least this far from v along the axis.  cell_of() rounds, so the slab is taken 2*slack wider on both sides.
+__device__ __forceinline__ float slab_gap(float v, int c, float lo, float h, float slack) {
+    const float a = __fmaf_rn((float)c, h, lo), b = __fmaf_rn((float)(c + 1), h, lo);
+    const float g = fmaxf(fmaxf(a - v, v - b), 0.f);
+    return fmaxf(__fmul_rn(g, 0.99999f) - 2.f * slack, 0.f);
+}
+
 template <int KMAX>
 __global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryParams P) {
     __shared__ float s_hd[KMAX * 128];
@@ -375,6 +384,7 @@ __global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryPa
     int px0 = 1, px1 = 0, py0 = 1, py1 = 0, pz0 = 1, pz1 = 0;  // cells already scanned (empty box)
     float R = P.r0_cells * H.h;
     const bool q_ok = (qx == qx) && (qy == qy) && (qz == qz);   // NaN query: nothing compares, scan everything once
+    const int cyq = cell_of(qy, H.lo[1], H.inv_h, H.gy), czq = cell_of(qz, H.lo[2], H.inv_h, H.gz);
     for (int pass = 0; pass < 64; ++pass) {
         const float Rb = __fmaf_rn(R, 1.0001f, H.slack);
         int x0 = cell_of(qx - Rb, H.lo[0], H.inv_h, H.gx), x1 = cell_of(qx + Rb, H.lo[0], H.inv_h, H.gx);
@@ -383,8 +393,20 @@ __global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryPa
         if (!q_ok || !(Rb < INFINITY)) { x0 = 0; x1 = H.gx - 1; y0 = 0; y1 = H.gy - 1; z0 = 0; z1 = H.gz - 1; }
         // never shrink (R only grows, but keep the invariant explicit)
         if (px0 <= px1) { x0 = min(x0, px0); x1 = max(x1, px1); y0 = min(y0, py0); y1 = max(y1, py1); z0 = min(z0, pz0); z1 = max(z1, pz1); }
-        for (int z = z0; z <= z1; ++z) {
-            for (int y = y0; y <= y1; ++y) {
+        // rows (z, y) of the box, centre first.  A row whose slab is provably farther than the current k-th distance
+        // cannot contribute now or later (the k-th distance only shrinks), so it counts as scanned without being read.
+        const int nz = 2 * max(czq - z0, z1 - czq) + 1, ny = 2 * max(cyq - y0, y1 - cyq) + 1;
+        for (int iz = 0; iz < nz; ++iz) {
+            const int z = czq + zigzag(iz);
+            if (z < z0 || z > z1) continue;
+            const float gz = q_ok ? slab_gap(qz, z, H.lo[2], H.h, H.slack) : 0.f;
+            const float gz2 = __fmul_rn(gz, gz);
+            if (gz2 > hp.rd) continue;
+            for (int iy = 0; iy < ny; ++iy) {
+                const int y = cyq + zigzag(iy);
+                if (y < y0 || y > y1) continue;
+                const float gy = q_ok ? slab_gap(qy, y, H.lo[1], H.h, H.slack) : 0.f;
+                if (__fmul_rn(__fmaf_rn(gy, gy, gz2), 0.99999f) > hp.rd) continue;   // lower bound of every d2 in the row
                 const int row = (z * H.gy + y) * H.gx;
                 const bool inner = (px0 <= px1) && y >= py0 && y <= py1 && z >= pz0 && z <= pz1;
                 // run A: [x0, inner ? px0-1 : x1]   run B: inner ? [px1+1, x1] : empty
@@ -435,14 +457,51 @@ __global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryPa
     int64_t *o = P.idx + (size_t)b * P.idx_bs + (size_t)qi * P.k;
     int64_t *o2 = (P.idx2 != nullptr && qi < P.idx2_rows) ? P.idx2 + (size_t)b * P.idx2_bs + (size_t)qi * P.k : nullptr;
     float *od = P.dist2 != nullptr ? P.dist2 + (size_t)b * P.idx_bs + (size_t)qi * P.k : nullptr;
-    for (int p = P.k - 1; p >= 0; --p) {     // the heap yields the k best in descending order
-        float dd;
-        int ii;
-        hp.pop(dd, ii);
-        const int64_t v = ii == 0x7fffffff ? (int64_t)-1 : (int64_t)ii;
-        o[p] = v;
-        if (o2) o2[p] = v;
-        if (od) od[p] = dd;
+    if (KMAX <= 16 && KNN_SORTNET) {
+        // the k best, unordered, go to registers and through a bitonic network on (d, idx): cheaper than k heap pops
+        float sd[KMAX];
+        int si[KMAX];
+#pragma unroll
+        for (int p = 0; p < KMAX; ++p) {
+            const bool in = p < P.k;
+            sd[p] = in ? hp.d[p * 128] : INFINITY;
+            si[p] = in ? hp.i[p * 128] : 0x7fffffff;
+        }
+#pragma unroll
+        for (int size = 2; size <= KMAX; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+                for (int t2 = 0; t2 < KMAX / 2; ++t2) {
+                    const int lo = 2 * t2 - (t2 & (stride - 1)), hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const bool sw = SmemHeap<KMAX>::gt(sd[lo], si[lo], sd[hi], si[hi]) == up;
+                    const float td = sw ? sd[hi] : sd[lo], ud = sw ? sd[lo] : sd[hi];
+                    const int ti = sw ? si[hi] : si[lo], ui = sw ? si[lo] : si[hi];
+                    sd[lo] = td; sd[hi] = ud; si[lo] = ti; si[hi] = ui;
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < KMAX; ++p) {
+            if (p < P.k) {
+                const int64_t v = si[p] == 0x7fffffff ? (int64_t)-1 : (int64_t)si[p];
+                o[p] = v;
+                if (o2) o2[p] = v;
+                if (od) od[p] = sd[p];
+            }
+        }
+    } else {
+        hp.finish();
+        for (int p = P.k - 1; p >= 0; --p) {     // the heap yields the k best in descending order
+            float dd;
+            int ii;
+            hp.pop(dd, ii);
+            const int64_t v = ii == 0x7fffffff ? (int64_t)-1 : (int64_t)ii;
+            o[p] = v;
+            if (o2) o2[p] = v;
+            if (od) od[p] = dd;
+        }
     }
 }
 
