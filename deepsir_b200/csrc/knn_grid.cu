@@ -240,6 +240,18 @@ struct SmemHeap {
     }
 };
 
+// zig-zag offset sequence 0, -1, +1, -2, +2, ...: the rows of a search box are visited centre first, so that the k-th
+// distance is tight before the far rows come up - most of which are then skipped by the row bound below
+__device__ __forceinline__ int zigzag(int i) { return (i & 1) ? -((i + 1) >> 1) : (i >> 1); }
+
+// conservative distance from coordinate v to the slab of cell c along one axis (0 inside): every point of the cell is
+// at least this far from v along the axis.  cell_of() rounds, so the slab is taken 2*slack wider on both sides.
+__device__ __forceinline__ float slab_gap(float v, int c, float lo, float h, float slack) {
+    const float a = __fmaf_rn((float)c, h, lo), b = __fmaf_rn((float)(c + 1), h, lo);
+    const float g = fmaxf(fmaxf(a - v, v - b), 0.f);
+    return fmaxf(__fmul_rn(g, 0.99999f) - 2.f * slack, 0.f);
+}
+
 template <int KMAX>
 __global__ __launch_bounds__(128) void knn_grid_query_kernel(KnnGridQueryParams P) {
     const int b = blockIdx.y;
@@ -268,6 +280,7 @@ __global__ __launch_bounds__(128) void knn_grid_query_kernel(KnnGridQueryParams 
     int px0 = 1, px1 = 0, py0 = 1, py1 = 0, pz0 = 1, pz1 = 0;  // cells already scanned (empty box)
     float R = P.r0_cells * H.h;
     const bool q_ok = (qx == qx) && (qy == qy) && (qz == qz);   // NaN query: nothing compares, scan everything once
+    const int cyq = cell_of(qy, H.lo[1], H.inv_h, H.gy), czq = cell_of(qz, H.lo[2], H.inv_h, H.gz);
     for (int pass = 0; pass < 64; ++pass) {
         const float Rb = __fmaf_rn(R, 1.0001f, H.slack);
         int x0 = cell_of(qx - Rb, H.lo[0], H.inv_h, H.gx), x1 = cell_of(qx + Rb, H.lo[0], H.inv_h, H.gx);
@@ -276,8 +289,19 @@ __global__ __launch_bounds__(128) void knn_grid_query_kernel(KnnGridQueryParams 
         if (!q_ok || !(Rb < INFINITY)) { x0 = 0; x1 = H.gx - 1; y0 = 0; y1 = H.gy - 1; z0 = 0; z1 = H.gz - 1; }
         // never shrink (R only grows, but keep the invariant explicit)
         if (px0 <= px1) { x0 = min(x0, px0); x1 = max(x1, px1); y0 = min(y0, py0); y1 = max(y1, py1); z0 = min(z0, pz0); z1 = max(z1, pz1); }
-        for (int z = z0; z <= z1; ++z) {
-            for (int y = y0; y <= y1; ++y) {
+        // rows centre first, rows provably farther than the current k-th distance skipped (see the heap kernel)
+        const int nz = 2 * max(czq - z0, z1 - czq) + 1, ny = 2 * max(cyq - y0, y1 - cyq) + 1;
+        for (int iz = 0; iz < nz; ++iz) {
+            const int z = czq + zigzag(iz);
+            if (z < z0 || z > z1) continue;
+            const float gz = q_ok ? slab_gap(qz, z, H.lo[2], H.h, H.slack) : 0.f;
+            const float gz2 = __fmul_rn(gz, gz);
+            if (gz2 > bd[KMAX - 1]) continue;
+            for (int iy = 0; iy < ny; ++iy) {
+                const int y = cyq + zigzag(iy);
+                if (y < y0 || y > y1) continue;
+                const float gy = q_ok ? slab_gap(qy, y, H.lo[1], H.h, H.slack) : 0.f;
+                if (__fmul_rn(__fmaf_rn(gy, gy, gz2), 0.99999f) > bd[KMAX - 1]) continue;
                 const int row = (z * H.gy + y) * H.gx;
                 const bool inner = (px0 <= px1) && y >= py0 && y <= py1 && z >= pz0 && z <= pz1;
                 // run A: [x0, inner ? px0-1 : x1]   run B: inner ? [px1+1, x1] : empty
@@ -342,18 +366,6 @@ __global__ __launch_bounds__(128) void knn_grid_query_kernel(KnnGridQueryParams 
         for (int p = 0; p < KMAX; ++p)
             if (p < P.k) od[p] = bd[p];
     }
-}
-
-// zig-zag offset sequence 0, -1, +1, -2, +2, ...: the rows of a search box are visited centre first, so that the k-th
-// distance is tight before the far rows come up - most of which are then skipped by the row bound below
-__device__ __forceinline__ int zigzag(int i) { return (i & 1) ? -((i + 1) >> 1) : (i >> 1); }
-
-// conservative distance from coordinate v to the slab of cell c along one axis (0 inside): every point of the cell is
-// at least this far from v along the axis.  cell_of() rounds, so the slab is taken 2*slack wider on both sides.
-__device__ __forceinline__ float slab_gap(float v, int c, float lo, float h, float slack) {
-    const float a = __fmaf_rn((float)c, h, lo), b = __fmaf_rn((float)(c + 1), h, lo);
-    const float g = fmaxf(fmaxf(a - v, v - b), 0.f);
-    return fmaxf(__fmul_rn(g, 0.99999f) - 2.f * slack, 0.f);
 }
 
 template <int KMAX>
