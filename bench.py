@@ -269,11 +269,14 @@ def main():
                       "l2": "inputs larger than L2 (268 MB of features per step vs 126 MB L2), no explicit flush",
                       "sharding": "by pair, no collective"},
            "clocks": clocks,
-           "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "h2d_gbs": h2d * args.steps / (ms_e2e / 1e3) / 1e9,
+                   "note": "upload-bound: the fp32 feature tensors of a step (268 MB) cross PCIe at the rate shown; a raw "
+                           "pinned->device copy of the same bytes measures 55.3 GB/s on this pool (tools/e2e_probe.py)"},
            "gpu_launches": int(launches),
            "roofline": {"bound": "tensor", "kernel": "match_tc_filter_kernel (tcgen05 fp16 distance + row-argmin filter)",
                         "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
-                        "traffic": 165.66e6,   # dram read+write per launch, ncu --set full (profiles/ncu_digest_filter_r1e.txt)
+                        "traffic": 169.48e6,   # dram read+write per launch, ncu --set full (profiles/ncu_digest_filter_r1f.txt)
                         "peak_source": f"{pk['src']} bf16_tflops_sustained (16-bit tensor-core inputs, fp32 accumulate; "
                                        "kernel timed inside the step by CUDA events on its stream)",
                         "ms_per_launch": filter_ms, "match_call_ms": match_ms,
