@@ -73,17 +73,23 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        recs = []
         for r in self.rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                recs.append((float(r[1]), float(r[2]), float(r[3]), [v.lower().startswith("active") for v in r[4:8]]))
             except Exception:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
-                if v.lower().startswith("active"):
+        # the sampler also sees the idle gaps around the timed loops: "under load" = power above half of the maximum seen
+        pmax = max((r[2] for r in recs), default=0.0)
+        load = [r for r in recs if r[2] >= 0.5 * pmax] or recs
+        reasons = set()
+        for r in load:
+            for name, on in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3]):
+                if on:
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(r[0] for r in load) if load else None,
+                "sm_max_mhz": max((r[1] for r in load), default=None), "power_w_max": pmax if recs else None,
+                "reasons": sorted(reasons), "samples": len(load), "samples_total": len(recs)}
 
 
 def make_inputs(batch, first_pair):
@@ -134,7 +140,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help=argparse.SUPPRESS)
@@ -188,12 +194,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- device-resident throughput (`value`)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs ~0.1 s to come up: started before the warm-up so that it is sampling
+        time.sleep(0.3)          # by the time the timed loops run; it keeps sampling through both timed regions
     for _ in range(warm):
         step_resident()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = D.lib().dsir_launch_count()
     t0, t1 = ev(), ev()
     t0.record()
