@@ -13,6 +13,7 @@ from .kabsch import (compute_rigid_transform, compute_rigid_transform_2, kabsch_
 from .knn import knn, nn_search, nn_search_cloud, nn_search_pair  # noqa: F401
 from .loop import align_loop, pred_pairs  # noqa: F401
 from .pipeline import RegistrationPipeline  # noqa: F401
+from .graphs import GraphedRegistration  # noqa: F401
 from .graph import (gather_neighbour, gather_neighbour_V2, gather_neighbour_V4, relative_pos_encoding, random_sample,  # noqa: F401
                     nearest_interpolation, sinkhorn)
 from .keypoint import score_fun, feat_score, topk  # noqa: F401

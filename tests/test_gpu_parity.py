@@ -617,3 +617,41 @@ def test_loop_to_metrics_without_host_sync():
     assert corr.float().mean().item() > 0.85                       # 10 % planted outliers
     pe = D.metrics.pose_errors(tr[-1], cu(b["transform_gt"]), 2.0, 5.0)
     assert pe["succ"].all() and pe["err_r_deg"].max().item() < 0.5 and pe["err_t"].max().item() < 0.3
+
+
+# ------------------------------------------------------------------------------------------- CUDA graphs, full sizes
+def test_graph_capture_replays_the_step_bit_exactly():
+    """Both KNN pyramids (with the library's internal fork/join) and a 2-iteration loop captured into ONE CUDA graph:
+    replays on new inputs equal the eager calls bit for bit."""
+    mk = lambda first: {k: cu(v) for k, v in synth.make_batch(2, 4096, 64, "kitti", config=2, first_pair=first).items()
+                        if k in ("points_src", "points_ref", "feat_src", "feat_ref", "weights")}
+    a, b = mk(60), mk(70)
+    a["weights"], b["weights"] = a["weights"][:, :, 0].contiguous(), b["weights"][:, :, 0].contiguous()
+    g = D.GraphedRegistration(a, 16, (4, 4, 4, 4), iters=2)
+    for batch in (b, a, b):
+        out = g.step(batch)
+        torch.cuda.synchronize()
+        gs, gr = D.nn_search_pair(batch["points_src"], batch["points_ref"], 16, (4, 4, 4, 4))
+        xs = batch["points_src"][:, :, :3].permute(0, 2, 1).contiguous()
+        xr = batch["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
+        tr, pred, xyz, st = D.align_loop(batch["feat_src"], batch["feat_ref"], xs, xr, batch["weights"], 2)
+        assert torch.equal(out["T"], torch.stack(tr)) and torch.equal(out["pred"], torch.stack(pred))
+        assert torch.equal(out["status"], st) and torch.equal(out["xyz_src"], xyz)
+        for k in gs:
+            assert torch.equal(out["graph_src"][k], gs[k]) and torch.equal(out["graph_ref"][k], gr[k])
+
+
+def test_match_c4_full_size_properties():
+    """BASELINE config 4 size (131072 x 131072, D=64) on one device: planted inliers are recovered, a row block matched
+    alone (what a rank of the row-block sharding does) equals the same rows of the full match, and the fp32 kernel agrees
+    on a sample of rows."""
+    b = synth.make_batch(1, 131072, 64, "kitti", config=4, first_pair=0)
+    fs, fr = cu(b["feat_src"]), cu(b["feat_ref"])
+    idx = D.match_argmin(fs, fr, algo=D.MATCH_TC)
+    ok = (idx.cpu() == b["perm"])
+    assert ok[b["inlier"]].float().mean().item() > 0.999
+    lo, hi = 70000, 70000 + 4096
+    part = D.match_argmin(fs[:, :, lo:hi], fr, algo=D.MATCH_TC)
+    assert torch.equal(part, idx[:, lo:hi])
+    exact = D.match_argmin(fs[:, :, lo:hi], fr, algo=D.MATCH_FP32)
+    assert torch.equal(exact, part)
