@@ -390,13 +390,38 @@ __global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryPa
         qx = qp[0]; qy = qp[1]; qz = qp[2]; qi = t;
     }
 
+    const bool q_ok = (qx == qx) && (qy == qy) && (qz == qz);   // NaN query: nothing compares, scan everything once
+    const int cyq = cell_of(qy, H.lo[1], H.inv_h, H.gy), czq = cell_of(qz, H.lo[2], H.inv_h, H.gz);
+
+    // SEED: the heap starts with k real support points - the k sorted-order neighbours of the query's own position
+    // (same / adjacent cells) - stored unordered and heapified once.  Filling an empty heap through k root replacements
+    // costs k full-depth sifts, more than half of all sift work of a query; and a tight k-th distance from the start makes
+    // the row bound effective at once.  The seeded positions [p0, p0 + k) are skipped by the scan.
     SmemHeap<KMAX> hp;
-    hp.init(s_hd + threadIdx.x, s_hi + threadIdx.x, P.k);
+    hp.d = s_hd + threadIdx.x; hp.i = s_hi + threadIdx.x; hp.K = P.k; hp.cnt = P.k;
+    int p0;
+    {
+        int pos = t;                                   // self-kNN in cell order: the query is support point t
+        if (P.q_sorted != S) {
+            const int cxq = cell_of(qx, H.lo[0], H.inv_h, H.gx);
+            pos = cs[(czq * H.gy + cyq) * H.gx + cxq];
+        }
+        p0 = min(max(pos - (P.k >> 1), 0), P.Ns - P.k);
+        for (int j = 0; j < P.k; ++j) {
+            const float4 p = S[p0 + j];
+            const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+            float d = __fmul_rn(dx, dx);
+            d = __fmaf_rn(dy, dy, d);
+            d = __fmaf_rn(dz, dz, d);
+            const bool nan = d != d;                   // never a candidate (like the scan's comparison): placeholder
+            hp.d[j * 128] = nan ? INFINITY : d;
+            hp.i[j * 128] = nan ? 0x7fffffff : __float_as_int(p.w);
+        }
+        hp.heapify();
+    }
 
     int px0 = 1, px1 = 0, py0 = 1, py1 = 0, pz0 = 1, pz1 = 0;  // cells already scanned (empty box)
     float R = P.r0_cells * H.h;
-    const bool q_ok = (qx == qx) && (qy == qy) && (qz == qz);   // NaN query: nothing compares, scan everything once
-    const int cyq = cell_of(qy, H.lo[1], H.inv_h, H.gy), czq = cell_of(qz, H.lo[2], H.inv_h, H.gz);
     for (int pass = 0; pass < 64; ++pass) {
         const float Rb = __fmaf_rn(R, 1.0001f, H.slack);
         int x0 = cell_of(qx - Rb, H.lo[0], H.inv_h, H.gx), x1 = cell_of(qx + Rb, H.lo[0], H.inv_h, H.gx);
@@ -418,12 +443,19 @@ __global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryPa
                 const int y = cyq + zigzag(iy);
                 if (y < y0 || y > y1) continue;
                 const float gy = q_ok ? slab_gap(qy, y, H.lo[1], H.h, H.slack) : 0.f;
-                if (__fmul_rn(__fmaf_rn(gy, gy, gz2), 0.99999f) > hp.rd) continue;   // lower bound of every d2 in the row
+                const float gyz2 = __fmul_rn(__fmaf_rn(gy, gy, gz2), 0.99999f);   // lower bound of every d2 in the row
+                if (gyz2 > hp.rd) continue;
                 const int row = (z * H.gy + y) * H.gx;
                 const bool inner = (px0 <= px1) && y >= py0 && y <= py1 && z >= pz0 && z <= pz1;
                 // run A: [x0, inner ? px0-1 : x1]   run B: inner ? [px1+1, x1] : empty
                 int a0 = x0, a1 = inner ? px0 - 1 : x1;
                 int b0 = inner ? px1 + 1 : 1, b1 = inner ? x1 : 0;
+                if (q_ok && hp.rd < INFINITY) {
+                    // along x only |dx| <= sqrt(kth - gyz2) can still matter: trim both runs to those cells
+                    const float ex = __fmaf_rn(sqrtf(fmaxf(hp.rd - gyz2, 0.f)), 1.00001f, 2.f * H.slack);
+                    const int xa = cell_of(qx - ex, H.lo[0], H.inv_h, H.gx), xb = cell_of(qx + ex, H.lo[0], H.inv_h, H.gx);
+                    a0 = max(a0, xa); a1 = min(a1, xb); b0 = max(b0, xa); b1 = min(b1, xb);
+                }
 #pragma unroll 1
                 for (int run = 0; run < 2; ++run) {
                     const int r0 = run == 0 ? a0 : b0, r1 = run == 0 ? a1 : b1;
@@ -435,7 +467,7 @@ __global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryPa
                         int p4[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const bool ok = i + u < e;
+                            const bool ok = i + u < e && (unsigned)(i + u - p0) >= (unsigned)P.k;   // in range, not a seed
                             const float4 p = S[ok ? i + u : s];
                             const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
                             float d = __fmul_rn(dx, dx);
@@ -460,7 +492,8 @@ __global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryPa
             // k points known: the k-th distance bounds the answer; make R^2 strictly exceed it
             float Rn = fmaxf(__fmul_rn(sqrtf(kth), 1.000001f), 1e-18f);
             while (!(kth < __fmul_rn(Rn, Rn))) Rn = __fmul_rn(Rn, 1.0001f);
-            R = fmaxf(Rn, __fmul_rn(R, 1.0001f));
+            // (the seeds can make the k-th distance finite long before k near points are known: never more than double)
+            R = fmaxf(fminf(Rn, __fmul_rn(R, 2.f)), __fmul_rn(R, 1.0001f));
         } else {
             R = __fmul_rn(R, 2.f);
         }
