@@ -301,12 +301,18 @@ __global__ __launch_bounds__(128) void knn_grid_query_kernel(KnnGridQueryParams 
                 const int y = cyq + zigzag(iy);
                 if (y < y0 || y > y1) continue;
                 const float gy = q_ok ? slab_gap(qy, y, H.lo[1], H.h, H.slack) : 0.f;
-                if (__fmul_rn(__fmaf_rn(gy, gy, gz2), 0.99999f) > bd[KMAX - 1]) continue;
+                const float gyz2 = __fmul_rn(__fmaf_rn(gy, gy, gz2), 0.99999f);
+                if (gyz2 > bd[KMAX - 1]) continue;
                 const int row = (z * H.gy + y) * H.gx;
                 const bool inner = (px0 <= px1) && y >= py0 && y <= py1 && z >= pz0 && z <= pz1;
                 // run A: [x0, inner ? px0-1 : x1]   run B: inner ? [px1+1, x1] : empty
                 int a0 = x0, a1 = inner ? px0 - 1 : x1;
                 int b0 = inner ? px1 + 1 : 1, b1 = inner ? x1 : 0;
+                if (q_ok && bd[KMAX - 1] < INFINITY) {   // along x only |dx| <= sqrt(kth - gyz2) can still matter
+                    const float ex = __fmaf_rn(sqrtf(fmaxf(bd[KMAX - 1] - gyz2, 0.f)), 1.00001f, 2.f * H.slack);
+                    const int xa = cell_of(qx - ex, H.lo[0], H.inv_h, H.gx), xb = cell_of(qx + ex, H.lo[0], H.inv_h, H.gx);
+                    a0 = max(a0, xa); a1 = min(a1, xb); b0 = max(b0, xa); b1 = min(b1, xb);
+                }
 #pragma unroll 1
                 for (int run = 0; run < 2; ++run) {
                     const int r0 = run == 0 ? a0 : b0, r1 = run == 0 ? a1 : b1;
