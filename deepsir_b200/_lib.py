@@ -16,7 +16,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libdeepsir_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
-SOURCES = ["api.cu", "knn.cu", "knn_grid.cu", "match_fp32.cu", "match_tc.cu", "kabsch.cu", "graph.cu", "keypoint.cu", "metrics.cu"]
+SOURCES = ["api.cu", "knn.cu", "knn_grid.cu", "match_fp32.cu", "match_tc.cu", "match_tc_soft.cu", "kabsch.cu", "graph.cu", "keypoint.cu", "metrics.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

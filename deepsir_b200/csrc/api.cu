@@ -473,9 +473,13 @@ int dsir_match_argmin_filter_trace(const void *ws, size_t ws_bytes, int B, int C
 }
 
 size_t dsir_match_soft_workspace_bytes(int B, int C, int J, int K) {
-    (void)C;
     if (B <= 0 || J <= 0 || K <= 0) return 256;
-    return ws_block((size_t)B * J * sizeof(float)) + ws_block((size_t)B * K * sizeof(float)) + 256;
+    size_t fp32 = ws_block((size_t)B * J * sizeof(float)) + ws_block((size_t)B * K * sizeof(float)) + 256;
+    if (match_tc_soft_supported(B, C, J, K)) {
+        size_t tc = match_tc_soft_workspace_bytes(B, C, J, K);
+        return tc > fp32 ? tc : fp32;
+    }
+    return fp32;
 }
 
 int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
@@ -485,6 +489,12 @@ int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, cons
     if (y_soft && !xyz_ref) return DSIR_ERR_BAD_ARG;
     if (topk != 0) { (void)topk_idx; (void)topk_w; return DSIR_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (match_tc_soft_supported(B, C, J, K) && (y_soft || lse)) {   // tcgen05: bf16 x3 split + online softmax in the TMEM epilogue
+        MatchParams T{};
+        T.fs = fs; T.fr = fr; T.B = B; T.C = C; T.J = J; T.K = K;
+        T.beta = beta; T.alpha = alpha; T.col_bias = col_bias; T.xyz_ref = xyz_ref; T.y_soft = y_soft; T.lse = lse;
+        return launch_match_tc_soft(T, ws, ws_bytes, st);
+    }
     Workspace W(ws, ws_bytes);
     float *ns = W.take<float>((size_t)B * J);
     float *nr = W.take<float>((size_t)B * K);

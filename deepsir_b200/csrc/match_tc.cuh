@@ -12,4 +12,10 @@ int match_tc_rescued_rows(const void *ws, int B, int C, int J, int K, int *out, 
 int match_tc_filter_trace(const void *ws, int B, int C, int J, int K, unsigned int *out, cudaStream_t st);
 int match_tc_filter_timing(const void *ws, int B, int C, int J, int K, double *out, cudaStream_t st);
 
+
+// tcgen05 soft match: bf16 x3 split contraction fused with the row-wise online softmax (match_tc_soft.cu), C <= 32
+bool match_tc_soft_supported(int B, int C, int J, int K);
+size_t match_tc_soft_workspace_bytes(int B, int C, int J, int K);
+int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace dsir

@@ -1,0 +1,552 @@
+// Fused feature-distance + affinity + row-wise ONLINE SOFTMAX + soft target on the 5th-generation tensor cores
+// (tcgen05 / TMEM / TMA), sm_100a.  Replaces, for C <= 32 channels (the 3DMatch-shaped configuration):
+//     match_features_V2 (network/matchnet.py:96-131) -> compute_affinity (:195-208) -> row normalisation (:259)
+//     -> weights @ xyz_ref / row mass (network/model.py:81-85)
+// without ever writing the [J,K] matrix: the score tile lives in TMEM, the running (max, sum, sum*xyz) of every row in
+// registers.
+//
+// Soft weights must agree with the fp32 reference to 1e-4 relative, i.e. the distance to ~1e-5 absolute at beta = 10:
+// single-pass fp16/bf16/tf32 operands (2^-9 .. 2^-11 relative) are three orders of magnitude short.  The operands are
+// therefore split three ways into bf16,  v = hi + lo + lolo  (24 significant bits), and the six products that matter
+//     hi*hi, hi*lo, lo*hi, lo*lo, hi*lolo, lolo*hi            (everything else is below 2^-24 |s||r|)
+// are laid out side by side along the contraction axis: an expanded point has 6 x 32 = 192 bf16 channels
+//     source     [hi | hi | lo | lo | hi   | lolo]
+//     reference  [hi | lo | hi | lo | lolo | hi  ] * (-2)      (exact)
+// so that ONE K = 192 contraction with fp32 accumulation yields -2<s,r> to fp32 accuracy; 16 more channels fold in the
+// three-term split of |r_k|^2 (source side 1,1,1,0..).  13 tcgen05.mma (M=128, N=128, K=16, kind::f16 with bf16 inputs)
+// per 128 x 128 tile.
+//
+//   warp 16      TMA producer: the source tiles of an item once (2 row blocks x 3 chunks x 16 KB), a 2-stage ring of
+//                reference tiles (3 x 16 KB + 4 KB norm tile), a 4-stage ring of (x, y, z, column bias) float4 per
+//                reference point (1-D bulk copies)
+//   warps 17-18  MMA issuers, one per row block; each row block owns two 128-column accumulators (double buffered), so
+//                the tensor pipe works on unit t+1 while unit t is being drained
+//   warps 0-15   epilogue: warp = (row block, column half, TMEM lane quadrant), thread = one source row.  Per 32
+//                columns: t_e = -beta' (x_e + |s|^2 - alpha) (+ bias), chunk maximum, ONE rescale of the running state,
+//                then p_e = 2^(t_e - m) (MUFU.EX2) accumulated into the sum and the three weighted coordinates.
+// Partial states of the two column halves (and of the K-splits) are merged by a small finalize kernel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+
+#include "match_tc.cuh"
+
+namespace dsir {
+
+namespace {
+
+constexpr int SF_RBS = 2, SF_ACC = 2, SF_HALVES = 2, SF_BSTAGES = 2, SF_XSTAGES = 4;
+constexpr int SF_BM = 128 * SF_RBS, SF_BN = 128;
+constexpr int SF_EPI_WARPS = 4 * SF_RBS * SF_HALVES;        // 16
+constexpr int SF_WARP_TMA = SF_EPI_WARPS, SF_WARP_MMA0 = SF_EPI_WARPS + 1;
+constexpr int SF_THREADS = (SF_EPI_WARPS + 1 + SF_RBS) * 32;   // 608
+constexpr int SF_CMAX = 32;                                  // channels supported by this path
+constexpr int SF_CH = 6 * SF_CMAX;                           // expanded channels per point
+constexpr int SF_CHUNKS = SF_CH / 64;                        // 64-channel (128-byte) TMA boxes per row
+constexpr int SF_AUG = 16;
+constexpr int SF_MAX_SPLIT = 8;
+constexpr uint32_t SF_TILE = 128 * 64 * 2;                   // 16 KB
+constexpr uint32_t SF_AUGT = 128 * SF_AUG * 2;               //  4 KB
+constexpr uint32_t SF_XT = 128 * 16;                         //  2 KB of float4 per unit
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+static_assert(SF_RBS * SF_ACC * 128 == 512, "TMEM budget");
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn soft_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// [B][N][W] bf16, box = bw channels x 128 rows; rows/batches beyond the extent read as zero
+bool make_bf16_tmap(CUtensorMap *m, const __nv_bfloat16 *base, int B, int N, int W, int bw, CUtensorMapSwizzle swz) {
+    EncodeTiledFn enc = soft_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)W * 2, (cuuint64_t)N * W * 2};
+    cuuint32_t box[3] = {(cuuint32_t)bw, 128, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, pe;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;        // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
+    return d;
+}
+// D = f32, A = B = bf16, both K-major, N = 128, M = 128
+constexpr uint32_t SF_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SF_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+struct Pipe {
+    int stage;
+    uint32_t phase;
+    __device__ __forceinline__ void advance(int n) {
+        if (++stage == n) { stage = 0; phase ^= 1u; }
+    }
+};
+
+struct SoftParams {
+    int B, J, K, C;
+    int RB, U, S, Jpad, Kpad;
+    const float *ns;         // [B,J] exact squared norms
+    const float *beta, *alpha;   // [B]
+    const float4 *xyzc;      // [B][Kpad] (x, y, z, bias * log2e; -inf beyond K)
+    float *part;             // [B][Jpad][S][HALVES][8]: m, l, sx, sy, sz (log2 domain)
+};
+
+template <bool XYZ>
+__global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                      const __grid_constant__ CUtensorMap mapB,
+                                                                      const __grid_constant__ CUtensorMap mapAaug,
+                                                                      const __grid_constant__ CUtensorMap mapBaug,
+                                                                      SoftParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                                             // [RBS][CHUNKS][16 KB]
+    uint8_t *sB = sA + SF_RBS * SF_CHUNKS * SF_TILE;                // [BSTAGES][CHUNKS][16 KB]
+    uint8_t *sAaug = sB + SF_BSTAGES * SF_CHUNKS * SF_TILE;         // [4 KB]
+    uint8_t *sBaug = sAaug + SF_AUGT;                               // [BSTAGES][4 KB]
+    uint8_t *sX = sBaug + SF_BSTAGES * SF_AUGT;                     // [XSTAGES][2 KB]
+    uint64_t *bars = (uint64_t *)(sX + SF_XSTAGES * SF_XT);
+    uint64_t *full_b = bars, *empty_b = full_b + SF_BSTAGES;
+    uint64_t *full_x = empty_b + SF_BSTAGES, *empty_x = full_x + SF_XSTAGES;
+    uint64_t *tmem_full = empty_x + SF_XSTAGES;                     // [ACC][RBS]
+    uint64_t *tmem_empty = tmem_full + SF_ACC * SF_RBS;
+    uint64_t *full_a = tmem_empty + SF_ACC * SF_RBS, *empty_a = full_a + 1;
+    uint32_t *tmem_slot = (uint32_t *)(empty_a + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int total_items = P.B * P.RB * P.S;
+
+    if (warp == SF_WARP_TMA && lane == 0) {
+        prefetch_tmap(&mapA); prefetch_tmap(&mapB); prefetch_tmap(&mapAaug); prefetch_tmap(&mapBaug);
+        for (int s = 0; s < SF_BSTAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], SF_RBS); }
+        for (int s = 0; s < SF_XSTAGES; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], SF_EPI_WARPS); }
+        for (int a = 0; a < SF_ACC * SF_RBS; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4 * SF_HALVES); }
+        mbar_init(full_a, 1);
+        mbar_init(empty_a, SF_RBS);
+        mbar_fence_init();
+    }
+    if (warp == SF_WARP_TMA) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == SF_WARP_TMA) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            Pipe pb{0, 0}, px{0, 0};
+            uint32_t iphase = 0;
+            bool first = true;
+            for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+                const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
+                const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
+                mbar_wait(empty_a, iphase ^ 1u);
+                mbar_expect_tx(full_a, SF_RBS * SF_CHUNKS * SF_TILE + (first ? SF_AUGT : 0u));
+#pragma unroll
+                for (int r = 0; r < SF_RBS; ++r)
+#pragma unroll
+                    for (int c = 0; c < SF_CHUNKS; ++c)
+                        tma_load_3d(sA + (r * SF_CHUNKS + c) * SF_TILE, &mapA, c * 64, rb * SF_BM + r * 128, b, full_a);
+                if (first) tma_load_3d(sAaug, &mapAaug, 0, 0, 0, full_a);
+                first = false;
+                for (int u = u0; u < u1; ++u) {
+                    while (!mbar_try_wait(&empty_x[px.stage], px.phase ^ 1u)) __nanosleep(32);
+                    mbar_expect_tx(&full_x[px.stage], SF_XT);
+                    bulk_g2s(sX + px.stage * SF_XT, P.xyzc + (size_t)b * P.Kpad + (size_t)u * SF_BN, SF_XT, &full_x[px.stage]);
+                    px.advance(SF_XSTAGES);
+                    while (!mbar_try_wait(&empty_b[pb.stage], pb.phase ^ 1u)) __nanosleep(32);
+                    mbar_expect_tx(&full_b[pb.stage], SF_CHUNKS * SF_TILE + SF_AUGT);
+#pragma unroll
+                    for (int c = 0; c < SF_CHUNKS; ++c)
+                        tma_load_3d(sB + (pb.stage * SF_CHUNKS + c) * SF_TILE, &mapB, c * 64, u * SF_BN, b, &full_b[pb.stage]);
+                    tma_load_3d(sBaug + pb.stage * SF_AUGT, &mapBaug, 0, u * SF_BN, b, &full_b[pb.stage]);
+                    pb.advance(SF_BSTAGES);
+                }
+                iphase ^= 1u;
+            }
+        }
+    } else if (warp >= SF_WARP_MMA0 && warp < SF_WARP_MMA0 + SF_RBS) {
+        // =========================== MMA issuer of row block r ===========================
+        const int r = warp - SF_WARP_MMA0;
+        Pipe pb{0, 0}, pa{0, 0};
+        uint32_t iphase = 0;
+        const uint64_t descA0 = make_kmajor_desc(smem_u32(sA + r * SF_CHUNKS * SF_TILE), 1024, 2);
+        const uint64_t descAaug = make_kmajor_desc(smem_u32(sAaug), 256, 6);
+        const uint64_t descB0 = make_kmajor_desc(smem_u32(sB), 1024, 2);
+        const uint64_t descBaug0 = make_kmajor_desc(smem_u32(sBaug), 256, 6);
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+            const int sp = it % P.S;
+            const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
+            mbar_wait(full_a, iphase);
+            for (int u = u0; u < u1; ++u) {
+                mbar_wait(&full_b[pb.stage], pb.phase);
+                mbar_wait(&tmem_empty[pa.stage * SF_RBS + r], pa.phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)((pa.stage * SF_RBS + r) * 128);
+                const uint64_t descB = descB0 + (uint64_t)((uint32_t)pb.stage * ((SF_CHUNKS * SF_TILE) >> 4));
+#pragma unroll
+                for (int c = 0; c < SF_CHUNKS; ++c)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)      // +32 bytes (16 bf16) inside the 128-byte swizzle row
+                        mma_bf16(d_tmem, descA0 + (uint64_t)(c * (SF_TILE >> 4) + ks * 2), descB + (uint64_t)(c * (SF_TILE >> 4) + ks * 2),
+                                 SF_IDESC, (c | ks) ? 1u : 0u);
+                mma_bf16(d_tmem, descAaug, descBaug0 + (uint64_t)((uint32_t)pb.stage * (SF_AUGT >> 4)), SF_IDESC, 1u);   // + |r_k|^2
+                tc_commit(&tmem_full[pa.stage * SF_RBS + r]);
+                tc_commit(&empty_b[pb.stage]);
+                pb.advance(SF_BSTAGES);
+                pa.advance(SF_ACC);
+            }
+            tc_commit(empty_a);
+            iphase ^= 1u;
+        }
+    } else if (warp < SF_EPI_WARPS) {
+        // =========================== epilogue: online softmax over the row ===========================
+        const int q = warp & 3;
+        const int h = (warp >> 2) % SF_HALVES;
+        const int r = (warp >> 2) / SF_HALVES;
+        const int trow = q * 32 + lane;
+        Pipe pa{0, 0}, px{0, 0};
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+            const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
+            const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
+            const int j = rb * SF_BM + r * 128 + trow;
+            const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
+            const float nb2 = -P.beta[b] * LOG2E;                  // t = nb2 * (x + ns - alpha)  (log2 domain)
+            const float cj = nb2 * (nsj - P.alpha[b]);
+            float m = -INFINITY, l = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+            for (int u = u0; u < u1; ++u) {
+                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                       (uint32_t)((pa.stage * SF_RBS + r) * 128 + h * (SF_BN / SF_HALVES));
+                mbar_wait(&tmem_full[pa.stage * SF_RBS + r], pa.phase);
+                tc_fence_after();
+                mbar_wait(&full_x[px.stage], px.phase);
+                const float4 *xs = reinterpret_cast<const float4 *>(sX + px.stage * SF_XT) + h * (SF_BN / SF_HALVES);
+                uint32_t va[32], vb[32];
+                tmem_ld32(tbase, va);
+                tmem_wait32(va);
+                tmem_ld32(tbase + 32, vb);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t(&v)[32] = half == 0 ? va : vb;
+                    if (half == 1) {
+                        tmem_wait32(vb);
+                        // every load of this accumulator has landed: hand it back to the issuer before the math
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[pa.stage * SF_RBS + r]);
+                    }
+                    const float4 *xc = xs + half * 32;
+                    float t[32];
+                    float mc = -INFINITY;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) t[e] = __fmaf_rn(nb2, __uint_as_float(v[e]), cj) + xc[e].w;
+#pragma unroll
+                    for (int e = 0; e + 2 < 32; e += 3) mc = fmaxf(mc, fmax3(t[e], t[e + 1], t[e + 2]));
+                    mc = fmax3(mc, t[30], t[31]);
+                    const float mn = fmaxf(m, mc);
+                    if (mn > -INFINITY) {                           // (a chunk of padding only leaves the state untouched)
+                        const float sc = ex2(m - mn);
+                        l *= sc;
+                        if (XYZ) { sx *= sc; sy *= sc; sz *= sc; }
+                        m = mn;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const float p = ex2(t[e] - mn);
+                            l += p;
+                            if (XYZ) {
+                                const float4 c4 = xc[e];
+                                sx = __fmaf_rn(p, c4.x, sx);
+                                sy = __fmaf_rn(p, c4.y, sy);
+                                sz = __fmaf_rn(p, c4.z, sz);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_x[px.stage]);
+                pa.advance(SF_ACC);
+                px.advance(SF_XSTAGES);
+            }
+            float *o = P.part + ((((size_t)b * P.Jpad + (size_t)j) * P.S + sp) * SF_HALVES + h) * 8;
+            *reinterpret_cast<float4 *>(o) = make_float4(m, l, sx, sy);
+            *reinterpret_cast<float4 *>(o + 4) = make_float4(sz, 0.f, 0.f, 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == SF_WARP_TMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// merge the partial (max, sum, weighted sums) of a row: lse = ln sum_k exp(a_jk), y = sum_k w_jk r_k / sum_k w_jk
+__global__ void soft_finalize_kernel(const float *__restrict__ part, int B, int J, int Jpad, int nparts, float *__restrict__ lse,
+                                     float *__restrict__ y_soft) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= (long long)B * J) return;
+    const int b = (int)(row / J), j = (int)(row % J);
+    const float *p = part + ((size_t)b * Jpad + j) * nparts * 8;
+    float m = -INFINITY;
+    for (int i = 0; i < nparts; ++i) m = fmaxf(m, p[i * 8]);
+    float l = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int i = 0; i < nparts; ++i) {
+        const float sc = p[i * 8] == -INFINITY ? 0.f : exp2f(p[i * 8] - m);
+        l = __fmaf_rn(p[i * 8 + 1], sc, l);
+        sx = __fmaf_rn(p[i * 8 + 2], sc, sx);
+        sy = __fmaf_rn(p[i * 8 + 3], sc, sy);
+        sz = __fmaf_rn(p[i * 8 + 4], sc, sz);
+    }
+    if (lse) lse[row] = (m + log2f(l)) * LN2;
+    if (y_soft) {
+        const float inv = 1.f / l;
+        y_soft[row * 3 + 0] = sx * inv;
+        y_soft[row * 3 + 1] = sy * inv;
+        y_soft[row * 3 + 2] = sz * inv;
+    }
+}
+
+// [B,C,N] fp32 (any strides) -> expanded bf16 [B][N][192]; reference side (is_ref) scaled by -2 and with the norm tile
+// [B][Npad][16] = three-term split of |r|^2.  One block = 32 points.
+__global__ __launch_bounds__(256) void soft_prep_kernel(dsir_feat f, int C, int N, int Npad, int is_ref, const float *__restrict__ nrm,
+                                                        __nv_bfloat16 *__restrict__ out, __nv_bfloat16 *__restrict__ aug,
+                                                        __nv_bfloat16 *__restrict__ aug_const) {
+    __shared__ float tile[SF_CMAX][33];
+    const int b = blockIdx.y, n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float *src = f.ptr + (size_t)b * f.batch_stride;
+    for (int c = ty; c < SF_CMAX; c += 8) {
+        const int n = n0 + tx;
+        tile[c][tx] = (c < C && n < N) ? src[(size_t)c * f.chan_stride + (size_t)n * f.point_stride] : 0.f;
+    }
+    __syncthreads();
+    const int i = threadIdx.x >> 3, g = threadIdx.x & 7;   // point, group of 4 channels
+    const int n = n0 + i;
+    if (n < N) {
+        __align__(8) __nv_bfloat16 hi[4], lo[4], ll[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float v = tile[4 * g + k][i] * (is_ref ? -2.f : 1.f);
+            hi[k] = __float2bfloat16_rn(v);
+            const float r1 = v - __bfloat162float(hi[k]);
+            lo[k] = __float2bfloat16_rn(r1);
+            ll[k] = __float2bfloat16_rn(r1 - __bfloat162float(lo[k]));
+        }
+        // source  [hi|hi|lo|lo|hi|lolo]     reference  [hi|lo|hi|lo|lolo|hi]
+        const __nv_bfloat16 *blk[6];
+        if (is_ref) { blk[0] = hi; blk[1] = lo; blk[2] = hi; blk[3] = lo; blk[4] = ll; blk[5] = hi; }
+        else        { blk[0] = hi; blk[1] = hi; blk[2] = lo; blk[3] = lo; blk[4] = hi; blk[5] = ll; }
+        __nv_bfloat16 *o = out + ((size_t)b * N + n) * SF_CH + 4 * g;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) *reinterpret_cast<uint2 *>(o + q * SF_CMAX) = *reinterpret_cast<const uint2 *>(blk[q]);
+    }
+    if (aug && n < Npad && g < 2) {
+        __align__(16) __nv_bfloat16 hh[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hh[k] = __float2bfloat16_rn(0.f);
+        if (g == 0 && n < N) {
+            const float x = nrm[(size_t)b * N + n];
+            hh[0] = __float2bfloat16_rn(x);
+            const float r1 = x - __bfloat162float(hh[0]);
+            hh[1] = __float2bfloat16_rn(r1);
+            hh[2] = __float2bfloat16_rn(r1 - __bfloat162float(hh[1]));
+        }
+        *reinterpret_cast<uint4 *>(aug + ((size_t)b * Npad + n) * SF_AUG + g * 8) = *reinterpret_cast<const uint4 *>(hh);
+    }
+    if (aug_const && blockIdx.x == 0 && b == 0)
+        for (int t = threadIdx.x; t < 128 * SF_AUG; t += blockDim.x) aug_const[t] = __float2bfloat16_rn((t % SF_AUG) < 3 ? 1.f : 0.f);
+}
+
+// (x, y, z, bias * log2e) per reference point; -inf bias beyond K so that padded columns weigh nothing
+__global__ void soft_xyzc_kernel(const float *__restrict__ xyz, const float *__restrict__ bias, int K, int Kpad, float4 *__restrict__ out) {
+    const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Kpad) return;
+    float4 v = make_float4(0.f, 0.f, 0.f, -INFINITY);
+    if (k < K) {
+        if (xyz) { v.x = xyz[((size_t)b * K + k) * 3]; v.y = xyz[((size_t)b * K + k) * 3 + 1]; v.z = xyz[((size_t)b * K + k) * 3 + 2]; }
+        v.w = bias ? bias[(size_t)b * K + k] * LOG2E : 0.f;
+    }
+    out[(size_t)b * Kpad + k] = v;
+}
+
+struct SoftPlan {
+    int RB, U, S, Jpad, Kpad;
+    size_t off_ns, off_nr, off_a, off_b, off_baug, off_aaug, off_xyzc, off_part, total;
+};
+
+SoftPlan make_soft_plan(int B, int J, int K) {
+    SoftPlan p;
+    p.RB = (J + SF_BM - 1) / SF_BM;
+    p.U = (K + SF_BN - 1) / SF_BN;
+    p.Jpad = p.RB * SF_BM;
+    p.Kpad = p.U * SF_BN;
+    long long items = (long long)B * p.RB;
+    int S = 1;
+    if (items < 2 * 148) {
+        S = (int)((2 * 148 + items - 1) / items);
+        if (S > SF_MAX_SPLIT) S = SF_MAX_SPLIT;
+        if (S > p.U) S = p.U;
+        if (S < 1) S = 1;
+    }
+    p.S = S;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += ws_block(bytes); return o; };
+    p.off_ns = take((size_t)B * J * 4);
+    p.off_nr = take((size_t)B * K * 4);
+    p.off_a = take((size_t)B * J * SF_CH * 2);
+    p.off_b = take((size_t)B * K * SF_CH * 2);
+    p.off_baug = take((size_t)B * p.Kpad * SF_AUG * 2);
+    p.off_aaug = take((size_t)128 * SF_AUG * 2);
+    p.off_xyzc = take((size_t)B * p.Kpad * 16);
+    p.off_part = take((size_t)B * p.Jpad * S * SF_HALVES * 8 * 4);
+    p.total = off + 1024;
+    return p;
+}
+
+constexpr size_t soft_smem_bytes() {
+    return 1024 + (size_t)(SF_RBS + SF_BSTAGES) * SF_CHUNKS * SF_TILE + (size_t)(1 + SF_BSTAGES) * SF_AUGT + (size_t)SF_XSTAGES * SF_XT + 512;
+}
+
+}  // namespace
+
+bool match_tc_soft_supported(int B, int C, int J, int K) {
+    if (C < 1 || C > SF_CMAX) return false;
+    if ((long long)B * J >= (1ll << 31) || (long long)B * K >= (1ll << 31)) return false;
+    static const bool off = getenv("DSIR_SOFT_FP32") != nullptr;
+    if (off) return false;
+    if ((double)B * J * K < 2.0e6) return false;   // tiny problems: the prep launches dominate
+    return soft_encode_fn() != nullptr;
+}
+
+size_t match_tc_soft_workspace_bytes(int B, int C, int J, int K) {
+    (void)C;
+    return make_soft_plan(B, J, K).total;
+}
+
+int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const SoftPlan pl = make_soft_plan(P.B, P.J, P.K);
+    char *base = (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    if (ws == nullptr || (size_t)(base - (char *)ws) + pl.total - 1024 > ws_bytes) return DSIR_ERR_WORKSPACE;
+    float *ns = (float *)(base + pl.off_ns), *nr = (float *)(base + pl.off_nr);
+    __nv_bfloat16 *a = (__nv_bfloat16 *)(base + pl.off_a), *bexp = (__nv_bfloat16 *)(base + pl.off_b);
+    __nv_bfloat16 *baug = (__nv_bfloat16 *)(base + pl.off_baug), *aaug = (__nv_bfloat16 *)(base + pl.off_aaug);
+    float4 *xyzc = (float4 *)(base + pl.off_xyzc);
+    float *part = (float *)(base + pl.off_part);
+    int rc;
+    if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, ns, st))) return rc;
+    if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, nr, st))) return rc;
+    soft_prep_kernel<<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, 0, nullptr, a, nullptr, aaug);
+    DSIR_LAUNCH_CHECK();
+    soft_prep_kernel<<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, 1, nr, bexp, baug, nullptr);
+    DSIR_LAUNCH_CHECK();
+    soft_xyzc_kernel<<<dim3(cdiv(pl.Kpad, 256), P.B), 256, 0, st>>>(P.y_soft ? P.xyz_ref : nullptr, P.col_bias, P.K, pl.Kpad, xyzc);
+    DSIR_LAUNCH_CHECK();
+    CUtensorMap mapA, mapB, mapAaug, mapBaug;
+    if (!make_bf16_tmap(&mapA, a, P.B, P.J, SF_CH, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_bf16_tmap(&mapB, bexp, P.B, P.K, SF_CH, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_bf16_tmap(&mapAaug, aaug, 1, 128, SF_AUG, SF_AUG, CU_TENSOR_MAP_SWIZZLE_32B) ||
+        !make_bf16_tmap(&mapBaug, baug, P.B, pl.Kpad, SF_AUG, SF_AUG, CU_TENSOR_MAP_SWIZZLE_32B))
+        return DSIR_ERR_UNSUPPORTED;
+    SoftParams T{};
+    T.B = P.B; T.J = P.J; T.K = P.K; T.C = P.C; T.RB = pl.RB; T.U = pl.U; T.S = pl.S; T.Jpad = pl.Jpad; T.Kpad = pl.Kpad;
+    T.ns = ns; T.beta = P.beta; T.alpha = P.alpha; T.xyzc = xyzc; T.part = part;
+    const int items = P.B * pl.RB * pl.S;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = items < sms ? items : sms;
+    const size_t smem = soft_smem_bytes();
+    if (P.y_soft) {
+        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_soft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        match_tc_soft_kernel<true><<<grid, SF_THREADS, smem, st>>>(mapA, mapB, mapAaug, mapBaug, T);
+    } else {
+        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_soft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        match_tc_soft_kernel<false><<<grid, SF_THREADS, smem, st>>>(mapA, mapB, mapAaug, mapBaug, T);
+    }
+    DSIR_LAUNCH_CHECK();
+    const long long rows = (long long)P.B * P.J;
+    soft_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(part, P.B, P.J, pl.Jpad, pl.S * SF_HALVES, P.lse, P.y_soft);
+    DSIR_LAUNCH_CHECK();
+    return DSIR_OK;
+}
+
+}  // namespace dsir

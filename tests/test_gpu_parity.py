@@ -655,3 +655,29 @@ def test_match_c4_full_size_properties():
     assert torch.equal(part, idx[:, lo:hi])
     exact = D.match_argmin(fs[:, :, lo:hi], fr, algo=D.MATCH_FP32)
     assert torch.equal(exact, part)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 3000, 2777), (1, 20, 1500, 4100), (3, 32, 700, 1100)])
+def test_match_soft_tensor_core_path(shape):
+    """The tcgen05 soft match (bf16 x3 split contraction + online softmax in the TMEM epilogue; C <= 32 and B*J*K >= 2e6):
+    lse, soft targets and reconstructed weights against the fp32 oracle, with and without a column bias, J/K not
+    multiples of the tile."""
+    B, C, J, K = shape
+    b = synth.make_batch(B, max(J, K), C, "3dmatch", config=3, first_pair=50)
+    fs, fr = b["feat_src"][:, :, :J].contiguous(), b["feat_ref"][:, :, :K].contiguous()
+    xyz = b["points_ref"][:, :K, :3].contiguous()
+    beta = torch.tensor([10.0, 6.0, 3.0][:B])
+    alpha = torch.tensor([0.5, 0.3, 0.1][:B])
+    w, y, s, lse = O.soft_correspondence(fs, fr, xyz, beta, alpha)
+    y_g, s_g, lse_g = D.match_soft(cu(fs), cu(fr), cu(xyz), cu(beta), cu(alpha))
+    assert torch.allclose(lse_g.cpu(), lse, rtol=SOFT_RTOL, atol=1e-5)
+    assert torch.allclose(y_g.cpu(), y, rtol=SOFT_RTOL, atol=1e-4)
+    a = O.compute_affinity(beta, O.match_features_V2(fs, fr), alpha)
+    w_g = torch.exp(a - lse_g.cpu()[:, :, None])
+    big = w > 1e-6
+    assert ((w_g - w).abs()[big] / w[big]).max() < 5 * SOFT_RTOL
+    # column bias (the Sinkhorn sweeps): lse_j = log sum_k exp(a_jk + bias_k)
+    bias = torch.randn(B, K, generator=torch.Generator().manual_seed(K)) * 2
+    _, _, lse_b = D.match_soft(cu(fs), cu(fr), None, cu(beta), cu(alpha), col_bias=cu(bias))
+    ref = torch.logsumexp(a + bias[:, None, :], dim=2)
+    assert torch.allclose(lse_b.cpu(), ref, rtol=SOFT_RTOL, atol=1e-5)
