@@ -9,22 +9,20 @@
 // single-pass fp16/bf16/tf32 operands (2^-9 .. 2^-11 relative) are three orders of magnitude short.  The operands are
 // therefore split three ways into bf16,  v = hi + lo + lolo  (24 significant bits), and the six products that matter
 //     hi*hi, hi*lo, lo*hi, lo*lo, hi*lolo, lolo*hi            (everything else is below 2^-24 |s||r|)
-// are laid out side by side along the contraction axis: an expanded point has 6 x 32 = 192 bf16 channels
-//     source     [hi | hi | lo | lo | hi   | lolo]
-//     reference  [hi | lo | hi | lo | lolo | hi  ] * (-2)      (exact)
-// so that ONE K = 192 contraction with fp32 accumulation yields -2<s,r> to fp32 accuracy; 16 more channels fold in the
-// three-term split of |r_k|^2 (source side 1,1,1,0..).  13 tcgen05.mma (M=128, N=128, K=16, kind::f16 with bf16 inputs)
-// per 128 x 128 tile.
+// are formed by SIX groups of MMAs over sub-blocks of one 128-channel bf16 row per point
+//     [ hi (32) | lo (32) | lolo (32) | norm (16) | pad (16) ]        (reference features scaled by -2, exact)
+// selected through the K-offset of the shared-memory descriptors, so that the operand tiles are only 3x (not 6x) the
+// one-pass size and a reference tile (32 KB) is shared by FOUR 128-row blocks: the kernel is otherwise bound by the
+// L2 -> shared-memory operand traffic.  The norm block folds the three-term split of |r_k|^2 into the contraction
+// (source side 1,1,1,0..).  13 tcgen05.mma (M=128, N=128, K=16, kind::f16 with bf16 inputs) per 128 x 128 tile.
 //
-//   warp 16      TMA producer: the source tiles of an item once (2 row blocks x 3 chunks x 16 KB), a 2-stage ring of
-//                reference tiles (3 x 16 KB + 4 KB norm tile), a 4-stage ring of (x, y, z, column bias) float4 per
-//                reference point (1-D bulk copies)
-//   warps 17-18  MMA issuers, one per row block; each row block owns two 128-column accumulators (double buffered), so
-//                the tensor pipe works on unit t+1 while unit t is being drained
-//   warps 0-15   epilogue: warp = (row block, column half, TMEM lane quadrant), thread = one source row.  Per 32
-//                columns: t_e = -beta' (x_e + |s|^2 - alpha) (+ bias), chunk maximum, ONE rescale of the running state,
-//                then p_e = 2^(t_e - m) (MUFU.EX2) accumulated into the sum and the three weighted coordinates.
-// Partial states of the two column halves (and of the K-splits) are merged by a small finalize kernel.
+//   warp 16      TMA producer: the source tiles of an item once (4 row blocks x 2 chunks x 16 KB), a 2-stage ring of
+//                reference tiles (2 x 16 KB), a 4-stage ring of (x, y, z, column bias) float4 per reference point
+//   warps 17-18  MMA issuers (row blocks w, w + 2): four single-stage 128-column accumulators fill the 512 TMEM columns
+//   warps 0-15   epilogue: warp = (row block, TMEM lane quadrant), thread = one source row.  Per 32 columns:
+//                t_e = -beta' (x_e + |s|^2 - alpha) (+ bias), chunk maximum, ONE rescale of the running state, then
+//                p_e = 2^(t_e - m) (MUFU.EX2) accumulated into the sum and the three weighted coordinates.
+// Partial states of the K-splits are merged by a small finalize kernel.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -36,21 +34,20 @@ namespace dsir {
 
 namespace {
 
-constexpr int SF_RBS = 2, SF_ACC = 2, SF_HALVES = 2, SF_BSTAGES = 2, SF_XSTAGES = 4;
+constexpr int SF_RBS = 4, SF_ACC = 1, SF_HALVES = 1, SF_BSTAGES = 2, SF_XSTAGES = 4;
+constexpr int SF_MMA_WARPS = 2;
 constexpr int SF_BM = 128 * SF_RBS, SF_BN = 128;
 constexpr int SF_EPI_WARPS = 4 * SF_RBS * SF_HALVES;        // 16
 constexpr int SF_WARP_TMA = SF_EPI_WARPS, SF_WARP_MMA0 = SF_EPI_WARPS + 1;
-constexpr int SF_THREADS = (SF_EPI_WARPS + 1 + SF_RBS) * 32;   // 608
+constexpr int SF_THREADS = (SF_EPI_WARPS + 1 + SF_MMA_WARPS) * 32;   // 608
 constexpr int SF_CMAX = 32;                                  // channels supported by this path
-constexpr int SF_CH = 6 * SF_CMAX;                           // expanded channels per point
+constexpr int SF_CH = 128;                                   // bf16 channels per point: hi | lo | lolo | norm(16) | pad(16)
 constexpr int SF_CHUNKS = SF_CH / 64;                        // 64-channel (128-byte) TMA boxes per row
-constexpr int SF_AUG = 16;
 constexpr int SF_MAX_SPLIT = 8;
 constexpr uint32_t SF_TILE = 128 * 64 * 2;                   // 16 KB
-constexpr uint32_t SF_AUGT = 128 * SF_AUG * 2;               //  4 KB
-constexpr uint32_t SF_XT = 128 * 16;                         //  2 KB of float4 per unit
+constexpr uint32_t SF_XT = 128 * 16 + 128 * 4;               //  (x, y, z, 1) float4 + bias float per reference point of a unit
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-static_assert(SF_RBS * SF_ACC * 128 == 512, "TMEM budget");
+static_assert(SF_RBS * SF_ACC * 128 == 512 && SF_HALVES == 1 && SF_RBS % SF_MMA_WARPS == 0, "TMEM / warp budget");
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -132,6 +129,40 @@ __device__ __forceinline__ void tmem_wait32(uint32_t (&r)[32]) {
                  :
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+// explicit shared-space loads (the generic pointer arithmetic on the dynamic smem base would compile to generic LD)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100): two lanes of a 64-bit register pair per instruction
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -167,41 +198,99 @@ struct SoftParams {
     int RB, U, S, Jpad, Kpad;
     const float *ns;         // [B,J] exact squared norms
     const float *beta, *alpha;   // [B]
-    const float4 *xyzc;      // [B][Kpad] (x, y, z, bias * log2e; -inf beyond K)
-    float *part;             // [B][Jpad][S][HALVES][8]: m, l, sx, sy, sz (log2 domain)
+    const float4 *xyz1;      // [B][Kpad] (x, y, z, 1)
+    const float *bias2;      // [B][Kpad] column bias * log2e
+    float *part;             // [B][Jpad][S][8]: m, l, sx, sy, sz (log2 domain)
 };
 
-template <bool XYZ>
+// one 16-column step of the online softmax of one row: v = accumulator values x_jk = |r_k|^2 - 2<s_j,r_k>.
+// (16 rather than 32 columns per step: with 32 the live registers - the step's values, the prefetched next step, the
+// running state - leave no room to keep several (x, y, z) loads in flight and their latency is exposed one by one.)
+constexpr int SW = 16;
+// Running state of a row: m (log2 domain) and two packed pairs, s01 = (sum p x, sum p y), s23 = (sum p z, sum p) with
+// XYZ, s23 = (sum of the even columns' p, sum of the odd columns' p) without.  Everything per column is one FADD2 (half),
+// one MUFU.EX2, one LDS.128 of (x, y, z, 1) and two FFMA2 with p as the scalar operand.
+template <bool XYZ, bool BIAS>
+__device__ __forceinline__ void soft_step(const uint32_t (&v)[SW], uint32_t xs /* shared address of the step's float4[16] */,
+                                          uint32_t bs /* shared address of the step's bias[16] */, int lane, int valid, float nb2,
+                                          float cj, float &m, f32x2 &s01, f32x2 &s23) {
+    f32x2 t2[SW / 2];
+    const f32x2 nb22 = pack2(nb2, nb2), cj2 = pack2(cj, cj);
+#pragma unroll
+    for (int e = 0; e < SW; e += 2) t2[e / 2] = fma2(pack2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), nb22, cj2);
+    float t[SW];
+#pragma unroll
+    for (int e = 0; e < SW; e += 2) unpack2(t2[e / 2], t[e], t[e + 1]);
+    if (BIAS) {
+        // the bias of the 16 columns: one conflict-free load per lane (lane e holds column e), broadcast by shuffles
+        const float mine = lds32(bs + (lane & (SW - 1)) * 4);
+#pragma unroll
+        for (int e = 0; e < SW; ++e) t[e] += __shfl_sync(0xffffffffu, mine, e);
+    }
+    if (valid < SW) {
+#pragma unroll
+        for (int e = 0; e < SW; ++e) t[e] = e < valid ? t[e] : -INFINITY;   // padding beyond K weighs nothing
+    }
+    float mc = fmax3(t[0], t[1], t[2]);
+#pragma unroll
+    for (int e = 3; e + 2 < SW; e += 3) mc = fmaxf(mc, fmax3(t[e], t[e + 1], t[e + 2]));
+    mc = fmaxf(mc, t[SW - 1]);
+    const float mn = fmaxf(m, mc);
+    if (mn > -INFINITY) {                        // (a step of padding only leaves the state untouched)
+        const float sc = ex2(m - mn);
+        const f32x2 sc2 = pack2(sc, sc);
+        if (XYZ) s01 = mul2(s01, sc2);
+        s23 = mul2(s23, sc2);
+        m = mn;
+        const f32x2 nm2 = pack2(-mn, -mn);
+        float4 c4[SW];
+        if (XYZ) {
+#pragma unroll
+            for (int e = 0; e < SW; ++e) c4[e] = lds128(xs + e * 16);   // broadcast loads of (x, y, z, 1), all in flight together
+        }
+#pragma unroll
+        for (int e = 0; e < SW; e += 2) {
+            float a0, a1;
+            unpack2(add2(pack2(t[e], t[e + 1]), nm2), a0, a1);
+            const float p0 = ex2(a0), p1 = ex2(a1);
+            if (XYZ) {
+                s01 = fma2(pack2(c4[e].x, c4[e].y), pack2(p0, p0), s01);
+                s23 = fma2(pack2(c4[e].z, c4[e].w), pack2(p0, p0), s23);
+                s01 = fma2(pack2(c4[e + 1].x, c4[e + 1].y), pack2(p1, p1), s01);
+                s23 = fma2(pack2(c4[e + 1].z, c4[e + 1].w), pack2(p1, p1), s23);
+            } else {
+                s23 = add2(s23, pack2(p0, p1));
+            }
+        }
+    }
+}
+
+template <bool XYZ, bool BIAS>
 __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                      const __grid_constant__ CUtensorMap mapB,
-                                                                      const __grid_constant__ CUtensorMap mapAaug,
-                                                                      const __grid_constant__ CUtensorMap mapBaug,
-                                                                      SoftParams P) {
+                                                                      const __grid_constant__ CUtensorMap mapB, SoftParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;                                             // [RBS][CHUNKS][16 KB]
     uint8_t *sB = sA + SF_RBS * SF_CHUNKS * SF_TILE;                // [BSTAGES][CHUNKS][16 KB]
-    uint8_t *sAaug = sB + SF_BSTAGES * SF_CHUNKS * SF_TILE;         // [4 KB]
-    uint8_t *sBaug = sAaug + SF_AUGT;                               // [BSTAGES][4 KB]
-    uint8_t *sX = sBaug + SF_BSTAGES * SF_AUGT;                     // [XSTAGES][2 KB]
+    uint8_t *sX = sB + SF_BSTAGES * SF_CHUNKS * SF_TILE;            // [XSTAGES][2 KB]
     uint64_t *bars = (uint64_t *)(sX + SF_XSTAGES * SF_XT);
     uint64_t *full_b = bars, *empty_b = full_b + SF_BSTAGES;
     uint64_t *full_x = empty_b + SF_BSTAGES, *empty_x = full_x + SF_XSTAGES;
-    uint64_t *tmem_full = empty_x + SF_XSTAGES;                     // [ACC][RBS]
-    uint64_t *tmem_empty = tmem_full + SF_ACC * SF_RBS;
-    uint64_t *full_a = tmem_empty + SF_ACC * SF_RBS, *empty_a = full_a + 1;
+    uint64_t *tmem_full = empty_x + SF_XSTAGES;                     // [RBS]
+    uint64_t *tmem_empty = tmem_full + SF_RBS;
+    uint64_t *full_a = tmem_empty + SF_RBS, *empty_a = full_a + 1;
     uint32_t *tmem_slot = (uint32_t *)(empty_a + 1);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int total_items = P.B * P.RB * P.S;
 
     if (warp == SF_WARP_TMA && lane == 0) {
-        prefetch_tmap(&mapA); prefetch_tmap(&mapB); prefetch_tmap(&mapAaug); prefetch_tmap(&mapBaug);
-        for (int s = 0; s < SF_BSTAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], SF_RBS); }
+        prefetch_tmap(&mapA); prefetch_tmap(&mapB);
+        for (int s = 0; s < SF_BSTAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], SF_MMA_WARPS); }
         for (int s = 0; s < SF_XSTAGES; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], SF_EPI_WARPS); }
-        for (int a = 0; a < SF_ACC * SF_RBS; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4 * SF_HALVES); }
+        for (int a = 0; a < SF_RBS; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
         mbar_init(full_a, 1);
-        mbar_init(empty_a, SF_RBS);
+        mbar_init(empty_a, SF_MMA_WARPS);
         mbar_fence_init();
     }
     if (warp == SF_WARP_TMA) tmem_alloc(tmem_slot, 512);
@@ -215,76 +304,77 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
         if (lane == 0) {
             Pipe pb{0, 0}, px{0, 0};
             uint32_t iphase = 0;
-            bool first = true;
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
                 const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
                 const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
                 mbar_wait(empty_a, iphase ^ 1u);
-                mbar_expect_tx(full_a, SF_RBS * SF_CHUNKS * SF_TILE + (first ? SF_AUGT : 0u));
+                mbar_expect_tx(full_a, SF_RBS * SF_CHUNKS * SF_TILE);
 #pragma unroll
                 for (int r = 0; r < SF_RBS; ++r)
 #pragma unroll
                     for (int c = 0; c < SF_CHUNKS; ++c)
                         tma_load_3d(sA + (r * SF_CHUNKS + c) * SF_TILE, &mapA, c * 64, rb * SF_BM + r * 128, b, full_a);
-                if (first) tma_load_3d(sAaug, &mapAaug, 0, 0, 0, full_a);
-                first = false;
                 for (int u = u0; u < u1; ++u) {
                     while (!mbar_try_wait(&empty_x[px.stage], px.phase ^ 1u)) __nanosleep(32);
                     mbar_expect_tx(&full_x[px.stage], SF_XT);
-                    bulk_g2s(sX + px.stage * SF_XT, P.xyzc + (size_t)b * P.Kpad + (size_t)u * SF_BN, SF_XT, &full_x[px.stage]);
+                    bulk_g2s(sX + px.stage * SF_XT, P.xyz1 + (size_t)b * P.Kpad + (size_t)u * SF_BN, SF_BN * 16, &full_x[px.stage]);
+                    bulk_g2s(sX + px.stage * SF_XT + SF_BN * 16, P.bias2 + (size_t)b * P.Kpad + (size_t)u * SF_BN, SF_BN * 4, &full_x[px.stage]);
                     px.advance(SF_XSTAGES);
                     while (!mbar_try_wait(&empty_b[pb.stage], pb.phase ^ 1u)) __nanosleep(32);
-                    mbar_expect_tx(&full_b[pb.stage], SF_CHUNKS * SF_TILE + SF_AUGT);
+                    mbar_expect_tx(&full_b[pb.stage], SF_CHUNKS * SF_TILE);
 #pragma unroll
                     for (int c = 0; c < SF_CHUNKS; ++c)
                         tma_load_3d(sB + (pb.stage * SF_CHUNKS + c) * SF_TILE, &mapB, c * 64, u * SF_BN, b, &full_b[pb.stage]);
-                    tma_load_3d(sBaug + pb.stage * SF_AUGT, &mapBaug, 0, u * SF_BN, b, &full_b[pb.stage]);
                     pb.advance(SF_BSTAGES);
                 }
                 iphase ^= 1u;
             }
         }
-    } else if (warp >= SF_WARP_MMA0 && warp < SF_WARP_MMA0 + SF_RBS) {
-        // =========================== MMA issuer of row block r ===========================
-        const int r = warp - SF_WARP_MMA0;
-        Pipe pb{0, 0}, pa{0, 0};
-        uint32_t iphase = 0;
-        const uint64_t descA0 = make_kmajor_desc(smem_u32(sA + r * SF_CHUNKS * SF_TILE), 1024, 2);
-        const uint64_t descAaug = make_kmajor_desc(smem_u32(sAaug), 256, 6);
+    } else if (warp >= SF_WARP_MMA0 && warp < SF_WARP_MMA0 + SF_MMA_WARPS) {
+        // =========================== MMA issuer (row blocks w, w + 2) ===========================
+        const int w = warp - SF_WARP_MMA0;
+        Pipe pb{0, 0};
+        uint32_t iphase = 0, aphase = 0;
+        const uint64_t descA0 = make_kmajor_desc(smem_u32(sA), 1024, 2);
         const uint64_t descB0 = make_kmajor_desc(smem_u32(sB), 1024, 2);
-        const uint64_t descBaug0 = make_kmajor_desc(smem_u32(sBaug), 256, 6);
+        // sub-blocks of the 128-channel row, as descriptor offsets (16-byte units): chunk 0 = hi | lo, chunk 1 = lolo | norm
+        constexpr uint32_t HI = 0, LO = 4, LL = SF_TILE >> 4, NRM = (SF_TILE >> 4) + 4;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int sp = it % P.S;
             const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
             mbar_wait(full_a, iphase);
             for (int u = u0; u < u1; ++u) {
                 mbar_wait(&full_b[pb.stage], pb.phase);
-                mbar_wait(&tmem_empty[pa.stage * SF_RBS + r], pa.phase ^ 1u);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)((pa.stage * SF_RBS + r) * 128);
                 const uint64_t descB = descB0 + (uint64_t)((uint32_t)pb.stage * ((SF_CHUNKS * SF_TILE) >> 4));
 #pragma unroll
-                for (int c = 0; c < SF_CHUNKS; ++c)
+                for (int r = w; r < SF_RBS; r += SF_MMA_WARPS) {
+                    mbar_wait(&tmem_empty[r], aphase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(r * 128);
+                    const uint64_t descA = descA0 + (uint64_t)(r * ((SF_CHUNKS * SF_TILE) >> 4));
+                    // six product groups, largest first: hi*hi, hi*lo, lo*hi, lo*lo, hi*lolo, lolo*hi (2 k-steps of 16 each)
+                    const uint32_t ao[6] = {HI, HI, LO, LO, HI, LL}, bo[6] = {HI, LO, HI, LO, LL, HI};
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)      // +32 bytes (16 bf16) inside the 128-byte swizzle row
-                        mma_bf16(d_tmem, descA0 + (uint64_t)(c * (SF_TILE >> 4) + ks * 2), descB + (uint64_t)(c * (SF_TILE >> 4) + ks * 2),
-                                 SF_IDESC, (c | ks) ? 1u : 0u);
-                mma_bf16(d_tmem, descAaug, descBaug0 + (uint64_t)((uint32_t)pb.stage * (SF_AUGT >> 4)), SF_IDESC, 1u);   // + |r_k|^2
-                tc_commit(&tmem_full[pa.stage * SF_RBS + r]);
+                    for (int g = 0; g < 6; ++g)
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                            mma_bf16(d_tmem, descA + (uint64_t)(ao[g] + ks * 2), descB + (uint64_t)(bo[g] + ks * 2), SF_IDESC, (g | ks) ? 1u : 0u);
+                    mma_bf16(d_tmem, descA + (uint64_t)NRM, descB + (uint64_t)NRM, SF_IDESC, 1u);   // + |r_k|^2
+                    tc_commit(&tmem_full[r]);
+                }
                 tc_commit(&empty_b[pb.stage]);
                 pb.advance(SF_BSTAGES);
-                pa.advance(SF_ACC);
+                aphase ^= 1u;
             }
             tc_commit(empty_a);
             iphase ^= 1u;
         }
     } else if (warp < SF_EPI_WARPS) {
         // =========================== epilogue: online softmax over the row ===========================
-        const int q = warp & 3;
-        const int h = (warp >> 2) % SF_HALVES;
-        const int r = (warp >> 2) / SF_HALVES;
+        const int q = warp & 3, r = warp >> 2;
         const int trow = q * 32 + lane;
-        Pipe pa{0, 0}, px{0, 0};
+        Pipe px{0, 0};
+        uint32_t aphase = 0;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
             const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
@@ -292,61 +382,43 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
             const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
             const float nb2 = -P.beta[b] * LOG2E;                  // t = nb2 * (x + ns - alpha)  (log2 domain)
             const float cj = nb2 * (nsj - P.alpha[b]);
-            float m = -INFINITY, l = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+            float m = -INFINITY;
+            f32x2 s01 = pack2(0.f, 0.f), s23 = pack2(0.f, 0.f);
             for (int u = u0; u < u1; ++u) {
-                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) +
-                                       (uint32_t)((pa.stage * SF_RBS + r) * 128 + h * (SF_BN / SF_HALVES));
-                mbar_wait(&tmem_full[pa.stage * SF_RBS + r], pa.phase);
+                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * 128);
+                mbar_wait(&tmem_full[r], aphase);
                 tc_fence_after();
                 mbar_wait(&full_x[px.stage], px.phase);
-                const float4 *xs = reinterpret_cast<const float4 *>(sX + px.stage * SF_XT) + h * (SF_BN / SF_HALVES);
-                uint32_t va[32], vb[32];
-                tmem_ld32(tbase, va);
-                tmem_wait32(va);
-                tmem_ld32(tbase + 32, vb);
+                const uint32_t xs = smem_u32(sX + px.stage * SF_XT), bs = xs + SF_BN * 16;
+                const int valid0 = P.K - u * SF_BN;                // columns < valid are real
+                uint32_t va[SW], vb[SW];
+                tmem_ld16(tbase, va);
+                constexpr int NST = SF_BN / SW;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t(&v)[32] = half == 0 ? va : vb;
-                    if (half == 1) {
-                        tmem_wait32(vb);
-                        // every load of this accumulator has landed: hand it back to the issuer before the math
+                for (int g = 0; g < NST; g += 2) {                 // ping-pong: the next 16 columns fly during this step's math
+                    tmem_wait16(va);
+                    tmem_ld16(tbase + (g + 1) * SW, vb);
+                    soft_step<XYZ, BIAS>(va, xs + g * SW * 16, bs + g * SW * 4, lane, valid0 - g * SW, nb2, cj, m, s01, s23);
+                    tmem_wait16(vb);
+                    if (g + 2 < NST) {
+                        tmem_ld16(tbase + (g + 2) * SW, va);
+                    } else {                                       // every load of the accumulator has landed: hand it back
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[pa.stage * SF_RBS + r]);
+                        if (lane == 0) mbar_arrive(&tmem_empty[r]);
                     }
-                    const float4 *xc = xs + half * 32;
-                    float t[32];
-                    float mc = -INFINITY;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) t[e] = __fmaf_rn(nb2, __uint_as_float(v[e]), cj) + xc[e].w;
-#pragma unroll
-                    for (int e = 0; e + 2 < 32; e += 3) mc = fmaxf(mc, fmax3(t[e], t[e + 1], t[e + 2]));
-                    mc = fmax3(mc, t[30], t[31]);
-                    const float mn = fmaxf(m, mc);
-                    if (mn > -INFINITY) {                           // (a chunk of padding only leaves the state untouched)
-                        const float sc = ex2(m - mn);
-                        l *= sc;
-                        if (XYZ) { sx *= sc; sy *= sc; sz *= sc; }
-                        m = mn;
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const float p = ex2(t[e] - mn);
-                            l += p;
-                            if (XYZ) {
-                                const float4 c4 = xc[e];
-                                sx = __fmaf_rn(p, c4.x, sx);
-                                sy = __fmaf_rn(p, c4.y, sy);
-                                sz = __fmaf_rn(p, c4.z, sz);
-                            }
-                        }
-                    }
+                    soft_step<XYZ, BIAS>(vb, xs + (g + 1) * SW * 16, bs + (g + 1) * SW * 4, lane, valid0 - (g + 1) * SW, nb2, cj, m, s01, s23);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_x[px.stage]);
-                pa.advance(SF_ACC);
                 px.advance(SF_XSTAGES);
+                aphase ^= 1u;
             }
-            float *o = P.part + ((((size_t)b * P.Jpad + (size_t)j) * P.S + sp) * SF_HALVES + h) * 8;
+            float sx, sy, sz, l;
+            unpack2(s01, sx, sy);
+            unpack2(s23, sz, l);
+            if (!XYZ) { l += sz; sz = 0.f; }      // (even, odd) column sums
+            float *o = P.part + (((size_t)b * P.Jpad + (size_t)j) * P.S + sp) * 8;
             *reinterpret_cast<float4 *>(o) = make_float4(m, l, sx, sy);
             *reinterpret_cast<float4 *>(o + 4) = make_float4(sz, 0.f, 0.f, 0.f);
         }
@@ -385,11 +457,11 @@ __global__ void soft_finalize_kernel(const float *__restrict__ part, int B, int 
     }
 }
 
-// [B,C,N] fp32 (any strides) -> expanded bf16 [B][N][192]; reference side (is_ref) scaled by -2 and with the norm tile
-// [B][Npad][16] = three-term split of |r|^2.  One block = 32 points.
-__global__ __launch_bounds__(256) void soft_prep_kernel(dsir_feat f, int C, int N, int Npad, int is_ref, const float *__restrict__ nrm,
-                                                        __nv_bfloat16 *__restrict__ out, __nv_bfloat16 *__restrict__ aug,
-                                                        __nv_bfloat16 *__restrict__ aug_const) {
+// [B,C,N] fp32 (any strides) -> bf16 [B][N][128] = hi(32) | lo(32) | lolo(32) | norm(16) | 0(16); the reference side
+// (is_ref) carries -2 f (exact) and the three-term split of |r|^2 in the norm block, the source side 1,1,1,0...
+// One block = 32 points; thread = (point, group of 4 channels).
+__global__ __launch_bounds__(256) void soft_prep_kernel(dsir_feat f, int C, int N, int is_ref, const float *__restrict__ nrm,
+                                                        __nv_bfloat16 *__restrict__ out) {
     __shared__ float tile[SF_CMAX][33];
     const int b = blockIdx.y, n0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -399,58 +471,53 @@ __global__ __launch_bounds__(256) void soft_prep_kernel(dsir_feat f, int C, int 
         tile[c][tx] = (c < C && n < N) ? src[(size_t)c * f.chan_stride + (size_t)n * f.point_stride] : 0.f;
     }
     __syncthreads();
-    const int i = threadIdx.x >> 3, g = threadIdx.x & 7;   // point, group of 4 channels
+    const int i = threadIdx.x >> 3, g = threadIdx.x & 7;
     const int n = n0 + i;
-    if (n < N) {
-        __align__(8) __nv_bfloat16 hi[4], lo[4], ll[4];
+    if (n >= N) return;
+    __align__(8) __nv_bfloat16 hi[4], lo[4], ll[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float v = tile[4 * g + k][i] * (is_ref ? -2.f : 1.f);
-            hi[k] = __float2bfloat16_rn(v);
-            const float r1 = v - __bfloat162float(hi[k]);
-            lo[k] = __float2bfloat16_rn(r1);
-            ll[k] = __float2bfloat16_rn(r1 - __bfloat162float(lo[k]));
-        }
-        // source  [hi|hi|lo|lo|hi|lolo]     reference  [hi|lo|hi|lo|lolo|hi]
-        const __nv_bfloat16 *blk[6];
-        if (is_ref) { blk[0] = hi; blk[1] = lo; blk[2] = hi; blk[3] = lo; blk[4] = ll; blk[5] = hi; }
-        else        { blk[0] = hi; blk[1] = hi; blk[2] = lo; blk[3] = lo; blk[4] = hi; blk[5] = ll; }
-        __nv_bfloat16 *o = out + ((size_t)b * N + n) * SF_CH + 4 * g;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) *reinterpret_cast<uint2 *>(o + q * SF_CMAX) = *reinterpret_cast<const uint2 *>(blk[q]);
+    for (int k = 0; k < 4; ++k) {
+        const float v = tile[4 * g + k][i] * (is_ref ? -2.f : 1.f);
+        hi[k] = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(hi[k]);
+        lo[k] = __float2bfloat16_rn(r1);
+        ll[k] = __float2bfloat16_rn(r1 - __bfloat162float(lo[k]));
     }
-    if (aug && n < Npad && g < 2) {
-        __align__(16) __nv_bfloat16 hh[8];
+    __nv_bfloat16 *o = out + ((size_t)b * N + n) * SF_CH;
+    *reinterpret_cast<uint2 *>(o + 4 * g) = *reinterpret_cast<const uint2 *>(hi);
+    *reinterpret_cast<uint2 *>(o + 32 + 4 * g) = *reinterpret_cast<const uint2 *>(lo);
+    *reinterpret_cast<uint2 *>(o + 64 + 4 * g) = *reinterpret_cast<const uint2 *>(ll);
+    __align__(8) __nv_bfloat16 t4[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) hh[k] = __float2bfloat16_rn(0.f);
-        if (g == 0 && n < N) {
+    for (int k = 0; k < 4; ++k) t4[k] = __float2bfloat16_rn(0.f);
+    if (g == 0) {
+        if (is_ref) {
             const float x = nrm[(size_t)b * N + n];
-            hh[0] = __float2bfloat16_rn(x);
-            const float r1 = x - __bfloat162float(hh[0]);
-            hh[1] = __float2bfloat16_rn(r1);
-            hh[2] = __float2bfloat16_rn(r1 - __bfloat162float(hh[1]));
+            t4[0] = __float2bfloat16_rn(x);
+            const float r1 = x - __bfloat162float(t4[0]);
+            t4[1] = __float2bfloat16_rn(r1);
+            t4[2] = __float2bfloat16_rn(r1 - __bfloat162float(t4[1]));
+        } else {
+            t4[0] = t4[1] = t4[2] = __float2bfloat16_rn(1.f);
         }
-        *reinterpret_cast<uint4 *>(aug + ((size_t)b * Npad + n) * SF_AUG + g * 8) = *reinterpret_cast<const uint4 *>(hh);
     }
-    if (aug_const && blockIdx.x == 0 && b == 0)
-        for (int t = threadIdx.x; t < 128 * SF_AUG; t += blockDim.x) aug_const[t] = __float2bfloat16_rn((t % SF_AUG) < 3 ? 1.f : 0.f);
+    *reinterpret_cast<uint2 *>(o + 96 + 4 * g) = *reinterpret_cast<const uint2 *>(t4);   // norm block (g < 4) and padding (g >= 4)
 }
 
-// (x, y, z, bias * log2e) per reference point; -inf bias beyond K so that padded columns weigh nothing
-__global__ void soft_xyzc_kernel(const float *__restrict__ xyz, const float *__restrict__ bias, int K, int Kpad, float4 *__restrict__ out) {
+// (x, y, z, 1) and bias * log2e per reference point (zeros beyond K: those columns are masked by their index)
+__global__ void soft_xyzc_kernel(const float *__restrict__ xyz, const float *__restrict__ bias, int K, int Kpad, float4 *__restrict__ out,
+                                 float *__restrict__ bias2) {
     const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Kpad) return;
-    float4 v = make_float4(0.f, 0.f, 0.f, -INFINITY);
-    if (k < K) {
-        if (xyz) { v.x = xyz[((size_t)b * K + k) * 3]; v.y = xyz[((size_t)b * K + k) * 3 + 1]; v.z = xyz[((size_t)b * K + k) * 3 + 2]; }
-        v.w = bias ? bias[(size_t)b * K + k] * LOG2E : 0.f;
-    }
+    float4 v = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (k < K && xyz) { v.x = xyz[((size_t)b * K + k) * 3]; v.y = xyz[((size_t)b * K + k) * 3 + 1]; v.z = xyz[((size_t)b * K + k) * 3 + 2]; }
     out[(size_t)b * Kpad + k] = v;
+    bias2[(size_t)b * Kpad + k] = (k < K && bias) ? bias[(size_t)b * K + k] * LOG2E : 0.f;
 }
 
 struct SoftPlan {
     int RB, U, S, Jpad, Kpad;
-    size_t off_ns, off_nr, off_a, off_b, off_baug, off_aaug, off_xyzc, off_part, total;
+    size_t off_ns, off_nr, off_a, off_b, off_xyzc, off_bias, off_part, total;
 };
 
 SoftPlan make_soft_plan(int B, int J, int K) {
@@ -474,16 +541,15 @@ SoftPlan make_soft_plan(int B, int J, int K) {
     p.off_nr = take((size_t)B * K * 4);
     p.off_a = take((size_t)B * J * SF_CH * 2);
     p.off_b = take((size_t)B * K * SF_CH * 2);
-    p.off_baug = take((size_t)B * p.Kpad * SF_AUG * 2);
-    p.off_aaug = take((size_t)128 * SF_AUG * 2);
     p.off_xyzc = take((size_t)B * p.Kpad * 16);
-    p.off_part = take((size_t)B * p.Jpad * S * SF_HALVES * 8 * 4);
+    p.off_bias = take((size_t)B * p.Kpad * 4);
+    p.off_part = take((size_t)B * p.Jpad * S * 8 * 4);
     p.total = off + 1024;
     return p;
 }
 
 constexpr size_t soft_smem_bytes() {
-    return 1024 + (size_t)(SF_RBS + SF_BSTAGES) * SF_CHUNKS * SF_TILE + (size_t)(1 + SF_BSTAGES) * SF_AUGT + (size_t)SF_XSTAGES * SF_XT + 512;
+    return 1024 + (size_t)(SF_RBS + SF_BSTAGES) * SF_CHUNKS * SF_TILE + (size_t)SF_XSTAGES * SF_XT + 512;
 }
 
 }  // namespace
@@ -508,43 +574,42 @@ int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaSt
     if (ws == nullptr || (size_t)(base - (char *)ws) + pl.total - 1024 > ws_bytes) return DSIR_ERR_WORKSPACE;
     float *ns = (float *)(base + pl.off_ns), *nr = (float *)(base + pl.off_nr);
     __nv_bfloat16 *a = (__nv_bfloat16 *)(base + pl.off_a), *bexp = (__nv_bfloat16 *)(base + pl.off_b);
-    __nv_bfloat16 *baug = (__nv_bfloat16 *)(base + pl.off_baug), *aaug = (__nv_bfloat16 *)(base + pl.off_aaug);
     float4 *xyzc = (float4 *)(base + pl.off_xyzc);
+    float *bias2 = (float *)(base + pl.off_bias);
     float *part = (float *)(base + pl.off_part);
     int rc;
     if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, ns, st))) return rc;
     if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, nr, st))) return rc;
-    soft_prep_kernel<<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, 0, nullptr, a, nullptr, aaug);
+    soft_prep_kernel<<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, 0, nullptr, a);
     DSIR_LAUNCH_CHECK();
-    soft_prep_kernel<<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, 1, nr, bexp, baug, nullptr);
+    soft_prep_kernel<<<dim3(cdiv(P.K, 32), P.B), 256, 0, st>>>(P.fr, P.C, P.K, 1, nr, bexp);
     DSIR_LAUNCH_CHECK();
-    soft_xyzc_kernel<<<dim3(cdiv(pl.Kpad, 256), P.B), 256, 0, st>>>(P.y_soft ? P.xyz_ref : nullptr, P.col_bias, P.K, pl.Kpad, xyzc);
+    soft_xyzc_kernel<<<dim3(cdiv(pl.Kpad, 256), P.B), 256, 0, st>>>(P.y_soft ? P.xyz_ref : nullptr, P.col_bias, P.K, pl.Kpad, xyzc, bias2);
     DSIR_LAUNCH_CHECK();
-    CUtensorMap mapA, mapB, mapAaug, mapBaug;
+    CUtensorMap mapA, mapB;
     if (!make_bf16_tmap(&mapA, a, P.B, P.J, SF_CH, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_bf16_tmap(&mapB, bexp, P.B, P.K, SF_CH, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_bf16_tmap(&mapAaug, aaug, 1, 128, SF_AUG, SF_AUG, CU_TENSOR_MAP_SWIZZLE_32B) ||
-        !make_bf16_tmap(&mapBaug, baug, P.B, pl.Kpad, SF_AUG, SF_AUG, CU_TENSOR_MAP_SWIZZLE_32B))
+        !make_bf16_tmap(&mapB, bexp, P.B, P.K, SF_CH, 64, CU_TENSOR_MAP_SWIZZLE_128B))
         return DSIR_ERR_UNSUPPORTED;
     SoftParams T{};
     T.B = P.B; T.J = P.J; T.K = P.K; T.C = P.C; T.RB = pl.RB; T.U = pl.U; T.S = pl.S; T.Jpad = pl.Jpad; T.Kpad = pl.Kpad;
-    T.ns = ns; T.beta = P.beta; T.alpha = P.alpha; T.xyzc = xyzc; T.part = part;
+    T.ns = ns; T.beta = P.beta; T.alpha = P.alpha; T.xyz1 = xyzc; T.bias2 = bias2; T.part = part;
     const int items = P.B * pl.RB * pl.S;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = items < sms ? items : sms;
     const size_t smem = soft_smem_bytes();
-    if (P.y_soft) {
-        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_soft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        match_tc_soft_kernel<true><<<grid, SF_THREADS, smem, st>>>(mapA, mapB, mapAaug, mapBaug, T);
-    } else {
-        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_soft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        match_tc_soft_kernel<false><<<grid, SF_THREADS, smem, st>>>(mapA, mapB, mapAaug, mapBaug, T);
-    }
+#define DSIR_SOFT_LAUNCH(X, BI)                                                                                              \
+    do {                                                                                                                     \
+        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_soft_kernel<X, BI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        match_tc_soft_kernel<X, BI><<<grid, SF_THREADS, smem, st>>>(mapA, mapB, T);                                          \
+    } while (0)
+    if (P.y_soft) { if (P.col_bias) DSIR_SOFT_LAUNCH(true, true); else DSIR_SOFT_LAUNCH(true, false); }
+    else          { if (P.col_bias) DSIR_SOFT_LAUNCH(false, true); else DSIR_SOFT_LAUNCH(false, false); }
+#undef DSIR_SOFT_LAUNCH
     DSIR_LAUNCH_CHECK();
     const long long rows = (long long)P.B * P.J;
-    soft_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(part, P.B, P.J, pl.Jpad, pl.S * SF_HALVES, P.lse, P.y_soft);
+    soft_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(part, P.B, P.J, pl.Jpad, pl.S, P.lse, P.y_soft);
     DSIR_LAUNCH_CHECK();
     return DSIR_OK;
 }
