@@ -6,25 +6,24 @@
 // registers.
 //
 // Soft weights must agree with the fp32 reference to 1e-4 relative, i.e. the distance to ~1e-5 absolute at beta = 10:
-// single-pass fp16/bf16/tf32 operands (2^-9 .. 2^-11 relative) are three orders of magnitude short.  The operands are
-// therefore split three ways into bf16,  v = hi + lo + lolo  (24 significant bits), and the six products that matter
-//     hi*hi, hi*lo, lo*hi, lo*lo, hi*lolo, lolo*hi            (everything else is below 2^-24 |s||r|)
-// are formed by SIX groups of MMAs over sub-blocks of one 128-channel bf16 row per point
-//     [ hi (32) | lo (32) | lolo (32) | norm (16) | pad (16) ]        (reference features scaled by -2, exact)
-// selected through the K-offset of the shared-memory descriptors, so that the operand tiles are only 3x (not 6x) the
-// one-pass size and a reference tile (32 KB) is shared by FOUR 128-row blocks: the kernel is otherwise bound by the
-// L2 -> shared-memory operand traffic.  The norm block folds the three-term split of |r_k|^2 into the contraction
-// (source side 1,1,1,0..).  13 tcgen05.mma (M=128, N=128, K=16, kind::f16 with bf16 inputs) per 128 x 128 tile.
+// single-pass fp16/bf16/tf32 operands (2^-9 .. 2^-11 relative) are three orders of magnitude short.  Every operand is
+// therefore split in two fp16 halves,  v = hi + lo  (22 significant bits; values are first scaled by a per-batch power
+// of two that brings the largest norm below 1, exactly like the argmin path, so that nothing overflows and lo keeps its
+// bits), and the three products that matter - hi*hi, hi*lo, lo*hi; lo*lo is below 2^-22 |s||r| - are formed by THREE
+// groups of MMAs over the two halves of ONE 64-channel fp16 row per point  [ hi (32) | lo (32) ]  (reference features
+// scaled by -2, exact), selected through the K offset of the shared-memory descriptors.  A 16-channel tile folds the
+// three-term split of |r_k|^2 into the contraction (source side 1,1,1,0..).  7 tcgen05.mma (M=128, N=128, K=16,
+// kind::f16) per 128 x 128 tile, fp32 accumulation in TMEM.
 //
-//   warp 16      TMA producer: the source tiles of an item once (4 row blocks x 2 chunks x 16 KB), a 2-stage ring of
-//                reference tiles (2 x 16 KB), a 4-stage ring of (x, y, z, column bias) float4 per reference point
+//   warp 16      TMA producer: the source tiles of an item once (4 row blocks x 16 KB), a 4-stage ring of reference
+//                tiles (16 KB + 4 KB norm tile), a 4-stage ring of (x, y, z, 1) float4 + bias per reference point
 //   warps 17-18  MMA issuers (row blocks w, w + 2): four single-stage 128-column accumulators fill the 512 TMEM columns
-//   warps 0-15   epilogue: warp = (row block, TMEM lane quadrant), thread = one source row.  Per 32 columns:
-//                t_e = -beta' (x_e + |s|^2 - alpha) (+ bias), chunk maximum, ONE rescale of the running state, then
-//                p_e = 2^(t_e - m) (MUFU.EX2) accumulated into the sum and the three weighted coordinates.
+//   warps 0-15   epilogue: warp = (row block, TMEM lane quadrant), thread = one source row.  Per 16 columns:
+//                t_e = -beta' (x_e + |s|^2 - alpha) (+ bias), step maximum, ONE rescale of the running state, then
+//                p_e = 2^(t_e - m) (MUFU.EX2) accumulated into the sum and the three weighted coordinates (FFMA2).
 // Partial states of the K-splits are merged by a small finalize kernel.
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -34,18 +33,20 @@ namespace dsir {
 
 namespace {
 
-constexpr int SF_RBS = 4, SF_ACC = 1, SF_HALVES = 1, SF_BSTAGES = 2, SF_XSTAGES = 4;
+constexpr int SF_RBS = 4, SF_ACC = 1, SF_HALVES = 1, SF_BSTAGES = 4, SF_XSTAGES = 4;
 constexpr int SF_MMA_WARPS = 2;
 constexpr int SF_BM = 128 * SF_RBS, SF_BN = 128;
 constexpr int SF_EPI_WARPS = 4 * SF_RBS * SF_HALVES;        // 16
 constexpr int SF_WARP_TMA = SF_EPI_WARPS, SF_WARP_MMA0 = SF_EPI_WARPS + 1;
 constexpr int SF_THREADS = (SF_EPI_WARPS + 1 + SF_MMA_WARPS) * 32;   // 608
 constexpr int SF_CMAX = 32;                                  // channels supported by this path
-constexpr int SF_CH = 128;                                   // bf16 channels per point: hi | lo | lolo | norm(16) | pad(16)
+constexpr int SF_CH = 64;                                    // fp16 channels per point: hi (32) | lo (32)
+constexpr int SF_AUG = 16;                                   // folded-norm channels (one K=16 MMA)
 constexpr int SF_CHUNKS = SF_CH / 64;                        // 64-channel (128-byte) TMA boxes per row
 constexpr int SF_MAX_SPLIT = 8;
 constexpr uint32_t SF_TILE = 128 * 64 * 2;                   // 16 KB
-constexpr uint32_t SF_XT = 128 * 16 + 128 * 4;               //  (x, y, z, 1) float4 + bias float per reference point of a unit
+constexpr uint32_t SF_AUGT = 128 * SF_AUG * 2;               //  4 KB
+constexpr uint32_t SF_XT = 128 * 16;                         //  per unit: (x, y) float2[128] | z[128] | bias[128]
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 static_assert(SF_RBS * SF_ACC * 128 == 512 && SF_HALVES == 1 && SF_RBS % SF_MMA_WARPS == 0, "TMEM / warp budget");
 
@@ -63,15 +64,15 @@ EncodeTiledFn soft_encode_fn() {
     }
     return fn;
 }
-// [B][N][W] bf16, box = bw channels x 128 rows; rows/batches beyond the extent read as zero
-bool make_bf16_tmap(CUtensorMap *m, const __nv_bfloat16 *base, int B, int N, int W, int bw, CUtensorMapSwizzle swz) {
+// [B][N][W] fp16, box = bw channels x 128 rows; rows/batches beyond the extent read as zero
+bool make_f16_tmap(CUtensorMap *m, const __half *base, int B, int N, int W, int bw, CUtensorMapSwizzle swz) {
     EncodeTiledFn enc = soft_encode_fn();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)N, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)W * 2, (cuuint64_t)N * W * 2};
     cuuint32_t box[3] = {(cuuint32_t)bw, 128, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -99,7 +100,7 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
         "elect.sync _|pe, 0xffffffff;\n\t"
         "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p, pe;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -107,27 +108,6 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t desc_a, uint6
         "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait32(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -149,6 +129,11 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ float lds32(uint32_t addr) {
@@ -182,8 +167,8 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
     d |= (uint64_t)layout << 61;        // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
     return d;
 }
-// D = f32, A = B = bf16, both K-major, N = 128, M = 128
-constexpr uint32_t SF_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SF_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// D = f32, A = B = f16, both K-major, N = 128, M = 128
+constexpr uint32_t SF_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(SF_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 struct Pipe {
     int stage;
@@ -198,8 +183,8 @@ struct SoftParams {
     int RB, U, S, Jpad, Kpad;
     const float *ns;         // [B,J] exact squared norms
     const float *beta, *alpha;   // [B]
-    const float4 *xyz1;      // [B][Kpad] (x, y, z, 1)
-    const float *bias2;      // [B][Kpad] column bias * log2e
+    const float *scale;      // [B] sigma (power of two): the accumulator holds sigma^2 (|r|^2 - 2<s,r>)
+    const float *xtile;      // [B][U][512]: per unit (x, y)[128] | z[128] | bias * log2e [128]
     float *part;             // [B][Jpad][S][8]: m, l, sx, sy, sz (log2 domain)
 };
 
@@ -207,13 +192,13 @@ struct SoftParams {
 // (16 rather than 32 columns per step: with 32 the live registers - the step's values, the prefetched next step, the
 // running state - leave no room to keep several (x, y, z) loads in flight and their latency is exposed one by one.)
 constexpr int SW = 16;
-// Running state of a row: m (log2 domain) and two packed pairs, s01 = (sum p x, sum p y), s23 = (sum p z, sum p) with
-// XYZ, s23 = (sum of the even columns' p, sum of the odd columns' p) without.  Everything per column is one FADD2 (half),
-// one MUFU.EX2, one LDS.128 of (x, y, z, 1) and two FFMA2 with p as the scalar operand.
+// Running state of a row: m (log2 domain), s01 = (sum p x, sum p y), sz = sum p z, l2 = (sum of the even columns' p,
+// sum of the odd columns' p).  Per column: half a FADD2, one MUFU.EX2, half a FADD2, and with XYZ an LDS.64 + LDS.32,
+// one FFMA2 with p as the scalar operand and one FFMA.
 template <bool XYZ, bool BIAS>
-__device__ __forceinline__ void soft_step(const uint32_t (&v)[SW], uint32_t xs /* shared address of the step's float4[16] */,
-                                          uint32_t bs /* shared address of the step's bias[16] */, int lane, int valid, float nb2,
-                                          float cj, float &m, f32x2 &s01, f32x2 &s23) {
+__device__ __forceinline__ void soft_step(const uint32_t (&v)[SW], uint32_t xs /* shared address of the step's (x, y)[16] */,
+                                          uint32_t zs /* ... z[16] */, uint32_t bs /* ... bias[16] */, int lane, int valid,
+                                          float nb2, float cj, float &m, f32x2 &s01, float &sz, f32x2 &l2) {
     f32x2 t2[SW / 2];
     const f32x2 nb22 = pack2(nb2, nb2), cj2 = pack2(cj, cj);
 #pragma unroll
@@ -239,27 +224,30 @@ __device__ __forceinline__ void soft_step(const uint32_t (&v)[SW], uint32_t xs /
     if (mn > -INFINITY) {                        // (a step of padding only leaves the state untouched)
         const float sc = ex2(m - mn);
         const f32x2 sc2 = pack2(sc, sc);
-        if (XYZ) s01 = mul2(s01, sc2);
-        s23 = mul2(s23, sc2);
+        if (XYZ) { s01 = mul2(s01, sc2); sz *= sc; }
+        l2 = mul2(l2, sc2);
         m = mn;
         const f32x2 nm2 = pack2(-mn, -mn);
-        float4 c4[SW];
+        // (x, y) and z of the 16 columns: broadcast loads, all in flight together.  Every broadcast load returns
+        // 32 lanes x its width through the 128 B/clk shared-memory return path, which is what bounds this loop: 12 bytes
+        // per column (LDS.64 + LDS.32) instead of a 16-byte LDS.128.
+        float2 xy[SW];
+        float zz[SW];
         if (XYZ) {
 #pragma unroll
-            for (int e = 0; e < SW; ++e) c4[e] = lds128(xs + e * 16);   // broadcast loads of (x, y, z, 1), all in flight together
+            for (int e = 0; e < SW; ++e) { xy[e] = lds64(xs + e * 8); zz[e] = lds32(zs + e * 4); }
         }
 #pragma unroll
         for (int e = 0; e < SW; e += 2) {
             float a0, a1;
             unpack2(add2(pack2(t[e], t[e + 1]), nm2), a0, a1);
             const float p0 = ex2(a0), p1 = ex2(a1);
+            l2 = add2(l2, pack2(p0, p1));
             if (XYZ) {
-                s01 = fma2(pack2(c4[e].x, c4[e].y), pack2(p0, p0), s01);
-                s23 = fma2(pack2(c4[e].z, c4[e].w), pack2(p0, p0), s23);
-                s01 = fma2(pack2(c4[e + 1].x, c4[e + 1].y), pack2(p1, p1), s01);
-                s23 = fma2(pack2(c4[e + 1].z, c4[e + 1].w), pack2(p1, p1), s23);
-            } else {
-                s23 = add2(s23, pack2(p0, p1));
+                s01 = fma2(pack2(xy[e].x, xy[e].y), pack2(p0, p0), s01);
+                sz = __fmaf_rn(p0, zz[e], sz);
+                s01 = fma2(pack2(xy[e + 1].x, xy[e + 1].y), pack2(p1, p1), s01);
+                sz = __fmaf_rn(p1, zz[e + 1], sz);
             }
         }
     }
@@ -267,12 +255,16 @@ __device__ __forceinline__ void soft_step(const uint32_t (&v)[SW], uint32_t xs /
 
 template <bool XYZ, bool BIAS>
 __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                      const __grid_constant__ CUtensorMap mapB, SoftParams P) {
+                                                                      const __grid_constant__ CUtensorMap mapB,
+                                                                      const __grid_constant__ CUtensorMap mapAaug,
+                                                                      const __grid_constant__ CUtensorMap mapBaug, SoftParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;                                             // [RBS][CHUNKS][16 KB]
     uint8_t *sB = sA + SF_RBS * SF_CHUNKS * SF_TILE;                // [BSTAGES][CHUNKS][16 KB]
-    uint8_t *sX = sB + SF_BSTAGES * SF_CHUNKS * SF_TILE;            // [XSTAGES][2 KB]
+    uint8_t *sAaug = sB + SF_BSTAGES * SF_CHUNKS * SF_TILE;         // [4 KB]
+    uint8_t *sBaug = sAaug + SF_AUGT;                               // [BSTAGES][4 KB]
+    uint8_t *sX = sBaug + SF_BSTAGES * SF_AUGT;                     // [XSTAGES][2.5 KB]
     uint64_t *bars = (uint64_t *)(sX + SF_XSTAGES * SF_XT);
     uint64_t *full_b = bars, *empty_b = full_b + SF_BSTAGES;
     uint64_t *full_x = empty_b + SF_BSTAGES, *empty_x = full_x + SF_XSTAGES;
@@ -285,7 +277,7 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
     const int total_items = P.B * P.RB * P.S;
 
     if (warp == SF_WARP_TMA && lane == 0) {
-        prefetch_tmap(&mapA); prefetch_tmap(&mapB);
+        prefetch_tmap(&mapA); prefetch_tmap(&mapB); prefetch_tmap(&mapAaug); prefetch_tmap(&mapBaug);
         for (int s = 0; s < SF_BSTAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], SF_MMA_WARPS); }
         for (int s = 0; s < SF_XSTAGES; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], SF_EPI_WARPS); }
         for (int a = 0; a < SF_RBS; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
@@ -304,11 +296,14 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
         if (lane == 0) {
             Pipe pb{0, 0}, px{0, 0};
             uint32_t iphase = 0;
+            bool first = true;
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
                 const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
                 const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
                 mbar_wait(empty_a, iphase ^ 1u);
-                mbar_expect_tx(full_a, SF_RBS * SF_CHUNKS * SF_TILE);
+                mbar_expect_tx(full_a, SF_RBS * SF_CHUNKS * SF_TILE + (first ? SF_AUGT : 0u));
+                if (first) tma_load_3d(sAaug, &mapAaug, 0, 0, 0, full_a);   // constant 1,1,1,0.. tile, loaded once
+                first = false;
 #pragma unroll
                 for (int r = 0; r < SF_RBS; ++r)
 #pragma unroll
@@ -317,14 +312,14 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
                 for (int u = u0; u < u1; ++u) {
                     while (!mbar_try_wait(&empty_x[px.stage], px.phase ^ 1u)) __nanosleep(32);
                     mbar_expect_tx(&full_x[px.stage], SF_XT);
-                    bulk_g2s(sX + px.stage * SF_XT, P.xyz1 + (size_t)b * P.Kpad + (size_t)u * SF_BN, SF_BN * 16, &full_x[px.stage]);
-                    bulk_g2s(sX + px.stage * SF_XT + SF_BN * 16, P.bias2 + (size_t)b * P.Kpad + (size_t)u * SF_BN, SF_BN * 4, &full_x[px.stage]);
+                    bulk_g2s(sX + px.stage * SF_XT, P.xtile + ((size_t)b * P.U + (size_t)u) * 512, SF_XT, &full_x[px.stage]);
                     px.advance(SF_XSTAGES);
                     while (!mbar_try_wait(&empty_b[pb.stage], pb.phase ^ 1u)) __nanosleep(32);
-                    mbar_expect_tx(&full_b[pb.stage], SF_CHUNKS * SF_TILE);
+                    mbar_expect_tx(&full_b[pb.stage], SF_CHUNKS * SF_TILE + SF_AUGT);
 #pragma unroll
                     for (int c = 0; c < SF_CHUNKS; ++c)
                         tma_load_3d(sB + (pb.stage * SF_CHUNKS + c) * SF_TILE, &mapB, c * 64, u * SF_BN, b, &full_b[pb.stage]);
+                    tma_load_3d(sBaug + pb.stage * SF_AUGT, &mapBaug, 0, u * SF_BN, b, &full_b[pb.stage]);
                     pb.advance(SF_BSTAGES);
                 }
                 iphase ^= 1u;
@@ -337,8 +332,10 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
         uint32_t iphase = 0, aphase = 0;
         const uint64_t descA0 = make_kmajor_desc(smem_u32(sA), 1024, 2);
         const uint64_t descB0 = make_kmajor_desc(smem_u32(sB), 1024, 2);
-        // sub-blocks of the 128-channel row, as descriptor offsets (16-byte units): chunk 0 = hi | lo, chunk 1 = lolo | norm
-        constexpr uint32_t HI = 0, LO = 4, LL = SF_TILE >> 4, NRM = (SF_TILE >> 4) + 4;
+        const uint64_t descAaug = make_kmajor_desc(smem_u32(sAaug), 256, 6);
+        const uint64_t descBaug0 = make_kmajor_desc(smem_u32(sBaug), 256, 6);
+        // halves of the 64-channel row, as descriptor offsets (16-byte units): hi at +0, lo at +64 bytes
+        constexpr uint32_t HI = 0, LO = 4;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int sp = it % P.S;
             const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
@@ -346,20 +343,21 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
             for (int u = u0; u < u1; ++u) {
                 mbar_wait(&full_b[pb.stage], pb.phase);
                 const uint64_t descB = descB0 + (uint64_t)((uint32_t)pb.stage * ((SF_CHUNKS * SF_TILE) >> 4));
+                const uint64_t descBaug = descBaug0 + (uint64_t)((uint32_t)pb.stage * (SF_AUGT >> 4));
 #pragma unroll
                 for (int r = w; r < SF_RBS; r += SF_MMA_WARPS) {
                     mbar_wait(&tmem_empty[r], aphase ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(r * 128);
                     const uint64_t descA = descA0 + (uint64_t)(r * ((SF_CHUNKS * SF_TILE) >> 4));
-                    // six product groups, largest first: hi*hi, hi*lo, lo*hi, lo*lo, hi*lolo, lolo*hi (2 k-steps of 16 each)
-                    const uint32_t ao[6] = {HI, HI, LO, LO, HI, LL}, bo[6] = {HI, LO, HI, LO, LL, HI};
+                    // three product groups, largest first: hi*hi, hi*lo, lo*hi (2 k-steps of 16 channels each)
+                    const uint32_t ao[3] = {HI, HI, LO}, bo[3] = {HI, LO, HI};
 #pragma unroll
-                    for (int g = 0; g < 6; ++g)
+                    for (int g = 0; g < 3; ++g)
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks)
-                            mma_bf16(d_tmem, descA + (uint64_t)(ao[g] + ks * 2), descB + (uint64_t)(bo[g] + ks * 2), SF_IDESC, (g | ks) ? 1u : 0u);
-                    mma_bf16(d_tmem, descA + (uint64_t)NRM, descB + (uint64_t)NRM, SF_IDESC, 1u);   // + |r_k|^2
+                            mma_f16(d_tmem, descA + (uint64_t)(ao[g] + ks * 2), descB + (uint64_t)(bo[g] + ks * 2), SF_IDESC, (g | ks) ? 1u : 0u);
+                    mma_f16(d_tmem, descAaug, descBaug, SF_IDESC, 1u);   // + sigma^2 |r_k|^2
                     tc_commit(&tmem_full[r]);
                 }
                 tc_commit(&empty_b[pb.stage]);
@@ -380,16 +378,19 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
             const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
             const int j = rb * SF_BM + r * 128 + trow;
             const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
-            const float nb2 = -P.beta[b] * LOG2E;                  // t = nb2 * (x + ns - alpha)  (log2 domain)
-            const float cj = nb2 * (nsj - P.alpha[b]);
+            const float nb2u = -P.beta[b] * LOG2E;                 // t = nb2u * (x / sigma^2 + ns - alpha)  (log2 domain)
+            const float cj = nb2u * (nsj - P.alpha[b]);
+            const float sg = P.scale[b];
+            const float nb2 = nb2u / (sg * sg);                    // sigma is a power of two: exact
             float m = -INFINITY;
-            f32x2 s01 = pack2(0.f, 0.f), s23 = pack2(0.f, 0.f);
+            f32x2 s01 = pack2(0.f, 0.f), l2 = pack2(0.f, 0.f);
+            float sz = 0.f;
             for (int u = u0; u < u1; ++u) {
                 const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * 128);
                 mbar_wait(&tmem_full[r], aphase);
                 tc_fence_after();
                 mbar_wait(&full_x[px.stage], px.phase);
-                const uint32_t xs = smem_u32(sX + px.stage * SF_XT), bs = xs + SF_BN * 16;
+                const uint32_t xs = smem_u32(sX + px.stage * SF_XT), zs = xs + SF_BN * 8, bs = xs + SF_BN * 12;
                 const int valid0 = P.K - u * SF_BN;                // columns < valid are real
                 uint32_t va[SW], vb[SW];
                 tmem_ld16(tbase, va);
@@ -398,7 +399,7 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
                 for (int g = 0; g < NST; g += 2) {                 // ping-pong: the next 16 columns fly during this step's math
                     tmem_wait16(va);
                     tmem_ld16(tbase + (g + 1) * SW, vb);
-                    soft_step<XYZ, BIAS>(va, xs + g * SW * 16, bs + g * SW * 4, lane, valid0 - g * SW, nb2, cj, m, s01, s23);
+                    soft_step<XYZ, BIAS>(va, xs + g * SW * 8, zs + g * SW * 4, bs + g * SW * 4, lane, valid0 - g * SW, nb2, cj, m, s01, sz, l2);
                     tmem_wait16(vb);
                     if (g + 2 < NST) {
                         tmem_ld16(tbase + (g + 2) * SW, va);
@@ -407,17 +408,17 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty[r]);
                     }
-                    soft_step<XYZ, BIAS>(vb, xs + (g + 1) * SW * 16, bs + (g + 1) * SW * 4, lane, valid0 - (g + 1) * SW, nb2, cj, m, s01, s23);
+                    soft_step<XYZ, BIAS>(vb, xs + (g + 1) * SW * 8, zs + (g + 1) * SW * 4, bs + (g + 1) * SW * 4, lane, valid0 - (g + 1) * SW, nb2, cj, m, s01, sz, l2);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_x[px.stage]);
                 px.advance(SF_XSTAGES);
                 aphase ^= 1u;
             }
-            float sx, sy, sz, l;
+            float sx, sy, l, l1;
             unpack2(s01, sx, sy);
-            unpack2(s23, sz, l);
-            if (!XYZ) { l += sz; sz = 0.f; }      // (even, odd) column sums
+            unpack2(l2, l, l1);
+            l += l1;                               // (even, odd) column sums
             float *o = P.part + (((size_t)b * P.Jpad + (size_t)j) * P.S + sp) * 8;
             *reinterpret_cast<float4 *>(o) = make_float4(m, l, sx, sy);
             *reinterpret_cast<float4 *>(o + 4) = make_float4(sz, 0.f, 0.f, 0.f);
@@ -457,14 +458,25 @@ __global__ void soft_finalize_kernel(const float *__restrict__ part, int B, int 
     }
 }
 
-// [B,C,N] fp32 (any strides) -> bf16 [B][N][128] = hi(32) | lo(32) | lolo(32) | norm(16) | 0(16); the reference side
-// (is_ref) carries -2 f (exact) and the three-term split of |r|^2 in the norm block, the source side 1,1,1,0...
-// One block = 32 points; thread = (point, group of 4 channels).
-__global__ __launch_bounds__(256) void soft_prep_kernel(dsir_feat f, int C, int N, int is_ref, const float *__restrict__ nrm,
-                                                        __nv_bfloat16 *__restrict__ out) {
+// sigma_b = 2^-e with 2^e > sqrt(max squared norm of the batch) (1 when the maximum is 0 or not finite)
+__device__ __forceinline__ float soft_sigma(float amax) {
+    if (!(amax > 0.f) || !(amax < INFINITY)) return 1.f;
+    int e = ilogbf(sqrtf(amax)) + 1;
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    return exp2f((float)-e);
+}
+
+// [B,C,N] fp32 (any strides) -> fp16 [B][N][64] = hi(32) | lo(32) of  mul * sigma * f  (mul = -2 on the reference side,
+// exact), and for the reference side the folded-norm tile [B][Npad][16] = three-term fp16 split of sigma^2 |r|^2.
+// One block = 32 points; thread = (point, group of 4 channels).  Block (0,0) also writes the constant source-side norm
+// tile; the first block of every batch writes sigma.
+__global__ __launch_bounds__(256) void soft_prep_kernel(dsir_feat f, int C, int N, int Npad, int is_ref, const float *__restrict__ amax,
+                                                        const float *__restrict__ nrm, __half *__restrict__ out, __half *__restrict__ aug,
+                                                        __half *__restrict__ aug_const, float *__restrict__ scale_out) {
     __shared__ float tile[SF_CMAX][33];
     const int b = blockIdx.y, n0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float sigma = soft_sigma(amax[b]);
     const float *src = f.ptr + (size_t)b * f.batch_stride;
     for (int c = ty; c < SF_CMAX; c += 8) {
         const int n = n0 + tx;
@@ -473,51 +485,54 @@ __global__ __launch_bounds__(256) void soft_prep_kernel(dsir_feat f, int C, int 
     __syncthreads();
     const int i = threadIdx.x >> 3, g = threadIdx.x & 7;
     const int n = n0 + i;
-    if (n >= N) return;
-    __align__(8) __nv_bfloat16 hi[4], lo[4], ll[4];
+    if (n < N) {
+        const float mul = (is_ref ? -2.f : 1.f) * sigma;     // power of two: the scaling is exact
+        __align__(8) __half hi[4], lo[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float v = tile[4 * g + k][i] * (is_ref ? -2.f : 1.f);
-        hi[k] = __float2bfloat16_rn(v);
-        const float r1 = v - __bfloat162float(hi[k]);
-        lo[k] = __float2bfloat16_rn(r1);
-        ll[k] = __float2bfloat16_rn(r1 - __bfloat162float(lo[k]));
-    }
-    __nv_bfloat16 *o = out + ((size_t)b * N + n) * SF_CH;
-    *reinterpret_cast<uint2 *>(o + 4 * g) = *reinterpret_cast<const uint2 *>(hi);
-    *reinterpret_cast<uint2 *>(o + 32 + 4 * g) = *reinterpret_cast<const uint2 *>(lo);
-    *reinterpret_cast<uint2 *>(o + 64 + 4 * g) = *reinterpret_cast<const uint2 *>(ll);
-    __align__(8) __nv_bfloat16 t4[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) t4[k] = __float2bfloat16_rn(0.f);
-    if (g == 0) {
-        if (is_ref) {
-            const float x = nrm[(size_t)b * N + n];
-            t4[0] = __float2bfloat16_rn(x);
-            const float r1 = x - __bfloat162float(t4[0]);
-            t4[1] = __float2bfloat16_rn(r1);
-            t4[2] = __float2bfloat16_rn(r1 - __bfloat162float(t4[1]));
-        } else {
-            t4[0] = t4[1] = t4[2] = __float2bfloat16_rn(1.f);
+        for (int k = 0; k < 4; ++k) {
+            const float v = tile[4 * g + k][i] * mul;
+            hi[k] = __float2half_rn(v);
+            lo[k] = __float2half_rn(v - __half2float(hi[k]));
         }
+        __half *o = out + ((size_t)b * N + n) * SF_CH;
+        *reinterpret_cast<uint2 *>(o + 4 * g) = *reinterpret_cast<const uint2 *>(hi);
+        *reinterpret_cast<uint2 *>(o + 32 + 4 * g) = *reinterpret_cast<const uint2 *>(lo);
     }
-    *reinterpret_cast<uint2 *>(o + 96 + 4 * g) = *reinterpret_cast<const uint2 *>(t4);   // norm block (g < 4) and padding (g >= 4)
+    if (aug && n < Npad && g < 2) {
+        __align__(16) __half h[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) h[k] = __float2half_rn(0.f);
+        if (g == 0 && n < N) {
+            const float x = nrm[(size_t)b * N + n] * sigma * sigma;
+            h[0] = __float2half_rn(x);
+            const float r1 = x - __half2float(h[0]);
+            h[1] = __float2half_rn(r1);
+            h[2] = __float2half_rn(r1 - __half2float(h[1]));
+        }
+        *reinterpret_cast<uint4 *>(aug + ((size_t)b * Npad + n) * SF_AUG + g * 8) = *reinterpret_cast<const uint4 *>(h);
+    }
+    if (aug_const && blockIdx.x == 0 && b == 0)
+        for (int t = threadIdx.x; t < 128 * SF_AUG; t += blockDim.x) aug_const[t] = __float2half_rn((t % SF_AUG) < 3 ? 1.f : 0.f);
+    if (scale_out && blockIdx.x == 0 && threadIdx.x == 0) scale_out[b] = sigma;
 }
 
-// (x, y, z, 1) and bias * log2e per reference point (zeros beyond K: those columns are masked by their index)
-__global__ void soft_xyzc_kernel(const float *__restrict__ xyz, const float *__restrict__ bias, int K, int Kpad, float4 *__restrict__ out,
-                                 float *__restrict__ bias2) {
+// per unit of 128 reference points: (x, y)[128] | z[128] | bias * log2e [128]  (zeros beyond K: masked by index)
+__global__ void soft_xtile_kernel(const float *__restrict__ xyz, const float *__restrict__ bias, int K, int Kpad, float *__restrict__ out) {
     const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Kpad) return;
-    float4 v = make_float4(0.f, 0.f, 0.f, 1.f);
-    if (k < K && xyz) { v.x = xyz[((size_t)b * K + k) * 3]; v.y = xyz[((size_t)b * K + k) * 3 + 1]; v.z = xyz[((size_t)b * K + k) * 3 + 2]; }
-    out[(size_t)b * Kpad + k] = v;
-    bias2[(size_t)b * Kpad + k] = (k < K && bias) ? bias[(size_t)b * K + k] * LOG2E : 0.f;
+    float x = 0.f, y = 0.f, z = 0.f, bb = 0.f;
+    if (k < K) {
+        if (xyz) { x = xyz[((size_t)b * K + k) * 3]; y = xyz[((size_t)b * K + k) * 3 + 1]; z = xyz[((size_t)b * K + k) * 3 + 2]; }
+        if (bias) bb = bias[(size_t)b * K + k] * LOG2E;
+    }
+    float *o = out + ((size_t)b * (Kpad / SF_BN) + k / SF_BN) * 512;
+    const int i = k % SF_BN;
+    o[2 * i] = x; o[2 * i + 1] = y; o[256 + i] = z; o[384 + i] = bb;
 }
 
 struct SoftPlan {
     int RB, U, S, Jpad, Kpad;
-    size_t off_ns, off_nr, off_a, off_b, off_xyzc, off_bias, off_part, total;
+    size_t off_ns, off_nr, off_a, off_b, off_baug, off_aaug, off_amax, off_scale, off_xyzc, off_bias, off_part, total;
 };
 
 SoftPlan make_soft_plan(int B, int J, int K) {
@@ -541,15 +556,19 @@ SoftPlan make_soft_plan(int B, int J, int K) {
     p.off_nr = take((size_t)B * K * 4);
     p.off_a = take((size_t)B * J * SF_CH * 2);
     p.off_b = take((size_t)B * K * SF_CH * 2);
+    p.off_baug = take((size_t)B * p.Kpad * SF_AUG * 2);
+    p.off_aaug = take((size_t)128 * SF_AUG * 2);
+    p.off_amax = take((size_t)B * 4);
+    p.off_scale = take((size_t)B * 4);
     p.off_xyzc = take((size_t)B * p.Kpad * 16);
-    p.off_bias = take((size_t)B * p.Kpad * 4);
+    p.off_bias = take(256);
     p.off_part = take((size_t)B * p.Jpad * S * 8 * 4);
     p.total = off + 1024;
     return p;
 }
 
 constexpr size_t soft_smem_bytes() {
-    return 1024 + (size_t)(SF_RBS + SF_BSTAGES) * SF_CHUNKS * SF_TILE + (size_t)SF_XSTAGES * SF_XT + 512;
+    return 1024 + (size_t)(SF_RBS + SF_BSTAGES) * SF_CHUNKS * SF_TILE + (size_t)(1 + SF_BSTAGES) * SF_AUGT + (size_t)SF_XSTAGES * SF_XT + 512;
 }
 
 }  // namespace
@@ -573,26 +592,31 @@ int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaSt
     char *base = (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     if (ws == nullptr || (size_t)(base - (char *)ws) + pl.total - 1024 > ws_bytes) return DSIR_ERR_WORKSPACE;
     float *ns = (float *)(base + pl.off_ns), *nr = (float *)(base + pl.off_nr);
-    __nv_bfloat16 *a = (__nv_bfloat16 *)(base + pl.off_a), *bexp = (__nv_bfloat16 *)(base + pl.off_b);
-    float4 *xyzc = (float4 *)(base + pl.off_xyzc);
-    float *bias2 = (float *)(base + pl.off_bias);
+    __half *a = (__half *)(base + pl.off_a), *bexp = (__half *)(base + pl.off_b);
+    __half *baug = (__half *)(base + pl.off_baug), *aaug = (__half *)(base + pl.off_aaug);
+    float *amax = (float *)(base + pl.off_amax), *scale = (float *)(base + pl.off_scale);
+    float *xtile = (float *)(base + pl.off_xyzc);
     float *part = (float *)(base + pl.off_part);
     int rc;
-    if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, ns, st))) return rc;
-    if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, nr, st))) return rc;
-    soft_prep_kernel<<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, 0, nullptr, a);
+    DSIR_CUDA_TRY(cudaMemsetAsync(amax, 0, (size_t)P.B * 4, st));
+    // exact squared norms (fma chains) + the per-batch maximum over both clouds for sigma
+    if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, ns, (int *)amax, nullptr, st))) return rc;
+    if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, nr, (int *)amax, nullptr, st))) return rc;
+    soft_prep_kernel<<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, 0, amax, nullptr, a, nullptr, aaug, scale);
     DSIR_LAUNCH_CHECK();
-    soft_prep_kernel<<<dim3(cdiv(P.K, 32), P.B), 256, 0, st>>>(P.fr, P.C, P.K, 1, nr, bexp);
+    soft_prep_kernel<<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, 1, amax, nr, bexp, baug, nullptr, nullptr);
     DSIR_LAUNCH_CHECK();
-    soft_xyzc_kernel<<<dim3(cdiv(pl.Kpad, 256), P.B), 256, 0, st>>>(P.y_soft ? P.xyz_ref : nullptr, P.col_bias, P.K, pl.Kpad, xyzc, bias2);
+    soft_xtile_kernel<<<dim3(cdiv(pl.Kpad, 256), P.B), 256, 0, st>>>(P.y_soft ? P.xyz_ref : nullptr, P.col_bias, P.K, pl.Kpad, xtile);
     DSIR_LAUNCH_CHECK();
-    CUtensorMap mapA, mapB;
-    if (!make_bf16_tmap(&mapA, a, P.B, P.J, SF_CH, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_bf16_tmap(&mapB, bexp, P.B, P.K, SF_CH, 64, CU_TENSOR_MAP_SWIZZLE_128B))
+    CUtensorMap mapA, mapB, mapAaug, mapBaug;
+    if (!make_f16_tmap(&mapA, a, P.B, P.J, SF_CH, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_f16_tmap(&mapB, bexp, P.B, P.K, SF_CH, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_f16_tmap(&mapAaug, aaug, 1, 128, SF_AUG, SF_AUG, CU_TENSOR_MAP_SWIZZLE_32B) ||
+        !make_f16_tmap(&mapBaug, baug, P.B, pl.Kpad, SF_AUG, SF_AUG, CU_TENSOR_MAP_SWIZZLE_32B))
         return DSIR_ERR_UNSUPPORTED;
     SoftParams T{};
     T.B = P.B; T.J = P.J; T.K = P.K; T.C = P.C; T.RB = pl.RB; T.U = pl.U; T.S = pl.S; T.Jpad = pl.Jpad; T.Kpad = pl.Kpad;
-    T.ns = ns; T.beta = P.beta; T.alpha = P.alpha; T.xyz1 = xyzc; T.bias2 = bias2; T.part = part;
+    T.ns = ns; T.beta = P.beta; T.alpha = P.alpha; T.scale = scale; T.xtile = xtile; T.part = part;
     const int items = P.B * pl.RB * pl.S;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -602,7 +626,7 @@ int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaSt
 #define DSIR_SOFT_LAUNCH(X, BI)                                                                                              \
     do {                                                                                                                     \
         DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_soft_kernel<X, BI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        match_tc_soft_kernel<X, BI><<<grid, SF_THREADS, smem, st>>>(mapA, mapB, T);                                          \
+        match_tc_soft_kernel<X, BI><<<grid, SF_THREADS, smem, st>>>(mapA, mapB, mapAaug, mapBaug, T);                                          \
     } while (0)
     if (P.y_soft) { if (P.col_bias) DSIR_SOFT_LAUNCH(true, true); else DSIR_SOFT_LAUNCH(true, false); }
     else          { if (P.col_bias) DSIR_SOFT_LAUNCH(false, true); else DSIR_SOFT_LAUNCH(false, false); }
