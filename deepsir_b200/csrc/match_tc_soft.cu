@@ -1,5 +1,5 @@
 // Fused feature-distance + affinity + row-wise ONLINE SOFTMAX + soft target on the 5th-generation tensor cores
-// (tcgen05 / TMEM / TMA), sm_100a.  Replaces, for C <= 32 channels (the 3DMatch-shaped configuration):
+// (tcgen05 / TMEM / TMA), sm_100a.  Replaces, for C <= 64 channels:
 //     match_features_V2 (network/matchnet.py:96-131) -> compute_affinity (:195-208) -> row normalisation (:259)
 //     -> weights @ xyz_ref / row mass (network/model.py:81-85)
 // without ever writing the [J,K] matrix: the score tile lives in TMEM, the running (max, sum, sum*xyz) of every row in
@@ -33,16 +33,25 @@ namespace dsir {
 
 namespace {
 
-constexpr int SF_RBS = 4, SF_ACC = 1, SF_HALVES = 1, SF_BSTAGES = 4, SF_XSTAGES = 4;
+constexpr int SF_RBS = 4, SF_ACC = 1, SF_HALVES = 1, SF_XSTAGES = 4;
 constexpr int SF_MMA_WARPS = 2;
 constexpr int SF_BM = 128 * SF_RBS, SF_BN = 128;
 constexpr int SF_EPI_WARPS = 4 * SF_RBS * SF_HALVES;        // 16
 constexpr int SF_WARP_TMA = SF_EPI_WARPS, SF_WARP_MMA0 = SF_EPI_WARPS + 1;
 constexpr int SF_THREADS = (SF_EPI_WARPS + 1 + SF_MMA_WARPS) * 32;   // 608
-constexpr int SF_CMAX = 32;                                  // channels supported by this path
-constexpr int SF_CH = 64;                                    // fp16 channels per point: hi (32) | lo (32)
+// Two operand widths: C <= 32 packs hi | lo into ONE 128-byte row (halves selected by a 64-byte descriptor offset),
+// 32 < C <= 64 uses two 128-byte chunks (hi chunk, lo chunk).  WIDE doubles the k-steps per product group (13 MMAs per
+// tile instead of 7) and the tile bytes; the epilogue, which bounds the kernel, is the same.
+template <bool WIDE>
+struct SoftCfg {
+    static constexpr int CMAX = WIDE ? 64 : 32;      // channels supported
+    static constexpr int CH = 2 * CMAX;              // fp16 channels per point: hi | lo
+    static constexpr int CHUNKS = CH / 64;           // 64-channel (128-byte) TMA boxes per row
+    static constexpr int KS = CMAX / 16;             // k-steps of 16 channels per product group
+    static constexpr int BSTAGES = WIDE ? 2 : 4;     // reference-tile ring depth
+    static constexpr uint32_t LO_OFF = WIDE ? (128 * 64 * 2) >> 4 : 4;   // descriptor offset (16-byte units) of the lo half
+};
 constexpr int SF_AUG = 16;                                   // folded-norm channels (one K=16 MMA)
-constexpr int SF_CHUNKS = SF_CH / 64;                        // 64-channel (128-byte) TMA boxes per row
 constexpr int SF_MAX_SPLIT = 8;
 constexpr uint32_t SF_TILE = 128 * 64 * 2;                   // 16 KB
 constexpr uint32_t SF_AUGT = 128 * SF_AUG * 2;               //  4 KB
@@ -253,11 +262,13 @@ __device__ __forceinline__ void soft_step(const uint32_t (&v)[SW], uint32_t xs /
     }
 }
 
-template <bool XYZ, bool BIAS>
+template <bool XYZ, bool BIAS, bool WIDE>
 __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                       const __grid_constant__ CUtensorMap mapB,
                                                                       const __grid_constant__ CUtensorMap mapAaug,
                                                                       const __grid_constant__ CUtensorMap mapBaug, SoftParams P) {
+    using Cfg = SoftCfg<WIDE>;
+    constexpr int SF_CHUNKS = Cfg::CHUNKS, SF_BSTAGES = Cfg::BSTAGES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;                                             // [RBS][CHUNKS][16 KB]
@@ -334,8 +345,8 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
         const uint64_t descB0 = make_kmajor_desc(smem_u32(sB), 1024, 2);
         const uint64_t descAaug = make_kmajor_desc(smem_u32(sAaug), 256, 6);
         const uint64_t descBaug0 = make_kmajor_desc(smem_u32(sBaug), 256, 6);
-        // halves of the 64-channel row, as descriptor offsets (16-byte units): hi at +0, lo at +64 bytes
-        constexpr uint32_t HI = 0, LO = 4;
+        // the two halves as descriptor offsets (16-byte units): hi at +0, lo at +64 bytes (or in the second chunk when WIDE)
+        constexpr uint32_t HI = 0, LO = Cfg::LO_OFF;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int sp = it % P.S;
             const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
@@ -350,12 +361,12 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(r * 128);
                     const uint64_t descA = descA0 + (uint64_t)(r * ((SF_CHUNKS * SF_TILE) >> 4));
-                    // three product groups, largest first: hi*hi, hi*lo, lo*hi (2 k-steps of 16 channels each)
+                    // three product groups, largest first: hi*hi, hi*lo, lo*hi (KS k-steps of 16 channels each)
                     const uint32_t ao[3] = {HI, HI, LO}, bo[3] = {HI, LO, HI};
 #pragma unroll
                     for (int g = 0; g < 3; ++g)
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks)
+                        for (int ks = 0; ks < Cfg::KS; ++ks)
                             mma_f16(d_tmem, descA + (uint64_t)(ao[g] + ks * 2), descB + (uint64_t)(bo[g] + ks * 2), SF_IDESC, (g | ks) ? 1u : 0u);
                     mma_f16(d_tmem, descAaug, descBaug, SF_IDESC, 1u);   // + sigma^2 |r_k|^2
                     tc_commit(&tmem_full[r]);
@@ -466,19 +477,21 @@ __device__ __forceinline__ float soft_sigma(float amax) {
     return exp2f((float)-e);
 }
 
-// [B,C,N] fp32 (any strides) -> fp16 [B][N][64] = hi(32) | lo(32) of  mul * sigma * f  (mul = -2 on the reference side,
+// [B,C,N] fp32 (any strides) -> fp16 [B][N][2 CMAX] = hi(CMAX) | lo(CMAX) of  mul * sigma * f  (mul = -2 on the reference side,
 // exact), and for the reference side the folded-norm tile [B][Npad][16] = three-term fp16 split of sigma^2 |r|^2.
 // One block = 32 points; thread = (point, group of 4 channels).  Block (0,0) also writes the constant source-side norm
 // tile; the first block of every batch writes sigma.
+template <bool WIDE>
 __global__ __launch_bounds__(256) void soft_prep_kernel(dsir_feat f, int C, int N, int Npad, int is_ref, const float *__restrict__ amax,
                                                         const float *__restrict__ nrm, __half *__restrict__ out, __half *__restrict__ aug,
                                                         __half *__restrict__ aug_const, float *__restrict__ scale_out) {
-    __shared__ float tile[SF_CMAX][33];
+    constexpr int CMAX = SoftCfg<WIDE>::CMAX, CH = SoftCfg<WIDE>::CH;
+    __shared__ float tile[CMAX][33];
     const int b = blockIdx.y, n0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float sigma = soft_sigma(amax[b]);
     const float *src = f.ptr + (size_t)b * f.batch_stride;
-    for (int c = ty; c < SF_CMAX; c += 8) {
+    for (int c = ty; c < CMAX; c += 8) {
         const int n = n0 + tx;
         tile[c][tx] = (c < C && n < N) ? src[(size_t)c * f.chan_stride + (size_t)n * f.point_stride] : 0.f;
     }
@@ -487,16 +500,19 @@ __global__ __launch_bounds__(256) void soft_prep_kernel(dsir_feat f, int C, int 
     const int n = n0 + i;
     if (n < N) {
         const float mul = (is_ref ? -2.f : 1.f) * sigma;     // power of two: the scaling is exact
-        __align__(8) __half hi[4], lo[4];
+        __half *o = out + ((size_t)b * N + n) * CH;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float v = tile[4 * g + k][i] * mul;
-            hi[k] = __float2half_rn(v);
-            lo[k] = __float2half_rn(v - __half2float(hi[k]));
+        for (int gg = g; gg < CMAX / 4; gg += 8) {           // groups of 4 channels: hi block at [0, CMAX), lo block at [CMAX, 2 CMAX)
+            __align__(8) __half hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float v = tile[4 * gg + k][i] * mul;
+                hi[k] = __float2half_rn(v);
+                lo[k] = __float2half_rn(v - __half2float(hi[k]));
+            }
+            *reinterpret_cast<uint2 *>(o + 4 * gg) = *reinterpret_cast<const uint2 *>(hi);
+            *reinterpret_cast<uint2 *>(o + CMAX + 4 * gg) = *reinterpret_cast<const uint2 *>(lo);
         }
-        __half *o = out + ((size_t)b * N + n) * SF_CH;
-        *reinterpret_cast<uint2 *>(o + 4 * g) = *reinterpret_cast<const uint2 *>(hi);
-        *reinterpret_cast<uint2 *>(o + 32 + 4 * g) = *reinterpret_cast<const uint2 *>(lo);
     }
     if (aug && n < Npad && g < 2) {
         __align__(16) __half h[8];
@@ -535,7 +551,8 @@ struct SoftPlan {
     size_t off_ns, off_nr, off_a, off_b, off_baug, off_aaug, off_amax, off_scale, off_xyzc, off_bias, off_part, total;
 };
 
-SoftPlan make_soft_plan(int B, int J, int K) {
+SoftPlan make_soft_plan(int B, int C, int J, int K) {
+    const int SF_CH = C > 32 ? SoftCfg<true>::CH : SoftCfg<false>::CH;
     SoftPlan p;
     p.RB = (J + SF_BM - 1) / SF_BM;
     p.U = (K + SF_BN - 1) / SF_BN;
@@ -567,14 +584,16 @@ SoftPlan make_soft_plan(int B, int J, int K) {
     return p;
 }
 
+template <bool WIDE>
 constexpr size_t soft_smem_bytes() {
-    return 1024 + (size_t)(SF_RBS + SF_BSTAGES) * SF_CHUNKS * SF_TILE + (size_t)(1 + SF_BSTAGES) * SF_AUGT + (size_t)SF_XSTAGES * SF_XT + 512;
+    return 1024 + (size_t)(SF_RBS + SoftCfg<WIDE>::BSTAGES) * SoftCfg<WIDE>::CHUNKS * SF_TILE + (size_t)(1 + SoftCfg<WIDE>::BSTAGES) * SF_AUGT +
+           (size_t)SF_XSTAGES * SF_XT + 512;
 }
 
 }  // namespace
 
 bool match_tc_soft_supported(int B, int C, int J, int K) {
-    if (C < 1 || C > SF_CMAX) return false;
+    if (C < 1 || C > SoftCfg<true>::CMAX) return false;
     if ((long long)B * J >= (1ll << 31) || (long long)B * K >= (1ll << 31)) return false;
     static const bool off = getenv("DSIR_SOFT_FP32") != nullptr;
     if (off) return false;
@@ -583,12 +602,13 @@ bool match_tc_soft_supported(int B, int C, int J, int K) {
 }
 
 size_t match_tc_soft_workspace_bytes(int B, int C, int J, int K) {
-    (void)C;
-    return make_soft_plan(B, J, K).total;
+    return make_soft_plan(B, C, J, K).total;
 }
 
 int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_t st) {
-    const SoftPlan pl = make_soft_plan(P.B, P.J, P.K);
+    const SoftPlan pl = make_soft_plan(P.B, P.C, P.J, P.K);
+    const bool wide = P.C > 32;
+    const int SF_CH = wide ? SoftCfg<true>::CH : SoftCfg<false>::CH;
     char *base = (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     if (ws == nullptr || (size_t)(base - (char *)ws) + pl.total - 1024 > ws_bytes) return DSIR_ERR_WORKSPACE;
     float *ns = (float *)(base + pl.off_ns), *nr = (float *)(base + pl.off_nr);
@@ -602,9 +622,11 @@ int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaSt
     // exact squared norms (fma chains) + the per-batch maximum over both clouds for sigma
     if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, ns, (int *)amax, nullptr, st))) return rc;
     if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, nr, (int *)amax, nullptr, st))) return rc;
-    soft_prep_kernel<<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, 0, amax, nullptr, a, nullptr, aaug, scale);
+    if (wide) soft_prep_kernel<true><<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, 0, amax, nullptr, a, nullptr, aaug, scale);
+    else soft_prep_kernel<false><<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, 0, amax, nullptr, a, nullptr, aaug, scale);
     DSIR_LAUNCH_CHECK();
-    soft_prep_kernel<<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, 1, amax, nr, bexp, baug, nullptr, nullptr);
+    if (wide) soft_prep_kernel<true><<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, 1, amax, nr, bexp, baug, nullptr, nullptr);
+    else soft_prep_kernel<false><<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, 1, amax, nr, bexp, baug, nullptr, nullptr);
     DSIR_LAUNCH_CHECK();
     soft_xtile_kernel<<<dim3(cdiv(pl.Kpad, 256), P.B), 256, 0, st>>>(P.y_soft ? P.xyz_ref : nullptr, P.col_bias, P.K, pl.Kpad, xtile);
     DSIR_LAUNCH_CHECK();
@@ -622,14 +644,16 @@ int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaSt
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = items < sms ? items : sms;
-    const size_t smem = soft_smem_bytes();
-#define DSIR_SOFT_LAUNCH(X, BI)                                                                                              \
+#define DSIR_SOFT_LAUNCH(X, BI, W)                                                                                           \
     do {                                                                                                                     \
-        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_soft_kernel<X, BI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        match_tc_soft_kernel<X, BI><<<grid, SF_THREADS, smem, st>>>(mapA, mapB, mapAaug, mapBaug, T);                                          \
+        const size_t smem = soft_smem_bytes<W>();                                                                           \
+        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_soft_kernel<X, BI, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        match_tc_soft_kernel<X, BI, W><<<grid, SF_THREADS, smem, st>>>(mapA, mapB, mapAaug, mapBaug, T);                     \
     } while (0)
-    if (P.y_soft) { if (P.col_bias) DSIR_SOFT_LAUNCH(true, true); else DSIR_SOFT_LAUNCH(true, false); }
-    else          { if (P.col_bias) DSIR_SOFT_LAUNCH(false, true); else DSIR_SOFT_LAUNCH(false, false); }
+#define DSIR_SOFT_LAUNCH_W(X, BI) do { if (wide) DSIR_SOFT_LAUNCH(X, BI, true); else DSIR_SOFT_LAUNCH(X, BI, false); } while (0)
+    if (P.y_soft) { if (P.col_bias) DSIR_SOFT_LAUNCH_W(true, true); else DSIR_SOFT_LAUNCH_W(true, false); }
+    else          { if (P.col_bias) DSIR_SOFT_LAUNCH_W(false, true); else DSIR_SOFT_LAUNCH_W(false, false); }
+#undef DSIR_SOFT_LAUNCH_W
 #undef DSIR_SOFT_LAUNCH
     DSIR_LAUNCH_CHECK();
     const long long rows = (long long)P.B * P.J;

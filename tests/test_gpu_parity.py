@@ -657,9 +657,9 @@ def test_match_c4_full_size_properties():
     assert torch.equal(exact, part)
 
 
-@pytest.mark.parametrize("shape", [(2, 32, 3000, 2777), (1, 20, 1500, 4100), (3, 32, 700, 1100)])
+@pytest.mark.parametrize("shape", [(2, 32, 3000, 2777), (1, 20, 1500, 4100), (3, 32, 700, 1100), (2, 64, 1500, 1300), (1, 48, 2100, 1000)])
 def test_match_soft_tensor_core_path(shape):
-    """The tcgen05 soft match (bf16 x3 split contraction + online softmax in the TMEM epilogue; C <= 32 and B*J*K >= 2e6):
+    """The tcgen05 soft match (fp16 x2 split contraction + online softmax in the TMEM epilogue; C <= 64 and B*J*K >= 2e6):
     lse, soft targets and reconstructed weights against the fp32 oracle, with and without a column bias, J/K not
     multiples of the tile."""
     B, C, J, K = shape
