@@ -425,10 +425,12 @@ size_t dsir_match_argmin_workspace_bytes(int B, int C, int J, int K, int algo) {
     return bytes;
 }
 
-int dsir_match_argmin(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int64_t *idx, float *min_d, void *ws,
-                      size_t ws_bytes, int algo, dsir_stream_t stream) {
+}  // extern "C"
+
+// reuse_prep: iterations 2.. of the alignment loop (same features, same workspace): norms / operand copies are kept
+static int match_argmin_impl(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int64_t *idx, float *min_d, void *ws,
+                             size_t ws_bytes, int algo, bool reuse_prep, cudaStream_t st) {
     if (!feat_ok(fs) || !feat_ok(fr) || !idx || B <= 0 || C <= 0 || J <= 0 || K <= 0) return DSIR_ERR_BAD_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
     Workspace W(ws, ws_bytes);
     float *ns = W.take<float>((size_t)B * J);
     float *nr = W.take<float>((size_t)B * K);
@@ -436,16 +438,25 @@ int dsir_match_argmin(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, in
     int rc;
     MatchParams P{};
     P.fs = fs; P.fr = fr; P.B = B; P.C = C; P.J = J; P.K = K; P.ns = ns; P.nr = nr;
-    P.idx = idx; P.min_d = min_d;
+    P.idx = idx; P.min_d = min_d; P.reuse_prep = reuse_prep ? 1 : 0;
     bool tc_ok = match_tc_supported(fs, fr, B, C, J, K);
     if (algo == DSIR_MATCH_TC && !tc_ok) return DSIR_ERR_UNSUPPORTED;
     if (algo == DSIR_MATCH_TC || (algo == DSIR_MATCH_AUTO && tc_ok && match_tc_profitable(B, C, J, K))) {
         size_t used = W.off;
         return launch_match_tc(P, (char *)ws + used, ws_bytes - used, st);   // fills ns / nr itself (norms + maxima fused)
     }
-    if ((rc = launch_sqnorm(fs, B, C, J, ns, st))) return rc;
-    if ((rc = launch_sqnorm(fr, B, C, K, nr, st))) return rc;
+    if (!reuse_prep) {
+        if ((rc = launch_sqnorm(fs, B, C, J, ns, st))) return rc;
+        if ((rc = launch_sqnorm(fr, B, C, K, nr, st))) return rc;
+    }
     return launch_match_fp32(P, MATCH_MODE_ARGMIN, st);
+}
+
+extern "C" {
+
+int dsir_match_argmin(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int64_t *idx, float *min_d, void *ws,
+                      size_t ws_bytes, int algo, dsir_stream_t stream) {
+    return match_argmin_impl(fs, fr, B, C, J, K, idx, min_d, ws, ws_bytes, algo, false, (cudaStream_t)stream);
 }
 
 int dsir_match_argmin_rescued_rows(const void *ws, size_t ws_bytes, int B, int C, int J, int K, int32_t *host_out,
@@ -650,7 +661,8 @@ int dsir_align_loop(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, floa
     dsir_points ref{xyz_ref, (int64_t)3 * K, 1, K};  // [B,3,K]
     for (int it = 0; it < iters; ++it) {
         int64_t *idx = pred_idx ? pred_idx + (size_t)it * B * J : idx_scratch;
-        int rc = dsir_match_argmin(fs, fr, B, C, J, K, idx, nullptr, match_ws, match_bytes, algo, stream);  // :558-569
+        // the features do not change inside this entry point: norms and operand copies are prepared once
+        int rc = match_argmin_impl(fs, fr, B, C, J, K, idx, nullptr, match_ws, match_bytes, algo, it > 0, st);  // :558-569
         if (rc) return rc;
         double *partials; int nblk;
         rc = kabsch_common(src, ref, weights, J, idx, B, J, &partials, &nblk, kab_ws, kab_bytes, st);    // :571,:588

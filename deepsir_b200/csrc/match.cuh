@@ -16,6 +16,9 @@ struct MatchParams {
     // soft
     const float *beta, *alpha, *col_bias, *xyz_ref;
     float *y_soft, *lse;
+    // the caller guarantees that features and workspace are those of its previous call (iterations 2.. of the alignment
+    // loop): norms, maxima and the tensor-core operand copies in the workspace are still valid and are not recomputed
+    int reuse_prep;
 };
 
 enum { MATCH_MODE_ARGMIN = 0, MATCH_MODE_DENSE = 1, MATCH_MODE_SOFT = 2 };

@@ -845,17 +845,19 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     float *cval = (float *)(base + pl.off_cval);
     int *cidx = (int *)(base + pl.off_cidx), *count = (int *)(base + pl.off_count), *rows = (int *)(base + pl.off_rows);
 
-    // rmax and amax are adjacent 256-byte blocks: one memset clears both
-    DSIR_CUDA_TRY(cudaMemsetAsync(rmax, 0, pl.off_scale - pl.off_rmax, st));
     DSIR_CUDA_TRY(cudaMemsetAsync(count, 0, 8, st));
     int rc;
-    // exact squared norms (fma chains, shared with the fp32 kernel) + per-batch maxima for sigma and the margin
-    if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, const_cast<float *>(P.nr), (int *)rmax, (int *)amax, st))) return rc;
-    if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, const_cast<float *>(P.ns), (int *)amax, nullptr, st))) return rc;
-    tc_prep_kernel<<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, amax, nullptr, 1.0f, a16, nullptr, aaug, scale);
-    DSIR_LAUNCH_CHECK();
-    tc_prep_kernel<<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, amax, P.nr, -2.0f, b16, baug, nullptr, nullptr);
-    DSIR_LAUNCH_CHECK();
+    if (!P.reuse_prep) {
+        // rmax and amax are adjacent 256-byte blocks: one memset clears both
+        DSIR_CUDA_TRY(cudaMemsetAsync(rmax, 0, pl.off_scale - pl.off_rmax, st));
+        // exact squared norms (fma chains, shared with the fp32 kernel) + per-batch maxima for sigma and the margin
+        if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, const_cast<float *>(P.nr), (int *)rmax, (int *)amax, st))) return rc;
+        if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, const_cast<float *>(P.ns), (int *)amax, nullptr, st))) return rc;
+        tc_prep_kernel<<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, amax, nullptr, 1.0f, a16, nullptr, aaug, scale);
+        DSIR_LAUNCH_CHECK();
+        tc_prep_kernel<<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, amax, P.nr, -2.0f, b16, baug, nullptr, nullptr);
+        DSIR_LAUNCH_CHECK();
+    }
     CUtensorMap mapA, mapB, mapAaug, mapBaug;
     if (!make_half_tmap(&mapA, a16, P.B, P.J, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
         !make_half_tmap(&mapB, b16, P.B, P.K, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
