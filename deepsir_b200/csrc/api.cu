@@ -493,14 +493,24 @@ size_t dsir_match_soft_workspace_bytes(int B, int C, int J, int K) {
     return fp32;
 }
 
-int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
-                    const float *col_bias, const float *xyz_ref, float *y_soft, float *lse, int topk,
-                    int64_t *topk_idx, float *topk_w, void *ws, size_t ws_bytes, dsir_stream_t stream) {
-    if (!feat_ok(fs) || !feat_ok(fr) || !beta || !alpha || B <= 0 || C <= 0 || J <= 0 || K <= 0) return DSIR_ERR_BAD_ARG;
-    if (y_soft && !xyz_ref) return DSIR_ERR_BAD_ARG;
-    if (topk != 0) { (void)topk_idx; (void)topk_w; return DSIR_ERR_UNSUPPORTED; }
-    cudaStream_t st = (cudaStream_t)stream;
-    if (match_tc_soft_supported(B, C, J, K) && (y_soft || lse)) {   // tcgen05: bf16 x3 split + online softmax in the TMEM epilogue
+// extra workspace of the top-k pass: a row chunk of the distance matrix (<= 256 MB), chunk norms, reference norms, lse
+static size_t soft_topk_chunk_rows(int B, int J, int K) {
+    long long rows = (256ll << 20) / ((long long)B * K * 4);
+    if (rows < 1) rows = 1;
+    if (rows > J) rows = J;
+    return (size_t)rows;
+}
+size_t dsir_match_soft_topk_workspace_bytes(int B, int C, int J, int K, int topk) {
+    size_t base = dsir_match_soft_workspace_bytes(B, C, J, K);
+    if (topk <= 0 || B <= 0 || J <= 0 || K <= 0) return base;
+    const size_t Jc = soft_topk_chunk_rows(B, J, K);
+    return base + ws_block((size_t)B * Jc * K * 4) + ws_block((size_t)B * Jc * 4) + ws_block((size_t)B * K * 4) + ws_block((size_t)B * J * 4) + 256;
+}
+
+static int match_soft_core(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
+                           const float *col_bias, const float *xyz_ref, float *y_soft, float *lse, void *ws, size_t ws_bytes,
+                           cudaStream_t st) {
+    if (match_tc_soft_supported(B, C, J, K) && (y_soft || lse)) {   // tcgen05: fp16 x2 split + online softmax in the TMEM epilogue
         MatchParams T{};
         T.fs = fs; T.fr = fr; T.B = B; T.C = C; T.J = J; T.K = K;
         T.beta = beta; T.alpha = alpha; T.col_bias = col_bias; T.xyz_ref = xyz_ref; T.y_soft = y_soft; T.lse = lse;
@@ -517,6 +527,43 @@ int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, cons
     P.fs = fs; P.fr = fr; P.B = B; P.C = C; P.J = J; P.K = K; P.ns = ns; P.nr = nr;
     P.beta = beta; P.alpha = alpha; P.col_bias = col_bias; P.xyz_ref = xyz_ref; P.y_soft = y_soft; P.lse = lse;
     return launch_match_fp32(P, MATCH_MODE_SOFT, st);
+}
+
+int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
+                    const float *col_bias, const float *xyz_ref, float *y_soft, float *lse, int topk,
+                    int64_t *topk_idx, float *topk_w, void *ws, size_t ws_bytes, dsir_stream_t stream) {
+    if (!feat_ok(fs) || !feat_ok(fr) || !beta || !alpha || B <= 0 || C <= 0 || J <= 0 || K <= 0) return DSIR_ERR_BAD_ARG;
+    if (y_soft && !xyz_ref) return DSIR_ERR_BAD_ARG;
+    if (topk < 0 || (topk > 0 && (!topk_idx || !topk_w))) return DSIR_ERR_BAD_ARG;
+    if (topk > 32 || topk > K) return topk > K ? DSIR_ERR_BAD_ARG : DSIR_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (topk == 0) return match_soft_core(fs, fr, B, C, J, K, beta, alpha, col_bias, xyz_ref, y_soft, lse, ws, ws_bytes, st);
+    // ---- top-k: the fused pass gives lse (and y); the k largest weights of a row come from row chunks of the exact fp32
+    //      distance matrix (DENSE kernel), one warp per row ----
+    const size_t base = dsir_match_soft_workspace_bytes(B, C, J, K);
+    if (!ws || ws_bytes < dsir_match_soft_topk_workspace_bytes(B, C, J, K, topk)) return DSIR_ERR_WORKSPACE;
+    Workspace W((char *)ws + base, ws_bytes - base);
+    const int Jc = (int)soft_topk_chunk_rows(B, J, K);
+    float *chunk = W.take<float>((size_t)B * Jc * K);
+    float *ns_c = W.take<float>((size_t)B * Jc);
+    float *nr = W.take<float>((size_t)B * K);
+    float *lse_tmp = W.take<float>((size_t)B * J);
+    if (!W.ok()) return DSIR_ERR_WORKSPACE;
+    float *lse_use = lse ? lse : lse_tmp;
+    int rc;
+    if ((rc = match_soft_core(fs, fr, B, C, J, K, beta, alpha, col_bias, xyz_ref, y_soft, lse_use, ws, base, st))) return rc;
+    if ((rc = launch_sqnorm(fr, B, C, K, nr, st))) return rc;
+    for (int j0 = 0; j0 < J; j0 += Jc) {
+        const int jc = J - j0 < Jc ? J - j0 : Jc;
+        dsir_feat fsc = fs;
+        fsc.ptr = fs.ptr + (size_t)j0 * fs.point_stride;
+        if ((rc = launch_sqnorm(fsc, B, C, jc, ns_c, st))) return rc;
+        MatchParams D{};
+        D.fs = fsc; D.fr = fr; D.B = B; D.C = C; D.J = jc; D.K = K; D.ns = ns_c; D.nr = nr; D.dense = chunk; D.metric = DSIR_METRIC_L2;
+        if ((rc = launch_match_fp32(D, MATCH_MODE_DENSE, st))) return rc;
+        if ((rc = launch_row_topk(chunk, B, jc, K, beta, alpha, col_bias, lse_use, J, j0, topk, topk_idx, topk_w, (long long)J * topk, st))) return rc;
+    }
+    return DSIR_OK;
 }
 
 int dsir_gather_points(const float *in, int B, int C, int N, const int64_t *idx, int M, float *out,

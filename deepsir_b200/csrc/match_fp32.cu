@@ -272,4 +272,75 @@ int launch_match_fp32(const MatchParams &P, int mode, cudaStream_t st) {
     return DSIR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// top-k soft correspondences of every row from a materialised distance chunk: a_jk = -beta (d_jk - alpha) (+ bias_k),
+// the k largest a_jk (= largest weights), descending, ties to the lower index; w = exp(a - lse_j).
+// One warp per row: every lane keeps the k best of its strided columns in a sorted register list, then k rounds of a
+// warp arg-max over the lane heads merge the 32 lists.
+// ---------------------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ __launch_bounds__(256) void row_topk_kernel(const float *__restrict__ dist, int B, int Jc, int K, const float *__restrict__ beta,
+                                                       const float *__restrict__ alpha, const float *__restrict__ bias, const float *__restrict__ lse,
+                                                       long long lse_bs, int j0, int topk, int64_t *__restrict__ out_idx, float *__restrict__ out_w,
+                                                       long long out_bs) {
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= (long long)B * Jc) return;
+    const int b = (int)(row / Jc), jr = (int)(row % Jc);
+    const float *d = dist + (size_t)row * K;
+    const float nb = -beta[b], al = alpha[b];
+    float bv[KMAX];
+    int bi[KMAX];
+#pragma unroll
+    for (int p = 0; p < KMAX; ++p) { bv[p] = -INFINITY; bi[p] = 0x7fffffff; }
+    for (int k = lane; k < K; k += 32) {
+        float a = nb * (d[k] - al);
+        if (bias) a += bias[(size_t)b * K + k];
+        if (a > bv[KMAX - 1] || (a == bv[KMAX - 1] && k < bi[KMAX - 1])) {   // sorted insertion, descending (value, -index)
+#pragma unroll
+            for (int p = KMAX - 1; p >= 0; --p) {
+                const int pm = p > 0 ? p - 1 : 0;
+                const bool shift = (p > 0) && (a > bv[pm] || (a == bv[pm] && k < bi[pm]));
+                const bool here = !shift && (a > bv[p] || (a == bv[p] && k < bi[p]));
+                bv[p] = shift ? bv[pm] : (here ? a : bv[p]);
+                bi[p] = shift ? bi[pm] : (here ? k : bi[p]);
+            }
+        }
+    }
+    const float l = lse[(size_t)b * lse_bs + j0 + jr];
+    int64_t *oi = out_idx + (size_t)b * out_bs + (size_t)(j0 + jr) * topk;
+    float *ow = out_w + (size_t)b * out_bs + (size_t)(j0 + jr) * topk;
+    for (int t = 0; t < topk; ++t) {
+        // warp arg-max over the lane heads
+        float v = bv[0];
+        int i = bi[0], src = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, i, o), s2 = __shfl_xor_sync(0xffffffffu, src, o);
+            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; src = s2; }
+        }
+        if (lane == src) {       // pop the head
+#pragma unroll
+            for (int p = 0; p < KMAX - 1; ++p) { bv[p] = bv[p + 1]; bi[p] = bi[p + 1]; }
+            bv[KMAX - 1] = -INFINITY; bi[KMAX - 1] = 0x7fffffff;
+        }
+        if (lane == 0) {
+            oi[t] = i == 0x7fffffff ? (int64_t)-1 : (int64_t)i;
+            ow[t] = i == 0x7fffffff ? 0.f : expf(v - l);
+        }
+    }
+}
+
+int launch_row_topk(const float *dist, int B, int Jc, int K, const float *beta, const float *alpha, const float *bias, const float *lse,
+                    long long lse_bs, int j0, int topk, int64_t *out_idx, float *out_w, long long out_bs, cudaStream_t st) {
+    const long long warps = (long long)B * Jc;
+    const unsigned grid = (unsigned)((warps + 7) / 8);
+    if (topk <= 8) row_topk_kernel<8><<<grid, 256, 0, st>>>(dist, B, Jc, K, beta, alpha, bias, lse, lse_bs, j0, topk, out_idx, out_w, out_bs);
+    else if (topk <= 32) row_topk_kernel<32><<<grid, 256, 0, st>>>(dist, B, Jc, K, beta, alpha, bias, lse, lse_bs, j0, topk, out_idx, out_w, out_bs);
+    else return DSIR_ERR_UNSUPPORTED;
+    DSIR_LAUNCH_CHECK();
+    return DSIR_OK;
+}
+
 }  // namespace dsir

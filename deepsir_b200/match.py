@@ -120,10 +120,11 @@ def compute_affinity(beta, feat_distance, alpha=0.5):
     return -beta[:, None, None] * (feat_distance - alpha[:, None, None])
 
 
-def match_soft(feat_src, feat_ref, xyz_ref, beta, alpha=0.5, col_bias=None):
+def match_soft(feat_src, feat_ref, xyz_ref, beta, alpha=0.5, col_bias=None, topk=0):
     """Fused compute_affinity (matchnet.py:195-208) + row softmax (sinkhorn row pass, :259) + soft target
     (network/model.py:81-84).  feat [B,C,J],[B,C,K]; xyz_ref [B,K,3]; beta [B]; alpha float or [B].
-    Returns (y_soft [B,J,3], rowmass [B,J], lse [B,J])."""
+    Returns (y_soft [B,J,3], rowmass [B,J], lse [B,J]); with topk > 0 additionally (topk_idx int64 [B,J,topk],
+    topk_w [B,J,topk]): the topk largest soft weights of every row, descending, ties to the lower index."""
     dev = L.require_cuda(feat_src, feat_ref, xyz_ref, beta)
     B, C, J = feat_src.shape
     K = feat_ref.shape[2]
@@ -135,12 +136,15 @@ def match_soft(feat_src, feat_ref, xyz_ref, beta, alpha=0.5, col_bias=None):
     cb = col_bias.contiguous() if col_bias is not None else None
     y = torch.empty(B, J, 3, dtype=torch.float32, device=dev) if xyz_ref is not None else None
     lse = torch.empty(B, J, dtype=torch.float32, device=dev)
+    tk_i = torch.empty(B, J, topk, dtype=torch.int64, device=dev) if topk > 0 else None
+    tk_w = torch.empty(B, J, topk, dtype=torch.float32, device=dev) if topk > 0 else None
     lib = L.lib()
-    ws = L.workspace(lib.dsir_match_soft_workspace_bytes(B, C, J, K), dev)
+    ws = L.workspace(lib.dsir_match_soft_topk_workspace_bytes(B, C, J, K, topk), dev)
     L.check(lib.dsir_match_soft(fs, fr, B, C, J, K, beta.data_ptr(), alpha_t.data_ptr(), L.ptr(cb), L.ptr(xyz_ref),
-                                L.ptr(y), lse.data_ptr(), 0, None, None, ws.data_ptr(), ws.numel(),
+                                L.ptr(y), lse.data_ptr(), topk, L.ptr(tk_i), L.ptr(tk_w), ws.data_ptr(), ws.numel(),
                                 L.stream_ptr(dev)), "dsir_match_soft")
-    return y, torch.ones(B, J, dtype=torch.float32, device=dev), lse
+    ones = torch.ones(B, J, dtype=torch.float32, device=dev)
+    return (y, ones, lse, tk_i, tk_w) if topk > 0 else (y, ones, lse)
 
 
 def sinkhorn_implicit(feat_src, feat_ref, xyz_ref, beta, alpha=0.5, n_iters=5, slack=True):

@@ -119,8 +119,10 @@ int dsir_match_argmin_filter_trace(const void *ws, size_t ws_bytes, int B, int C
  *   lse_j = log sum_k exp(a_jk);  w_jk = exp(a_jk - lse_j)      row pass of sinkhorn, matchnet.py:259
  *   y_j = sum_k w_jk xyz_ref[b,k,:] / (sum_k w_jk + 1e-16)      soft target, network/model.py:81-84
  * outputs: y_soft [B,J,3] (or NULL), lse [B,J] (or NULL); topk > 0 additionally returns the topk largest
- * weights per row, descending, ties to the lower index: topk_idx [B,J,topk] int64, topk_w [B,J,topk]. */
+ * weights per row, descending, ties to the lower index: topk_idx [B,J,topk] int64, topk_w [B,J,topk] (topk <= 32;
+ * workspace from dsir_match_soft_topk_workspace_bytes). */
 size_t dsir_match_soft_workspace_bytes(int B, int C, int J, int K);
+size_t dsir_match_soft_topk_workspace_bytes(int B, int C, int J, int K, int topk);
 int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
                     const float *col_bias, const float *xyz_ref, float *y_soft, float *lse, int topk,
                     int64_t *topk_idx, float *topk_w, void *ws, size_t ws_bytes, dsir_stream_t stream);

@@ -681,3 +681,33 @@ def test_match_soft_tensor_core_path(shape):
     _, _, lse_b = D.match_soft(cu(fs), cu(fr), None, cu(beta), cu(alpha), col_bias=cu(bias))
     ref = torch.logsumexp(a + bias[:, None, :], dim=2)
     assert torch.allclose(lse_b.cpu(), ref, rtol=SOFT_RTOL, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape,topk", [((2, 32, 700, 900), 4), ((1, 64, 300, 2500), 16), ((2, 32, 2100, 1000), 8)])
+def test_match_soft_topk(shape, topk):
+    """Top-k soft correspondences: the k largest weights of every row, descending, ties to the lower index; equal to the
+    top-k of the reference's materialised softmax (matchnet.py:195-208,259)."""
+    B, C, J, K = shape
+    b = synth.make_batch(B, max(J, K), C, "3dmatch", config=3, first_pair=77)
+    fs, fr = b["feat_src"][:, :, :J].contiguous(), b["feat_ref"][:, :, :K].contiguous()
+    fr[:, :, 5] = fr[:, :, 3]                                      # an exactly duplicated reference point: tie -> lower index
+    xyz = b["points_ref"][:, :K, :3].contiguous()
+    beta, alpha = torch.tensor([10.0, 6.0][:B]), torch.tensor([0.5, 0.3][:B])
+    w, y, s, lse = O.soft_correspondence(fs, fr, xyz, beta, alpha)
+    y_g, _, lse_g, ti, tw = D.match_soft(cu(fs), cu(fr), cu(xyz), cu(beta), cu(alpha), topk=topk)
+    assert torch.allclose(lse_g.cpu(), lse, rtol=SOFT_RTOL, atol=1e-5) and torch.allclose(y_g.cpu(), y, rtol=SOFT_RTOL, atol=1e-4)
+    a = O.compute_affinity(beta, O.match_features_V2(fs, fr), alpha)
+    ti, tw = ti.cpu(), tw.cpu()
+    assert (tw[:, :, 1:] <= tw[:, :, :-1]).all()
+    assert torch.allclose(tw, torch.gather(w, 2, ti), rtol=5 * SOFT_RTOL, atol=1e-7)
+    ref_w, _ = torch.topk(w, topk, dim=2)
+    assert torch.allclose(tw, ref_w, rtol=5 * SOFT_RTOL, atol=1e-7)
+    # index sets: equal wherever the k-th and (k+1)-th affinities are separated by more than fp32 round-off
+    srt, order = torch.sort(a, dim=2, descending=True, stable=True)
+    clear = (srt[:, :, topk - 1] - srt[:, :, topk]) > 1e-4
+    same = (torch.sort(ti, dim=2)[0] == torch.sort(order[:, :, :topk], dim=2)[0]).all(dim=2)
+    assert same[clear].all() and clear.float().mean() > 0.9
+    has3 = (ti == 3).any(dim=2) & (ti == 5).any(dim=2)            # the duplicated pair appears as (3 before 5)
+    pos3 = (ti == 3).float().argmax(dim=2)
+    pos5 = (ti == 5).float().argmax(dim=2)
+    assert (pos3[has3] < pos5[has3]).all()
