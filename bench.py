@@ -173,12 +173,14 @@ def main():
     ev = lambda: torch.cuda.Event(enable_timing=True)
     match_events, knn_events = [], []
 
+    knn_stream = torch.cuda.Stream(dev)
+
     def step_resident(record=False):
-        if record:
+        cur = torch.cuda.current_stream(dev)
+        if record:      # attribution passes: everything in sequence on one stream, bracketed by events
             k0, k1 = ev(), ev()
             k0.record()
-        D.nn_search_pair(devt["points_src"], devt["points_ref"], KNN_K, RATIOS)   # two streams, joined on return
-        if record:
+            D.nn_search_pair(devt["points_src"], devt["points_ref"], KNN_K, RATIOS)
             k1.record()
             knn_events.append((k0, k1))
             e0, e1 = ev(), ev()
@@ -186,7 +188,16 @@ def main():
             D.match_argmin(devt["feat_src"], devt["feat_ref"])        # the dominant kernel, timed on its own stream
             e1.record()
             match_events.append((e0, e1))
-        return D.align_loop(devt["feat_src"], devt["feat_ref"], xs0, xr0, devt["weights"], 1)
+            return D.align_loop(devt["feat_src"], devt["feat_ref"], xs0, xr0, devt["weights"], 1)
+        # The KNN pyramids of a batch do not depend on its match / Kabsch (in the reference they run in the DataLoader
+        # workers while the GPU is busy with the previous batch): they go to a forked stream and are joined at the end of
+        # the step, so that their latency-bound kernels fill the gaps around the persistent match kernel.
+        knn_stream.wait_stream(cur)
+        with torch.cuda.stream(knn_stream):
+            g = D.nn_search_pair(devt["points_src"], devt["points_ref"], KNN_K, RATIOS)
+        out = D.align_loop(devt["feat_src"], devt["feat_ref"], xs0, xr0, devt["weights"], 1)
+        cur.wait_stream(knn_stream)
+        return out, g
 
     def barrier():
         if world > 1:
@@ -216,6 +227,10 @@ def main():
     import re
     lib = D.lib()
     n_prof = 3
+    torch.cuda.empty_cache()          # the timed loop used the forked KNN stream's pool: start the sequential passes clean
+    step_resident(record=True)        # (absorbs the allocations of the first sequential pass)
+    torch.cuda.synchronize()
+    match_events.clear(); knn_events.clear()
     lib.dsir_profile_begin(torch.cuda.current_stream().cuda_stream)
     for _ in range(n_prof):
         step_resident(record=True)
@@ -235,6 +250,7 @@ def main():
     # ---------------------------------------------------------------- end to end through the host API (`e2e`)
     # RegistrationPipeline.run: every step uploads its inputs from pinned host memory (copy stream, overlapped with
     # the previous step's kernels) and downloads transforms + int32 correspondences (model.py:599-601) to the host.
+    torch.cuda.empty_cache()
     pipe = D.RegistrationPipeline(dev, KNN_K, RATIOS, iters=1, depth=2)
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())
     d2h = 0
