@@ -711,3 +711,24 @@ def test_match_soft_topk(shape, topk):
     pos3 = (ti == 3).float().argmax(dim=2)
     pos5 = (ti == 5).float().argmax(dim=2)
     assert (pos3[has3] < pos5[has3]).all()
+
+
+@pytest.mark.parametrize("shape,beta", [((64, 16, 200, 180), 10.0), ((1, 32, 130, 20001), 25.0), ((2, 64, 1111, 1000), 100.0),
+                                        ((4, 8, 777, 777), 1.0)])
+def test_match_soft_tensor_core_edge_shapes(shape, beta):
+    """Tensor-core soft path on awkward shapes: many tiny pairs, one short/very wide pair (K-splits), a sharp softmax
+    (beta = 100: weights span > 100 binades), few channels.  Includes rows that are exact copies of reference rows
+    (d = 0: the weight concentrates on one column)."""
+    B, C, J, K = shape
+    g = torch.Generator().manual_seed(J + K)
+    fs = torch.nn.functional.normalize(torch.randn(B, C, J, generator=g), dim=1)
+    fr = torch.nn.functional.normalize(torch.randn(B, C, K, generator=g), dim=1)
+    fs[:, :, : min(J, K) // 2] = fr[:, :, : min(J, K) // 2]
+    xyz = torch.rand(B, K, 3, generator=g) * 3
+    bt = torch.full((B,), beta)
+    w, y, s, lse = O.soft_correspondence(fs, fr, xyz, bt, 0.5)
+    y_g, _, lse_g = D.match_soft(cu(fs), cu(fr), cu(xyz), cu(bt), 0.5)
+    assert torch.allclose(lse_g.cpu(), lse, rtol=SOFT_RTOL, atol=2e-5 * max(1.0, beta / 10))
+    assert torch.allclose(y_g.cpu(), y, rtol=SOFT_RTOL, atol=1e-4 * max(1.0, beta / 25))
+    T_o, _ = O.compute_rigid_transform(torch.rand(B, J, 3, generator=g), xyz, w)
+    assert torch.isfinite(y_g).all() and torch.isfinite(lse_g).all()
