@@ -87,6 +87,8 @@ _SIGS = {
     "dsir_match_argmin_filter_trace": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                                   _c.c_void_p, _c.c_void_p]),
     "dsir_match_soft_workspace_bytes": (_c.c_size_t, [_c.c_int] * 4),
+    "dsir_match_soft_sweep": (_c.c_int, [Feat, Feat, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "dsir_match_soft_topk_workspace_bytes": (_c.c_size_t, [_c.c_int] * 5),
     "dsir_match_soft": (_c.c_int, [Feat, Feat, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                    _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,

@@ -509,11 +509,12 @@ size_t dsir_match_soft_topk_workspace_bytes(int B, int C, int J, int K, int topk
 
 static int match_soft_core(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
                            const float *col_bias, const float *xyz_ref, float *y_soft, float *lse, void *ws, size_t ws_bytes,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool reuse_prep = false) {
     if (match_tc_soft_supported(B, C, J, K) && (y_soft || lse)) {   // tcgen05: fp16 x2 split + online softmax in the TMEM epilogue
         MatchParams T{};
         T.fs = fs; T.fr = fr; T.B = B; T.C = C; T.J = J; T.K = K;
         T.beta = beta; T.alpha = alpha; T.col_bias = col_bias; T.xyz_ref = xyz_ref; T.y_soft = y_soft; T.lse = lse;
+        T.reuse_prep = reuse_prep ? 1 : 0;
         return launch_match_tc_soft(T, ws, ws_bytes, st);
     }
     Workspace W(ws, ws_bytes);
@@ -521,8 +522,10 @@ static int match_soft_core(dsir_feat fs, dsir_feat fr, int B, int C, int J, int 
     float *nr = W.take<float>((size_t)B * K);
     if (!W.ok()) return DSIR_ERR_WORKSPACE;
     int rc;
-    if ((rc = launch_sqnorm(fs, B, C, J, ns, st))) return rc;
-    if ((rc = launch_sqnorm(fr, B, C, K, nr, st))) return rc;
+    if (!reuse_prep) {
+        if ((rc = launch_sqnorm(fs, B, C, J, ns, st))) return rc;
+        if ((rc = launch_sqnorm(fr, B, C, K, nr, st))) return rc;
+    }
     MatchParams P{};
     P.fs = fs; P.fr = fr; P.B = B; P.C = C; P.J = J; P.K = K; P.ns = ns; P.nr = nr;
     P.beta = beta; P.alpha = alpha; P.col_bias = col_bias; P.xyz_ref = xyz_ref; P.y_soft = y_soft; P.lse = lse;
@@ -564,6 +567,15 @@ int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, cons
         if ((rc = launch_row_topk(chunk, B, jc, K, beta, alpha, col_bias, lse_use, J, j0, topk, topk_idx, topk_w, (long long)J * topk, st))) return rc;
     }
     return DSIR_OK;
+}
+
+int dsir_match_soft_sweep(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
+                          const float *col_bias, const float *xyz_ref, float *y_soft, float *lse, int reuse_prep, void *ws,
+                          size_t ws_bytes, dsir_stream_t stream) {
+    if (!feat_ok(fs) || !feat_ok(fr) || !beta || !alpha || B <= 0 || C <= 0 || J <= 0 || K <= 0) return DSIR_ERR_BAD_ARG;
+    if (y_soft && !xyz_ref) return DSIR_ERR_BAD_ARG;
+    return match_soft_core(fs, fr, B, C, J, K, beta, alpha, col_bias, xyz_ref, y_soft, lse, ws, ws_bytes, (cudaStream_t)stream,
+                           reuse_prep != 0);
 }
 
 int dsir_gather_points(const float *in, int B, int C, int N, const int64_t *idx, int M, float *out,

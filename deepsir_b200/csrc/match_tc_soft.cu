@@ -618,16 +618,18 @@ int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaSt
     float *xtile = (float *)(base + pl.off_xyzc);
     float *part = (float *)(base + pl.off_part);
     int rc;
-    DSIR_CUDA_TRY(cudaMemsetAsync(amax, 0, (size_t)P.B * 4, st));
-    // exact squared norms (fma chains) + the per-batch maximum over both clouds for sigma
-    if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, ns, (int *)amax, nullptr, st))) return rc;
-    if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, nr, (int *)amax, nullptr, st))) return rc;
-    if (wide) soft_prep_kernel<true><<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, 0, amax, nullptr, a, nullptr, aaug, scale);
-    else soft_prep_kernel<false><<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, 0, amax, nullptr, a, nullptr, aaug, scale);
-    DSIR_LAUNCH_CHECK();
-    if (wide) soft_prep_kernel<true><<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, 1, amax, nr, bexp, baug, nullptr, nullptr);
-    else soft_prep_kernel<false><<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, 1, amax, nr, bexp, baug, nullptr, nullptr);
-    DSIR_LAUNCH_CHECK();
+    if (!P.reuse_prep) {   // (a sweep of Sinkhorn re-uses the operands of its previous sweep: only the bias changes)
+        DSIR_CUDA_TRY(cudaMemsetAsync(amax, 0, (size_t)P.B * 4, st));
+        // exact squared norms (fma chains) + the per-batch maximum over both clouds for sigma
+        if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, ns, (int *)amax, nullptr, st))) return rc;
+        if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, nr, (int *)amax, nullptr, st))) return rc;
+        if (wide) soft_prep_kernel<true><<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, 0, amax, nullptr, a, nullptr, aaug, scale);
+        else soft_prep_kernel<false><<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, 0, amax, nullptr, a, nullptr, aaug, scale);
+        DSIR_LAUNCH_CHECK();
+        if (wide) soft_prep_kernel<true><<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, 1, amax, nr, bexp, baug, nullptr, nullptr);
+        else soft_prep_kernel<false><<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, 1, amax, nr, bexp, baug, nullptr, nullptr);
+        DSIR_LAUNCH_CHECK();
+    }
     soft_xtile_kernel<<<dim3(cdiv(pl.Kpad, 256), P.B), 256, 0, st>>>(P.y_soft ? P.xyz_ref : nullptr, P.col_bias, P.K, pl.Kpad, xtile);
     DSIR_LAUNCH_CHECK();
     CUtensorMap mapA, mapB, mapAaug, mapBaug;

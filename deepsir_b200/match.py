@@ -161,12 +161,34 @@ def sinkhorn_implicit(feat_src, feat_ref, xyz_ref, beta, alpha=0.5, n_iters=5, s
     u = torch.zeros(B, J, dtype=torch.float32, device=dev)
     v = torch.zeros(B, K, dtype=torch.float32, device=dev)
     zero = torch.zeros((), dtype=torch.float32, device=dev)
-    for _ in range(n_iters):
-        _, _, lse_r = match_soft(feat_src, feat_ref, None, beta, alpha, col_bias=-v)       # [B,J]
-        u = torch.logaddexp(lse_r, zero) if slack else lse_r
-        _, _, lse_c = match_soft(feat_ref, feat_src, None, beta, alpha, col_bias=-u)       # [B,K]
-        v = torch.logaddexp(lse_c, zero) if slack else lse_c
-    y, _, lse_r = match_soft(feat_src, feat_ref, xyz_ref, beta, alpha, col_bias=-v)
+    lib = L.lib()
+    (fs, _a), (fr, _b) = L.feat_cn(feat_src), L.feat_cn(feat_ref)
+    beta_t = beta.to(torch.float32).contiguous()
+    alpha_t = torch.full((B,), float(alpha), dtype=torch.float32, device=dev) if isinstance(alpha, float) \
+        else alpha.to(torch.float32).contiguous()
+    xyz_c = xyz_ref.contiguous()
+    # one workspace per direction: after its first sweep the norms / tensor-core operands in it are re-used (only the
+    # column bias changes between the half-steps)
+    ws_row = L.workspace(lib.dsir_match_soft_workspace_bytes(B, C, J, K), dev)
+    ws_col = L.workspace(lib.dsir_match_soft_workspace_bytes(B, C, K, J), dev)
+    lse_r = torch.empty(B, J, dtype=torch.float32, device=dev)
+    lse_c = torch.empty(B, K, dtype=torch.float32, device=dev)
+
+    def sweep(row, bias, reuse, y=None):
+        a, b2, n1, n2, ws, out = (fs, fr, J, K, ws_row, lse_r) if row else (fr, fs, K, J, ws_col, lse_c)
+        bias = bias.contiguous()
+        L.check(lib.dsir_match_soft_sweep(a, b2, B, C, n1, n2, beta_t.data_ptr(), alpha_t.data_ptr(), bias.data_ptr(),
+                                          xyz_c.data_ptr() if y is not None else None, L.ptr(y), out.data_ptr(), int(reuse),
+                                          ws.data_ptr(), ws.numel(), L.stream_ptr(dev)), "dsir_match_soft_sweep")
+        return out
+
+    for it in range(n_iters):
+        u = sweep(True, -v, it > 0)                                                          # [B,J]
+        u = torch.logaddexp(u, zero) if slack else u.clone()
+        v = sweep(False, -u, it > 0)                                                         # [B,K]
+        v = torch.logaddexp(v, zero) if slack else v.clone()
+    y = torch.empty(B, J, 3, dtype=torch.float32, device=dev)
+    lse_r = sweep(True, -v, n_iters > 0, y=y)
     return y, torch.exp(lse_r - u), u, v
 
 

@@ -123,6 +123,12 @@ int dsir_match_argmin_filter_trace(const void *ws, size_t ws_bytes, int B, int C
  * workspace from dsir_match_soft_topk_workspace_bytes). */
 size_t dsir_match_soft_workspace_bytes(int B, int C, int J, int K);
 size_t dsir_match_soft_topk_workspace_bytes(int B, int C, int J, int K, int topk);
+/* one sweep of an iteration that calls the fused soft match repeatedly with the SAME features and workspace and only the
+ * column bias changing (the Sinkhorn half-steps of matchnet.py:211-271 in dual form): with reuse_prep != 0 the norms and
+ * the tensor-core operand copies left in `ws` by the previous sweep are used as they are. */
+int dsir_match_soft_sweep(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
+                          const float *col_bias, const float *xyz_ref, float *y_soft, float *lse, int reuse_prep, void *ws,
+                          size_t ws_bytes, dsir_stream_t stream);
 int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
                     const float *col_bias, const float *xyz_ref, float *y_soft, float *lse, int topk,
                     int64_t *topk_idx, float *topk_w, void *ws, size_t ws_bytes, dsir_stream_t stream);

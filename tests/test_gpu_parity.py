@@ -732,3 +732,20 @@ def test_match_soft_tensor_core_edge_shapes(shape, beta):
     assert torch.allclose(y_g.cpu(), y, rtol=SOFT_RTOL, atol=1e-4 * max(1.0, beta / 25))
     T_o, _ = O.compute_rigid_transform(torch.rand(B, J, 3, generator=g), xyz, w)
     assert torch.isfinite(y_g).all() and torch.isfinite(lse_g).all()
+
+
+def test_sinkhorn_implicit_tensor_core_sweeps():
+    """Sinkhorn on the never-materialised affinity with the tcgen05 sweeps (operands prepared once per direction and re-used
+    across the half-steps): equals the reference's sinkhorn() on the materialised matrix."""
+    b = synth.make_batch(2, 1500, 32, "3dmatch", config=3, first_pair=11)
+    fs, fr = b["feat_src"], b["feat_ref"][:, :, :1300].contiguous()
+    xr = b["points_ref"][:, :1300, :3].contiguous()
+    beta, alpha = torch.tensor([10.0, 6.0]), torch.tensor([0.5, 0.4])
+    for slack in (True, False):
+        logp = O.sinkhorn(O.compute_affinity(beta, O.match_features_V2(fs, fr), alpha), 5, slack)     # [B,J,K]
+        P = torch.exp(logp)
+        y, mass, u, v = D.sinkhorn_implicit(cu(fs), cu(fr), cu(xr), cu(beta), cu(alpha), n_iters=5, slack=slack)
+        mass_o = P.sum(dim=2)
+        y_o = (P @ xr) / mass_o[:, :, None]
+        assert torch.allclose(mass.cpu(), mass_o, rtol=5e-4, atol=1e-6)
+        assert torch.allclose(y.cpu(), y_o, rtol=5e-4, atol=2e-4)
