@@ -183,22 +183,16 @@ __device__ __forceinline__ void topk_insert_lex(float (&bd)[KMAX], int (&bi)[KMA
 // costs ~100 compare/select instructions per insertion on the ALU pipe, which bounded the kernel; the heap needs
 // <= log2(k) levels of two loads + two stores and keeps 2k registers free (higher occupancy).  Order is lexicographic
 // (d, idx); the root is the current k-th best and is mirrored in registers.
-#ifndef DSIR_KNN_SORTNET
-#define DSIR_KNN_SORTNET 0
-#endif
-constexpr bool KNN_SORTNET = DSIR_KNN_SORTNET != 0;
-
 template <int KMAX>
 struct SmemHeap {
     float *d;   // [KMAX][128]
     int *i;
     int K;      // heap size (= k)
-    int cnt;    // filled slots; the heap property holds once cnt == K
-    float rd;   // filter: the root (k-th best) once the heap is built, (+inf, max) while it fills
+    float rd;   // root (the current k-th best), mirrored in registers
     int ri;
     __device__ __forceinline__ static bool gt(float da, int ia, float db, int ib) { return da > db || (da == db && ia > ib); }
     __device__ __forceinline__ void init(float *dcol, int *icol, int k) {
-        d = dcol; i = icol; K = k; cnt = 0;
+        d = dcol; i = icol; K = k;
         for (int p = 0; p < k; ++p) { d[p * 128] = INFINITY; i[p * 128] = 0x7fffffff; }
         rd = INFINITY; ri = 0x7fffffff;
     }
@@ -224,14 +218,11 @@ struct SmemHeap {
         for (int p = K / 2 - 1; p >= 0; --p) sift(p, d[p * 128], i[p * 128]);
         rd = d[0]; ri = i[0];
     }
-    // precondition: (x, s) < root.  Replace the root and sift down.  (Filling the first k slots directly and heapifying
-    // once was measured slower: the extra branch splits the warp between lanes that still fill and lanes that sift.)
+    // precondition: (x, s) < root.  Replace the root and sift down.
     __device__ __forceinline__ void replace_root(float x, int s) {
         sift(0, x, s);
         rd = d[0]; ri = i[0];
     }
-    // fewer than k candidates were ever offered (placeholders (+inf, max) fill the rest): make it a heap for pop()
-    __device__ __forceinline__ void finish() {}
     // remove and return the root (largest); heap shrinks by one
     __device__ __forceinline__ void pop(float &od, int &oi) {
         od = d[0]; oi = i[0];
@@ -404,7 +395,7 @@ __global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryPa
     // costs k full-depth sifts, more than half of all sift work of a query; and a tight k-th distance from the start makes
     // the row bound effective at once.  The seeded positions [p0, p0 + k) are skipped by the scan.
     SmemHeap<KMAX> hp;
-    hp.d = s_hd + threadIdx.x; hp.i = s_hi + threadIdx.x; hp.K = P.k; hp.cnt = P.k;
+    hp.d = s_hd + threadIdx.x; hp.i = s_hi + threadIdx.x; hp.K = P.k;
     int p0;
     {
         int pos = t;                                   // self-kNN in cell order: the query is support point t
@@ -508,42 +499,7 @@ __global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryPa
     int64_t *o = P.idx + (size_t)b * P.idx_bs + (size_t)qi * P.k;
     int64_t *o2 = (P.idx2 != nullptr && qi < P.idx2_rows) ? P.idx2 + (size_t)b * P.idx2_bs + (size_t)qi * P.k : nullptr;
     float *od = P.dist2 != nullptr ? P.dist2 + (size_t)b * P.idx_bs + (size_t)qi * P.k : nullptr;
-    if (KMAX <= 16 && KNN_SORTNET) {
-        // the k best, unordered, go to registers and through a bitonic network on (d, idx): cheaper than k heap pops
-        float sd[KMAX];
-        int si[KMAX];
-#pragma unroll
-        for (int p = 0; p < KMAX; ++p) {
-            const bool in = p < P.k;
-            sd[p] = in ? hp.d[p * 128] : INFINITY;
-            si[p] = in ? hp.i[p * 128] : 0x7fffffff;
-        }
-#pragma unroll
-        for (int size = 2; size <= KMAX; size <<= 1) {
-#pragma unroll
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-                for (int t2 = 0; t2 < KMAX / 2; ++t2) {
-                    const int lo = 2 * t2 - (t2 & (stride - 1)), hi = lo + stride;
-                    const bool up = (lo & size) == 0;
-                    const bool sw = SmemHeap<KMAX>::gt(sd[lo], si[lo], sd[hi], si[hi]) == up;
-                    const float td = sw ? sd[hi] : sd[lo], ud = sw ? sd[lo] : sd[hi];
-                    const int ti = sw ? si[hi] : si[lo], ui = sw ? si[lo] : si[hi];
-                    sd[lo] = td; sd[hi] = ud; si[lo] = ti; si[hi] = ui;
-                }
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < KMAX; ++p) {
-            if (p < P.k) {
-                const int64_t v = si[p] == 0x7fffffff ? (int64_t)-1 : (int64_t)si[p];
-                o[p] = v;
-                if (o2) o2[p] = v;
-                if (od) od[p] = sd[p];
-            }
-        }
-    } else {
-        hp.finish();
+    {
         for (int p = P.k - 1; p >= 0; --p) {     // the heap yields the k best in descending order
             float dd;
             int ii;
