@@ -80,6 +80,8 @@ _SIGS = {
     "dsir_match_argmin_workspace_bytes": (_c.c_size_t, [_c.c_int] * 5),
     "dsir_match_argmin": (_c.c_int, [Feat, Feat, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                      _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
+    "dsir_match_argmin_hint": (_c.c_int, [Feat, Feat, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                          _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
     "dsir_match_argmin_rescued_rows": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                                   _c.c_void_p, _c.c_void_p]),
     "dsir_match_argmin_filter_timing": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int,

@@ -429,7 +429,7 @@ size_t dsir_match_argmin_workspace_bytes(int B, int C, int J, int K, int algo) {
 
 // reuse_prep: iterations 2.. of the alignment loop (same features, same workspace): norms / operand copies are kept
 static int match_argmin_impl(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int64_t *idx, float *min_d, void *ws,
-                             size_t ws_bytes, int algo, bool reuse_prep, cudaStream_t st) {
+                             size_t ws_bytes, int algo, bool reuse_prep, cudaStream_t st, const int64_t *prior = nullptr) {
     if (!feat_ok(fs) || !feat_ok(fr) || !idx || B <= 0 || C <= 0 || J <= 0 || K <= 0) return DSIR_ERR_BAD_ARG;
     Workspace W(ws, ws_bytes);
     float *ns = W.take<float>((size_t)B * J);
@@ -438,7 +438,7 @@ static int match_argmin_impl(dsir_feat fs, dsir_feat fr, int B, int C, int J, in
     int rc;
     MatchParams P{};
     P.fs = fs; P.fr = fr; P.B = B; P.C = C; P.J = J; P.K = K; P.ns = ns; P.nr = nr;
-    P.idx = idx; P.min_d = min_d; P.reuse_prep = reuse_prep ? 1 : 0;
+    P.idx = idx; P.min_d = min_d; P.reuse_prep = reuse_prep ? 1 : 0; P.prior_idx = prior;
     bool tc_ok = match_tc_supported(fs, fr, B, C, J, K);
     if (algo == DSIR_MATCH_TC && !tc_ok) return DSIR_ERR_UNSUPPORTED;
     if (algo == DSIR_MATCH_TC || (algo == DSIR_MATCH_AUTO && tc_ok && match_tc_profitable(B, C, J, K))) {
@@ -457,6 +457,11 @@ extern "C" {
 int dsir_match_argmin(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int64_t *idx, float *min_d, void *ws,
                       size_t ws_bytes, int algo, dsir_stream_t stream) {
     return match_argmin_impl(fs, fr, B, C, J, K, idx, min_d, ws, ws_bytes, algo, false, (cudaStream_t)stream);
+}
+
+int dsir_match_argmin_hint(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int64_t *idx, float *min_d,
+                           const int64_t *prior_idx, void *ws, size_t ws_bytes, int algo, dsir_stream_t stream) {
+    return match_argmin_impl(fs, fr, B, C, J, K, idx, min_d, ws, ws_bytes, algo, false, (cudaStream_t)stream, prior_idx);
 }
 
 int dsir_match_argmin_rescued_rows(const void *ws, size_t ws_bytes, int B, int C, int J, int K, int32_t *host_out,
@@ -721,7 +726,9 @@ int dsir_align_loop(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, floa
     for (int it = 0; it < iters; ++it) {
         int64_t *idx = pred_idx ? pred_idx + (size_t)it * B * J : idx_scratch;
         // the features do not change inside this entry point: norms and operand copies are prepared once
-        int rc = match_argmin_impl(fs, fr, B, C, J, K, idx, nullptr, match_ws, match_bytes, algo, it > 0, st);  // :558-569
+        // ... and the previous iteration's correspondences prime the filter (a hint: results do not depend on it)
+        const int64_t *prior = it > 0 ? (pred_idx ? pred_idx + (size_t)(it - 1) * B * J : idx_scratch) : nullptr;
+        int rc = match_argmin_impl(fs, fr, B, C, J, K, idx, nullptr, match_ws, match_bytes, algo, it > 0, st, prior);  // :558-569
         if (rc) return rc;
         double *partials; int nblk;
         rc = kabsch_common(src, ref, weights, J, idx, B, J, &partials, &nblk, kab_ws, kab_bytes, st);    // :571,:588

@@ -19,6 +19,8 @@ struct MatchParams {
     // the caller guarantees that features and workspace are those of its previous call (iterations 2.. of the alignment
     // loop): norms, maxima and the tensor-core operand copies in the workspace are still valid and are not recomputed
     int reuse_prep;
+    // optional [B,J] correspondences of the previous iteration (argmin only): a hint that tightens the filter, never changes the result
+    const int64_t *prior_idx;
 };
 
 enum { MATCH_MODE_ARGMIN = 0, MATCH_MODE_DENSE = 1, MATCH_MODE_SOFT = 2 };

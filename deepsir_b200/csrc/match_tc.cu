@@ -319,6 +319,11 @@ struct TcParams {
     float *cand_val;        // [B][Jpad][S][T]  (scaled units)
     int *cand_idx;
     int prime_div;            // priming pass over every prime_div-th unit (0 = none)
+    // optional prior correspondences [B,J] (the previous iteration of the alignment loop): the distance to the prior match
+    // bounds the row minimum, so no priming pass is needed
+    const int64_t *prior;
+    const __half *a16, *b16;  // tensor-core copies [B][J][64], [B][K][64]
+    const float *nr;          // [B,K] exact squared norms
     int dbg_flags;            // experiments only (DSIR_TC_DEBUG): bit 0 = never take the slow path (wrong results)
     unsigned int *trace;      // DSIR_TC_DEBUG bit 1: block 0 logs clock stamps of its first 256 units (see match_tc_filter_trace)
     unsigned long long *dbg;  // [grid][4]: start ns, end ns, cycles, units (diagnostic, always written)
@@ -458,6 +463,29 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
             float thr = dead ? -INFINITY : INFINITY;
             const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
             const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C);
+            if (P.prior != nullptr && !dead) {
+                // x of the prior match from the same fp16 operands the tensor core sees (fp32 accumulation in another
+                // order: within eps <= margin / 2 of the accumulator value) -> an upper bound of the row minimum
+                const long long kp = P.prior[(size_t)b * P.J + j];
+                if (kp >= 0 && kp < P.K) {
+                    const uint4 *pa = reinterpret_cast<const uint4 *>(P.a16 + ((size_t)b * P.J + j) * TC_CH);
+                    const uint4 *pb = reinterpret_cast<const uint4 *>(P.b16 + ((size_t)b * P.K + kp) * TC_CH);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int v8 = 0; v8 < TC_CH / 8; ++v8) {
+                        const uint4 ua = pa[v8], ub = pb[v8];
+                        const __half2 *ha = reinterpret_cast<const __half2 *>(&ua), *hb = reinterpret_cast<const __half2 *>(&ub);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
+                            acc = __fmaf_rn(fa.x, fb.x, acc);
+                            acc = __fmaf_rn(fa.y, fb.y, acc);
+                        }
+                    }
+                    const float sg = P.scale[b];
+                    thr = __fmaf_rn(P.nr[(size_t)b * P.K + kp], sg * sg, acc) + 1.5f * margin;
+                }
+            }
             for (int t = 0; t < us.total(); ++t) {
                 const int u = us.unit(t);
                 const bool sample = t < us.ns;
@@ -872,6 +900,8 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     T.trace = (unsigned int *)(base + pl.off_trace);
     { const char *e = getenv("DSIR_TC_DEBUG"); T.dbg_flags = e ? atoi(e) : 0; }
     { const char *e = getenv("DSIR_TC_PRIME"); T.prime_div = e ? atoi(e) : 8; }
+    T.prior = P.prior_idx; T.a16 = a16; T.b16 = b16; T.nr = P.nr;
+    if (T.prior) T.prime_div = 0;
     const int items = P.B * pl.RB * pl.S;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

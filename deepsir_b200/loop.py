@@ -37,7 +37,7 @@ def align_loop(feat_src, feat_ref, xyz_src, xyz_ref, weights, num_iter, feature_
     transforms, preds, stats = [], [], []
     for it in range(num_iter):
         fs = feature_fn(xyz_src) if feature_fn is not None else feat_src
-        idx = M.match_argmin(fs, feat_ref, algo=algo)                               # :558-569
+        idx = M.match_argmin(fs, feat_ref, algo=algo, prior=preds[-1] if preds else None)   # :558-569 (hinted by the last match)
         if weight_fn is not None:
             w = weight_fn(xyz_src, M.gather_neighbour_V3(xyz_ref, idx))             # :571-577
         else:

@@ -84,9 +84,11 @@ def feat_dist(feat_src, feat_ref, metric="sqeuclidean"):
     return _dense(fs, fr, feat_src.shape[0], feat_src.shape[1], feat_src.shape[2], feat_ref.shape[2], code, (a, b), dev)
 
 
-def match_argmin(feat_src, feat_ref, return_min=False, algo=L.MATCH_AUTO, return_rescued=False, timing=None):
+def match_argmin(feat_src, feat_ref, return_min=False, algo=L.MATCH_AUTO, return_rescued=False, timing=None, prior=None):
     """The fused replacement of network/model.py:558-569 (chunked match_features_V2 + .min(dim=2)[1]):
-    feat_src [B,C,J], feat_ref [B,C,K] -> indexs int64 [B,J]; the [J,K] matrix is never written."""
+    feat_src [B,C,J], feat_ref [B,C,K] -> indexs int64 [B,J]; the [J,K] matrix is never written.
+    prior: optional int64 [B,J] correspondences of the previous loop iteration - a hint that speeds the filter up and
+    never changes the result."""
     assert feat_src.shape[1] == feat_ref.shape[1]
     dev = L.require_cuda(feat_src, feat_ref)
     B, C, J = feat_src.shape
@@ -96,8 +98,11 @@ def match_argmin(feat_src, feat_ref, return_min=False, algo=L.MATCH_AUTO, return
     mind = torch.empty(B, J, dtype=torch.float32, device=dev) if return_min else None
     lib = L.lib()
     ws = L.workspace(lib.dsir_match_argmin_workspace_bytes(B, C, J, K, algo), dev)
-    L.check(lib.dsir_match_argmin(fs, fr, B, C, J, K, idx.data_ptr(), L.ptr(mind), ws.data_ptr(), ws.numel(), algo,
-                                  L.stream_ptr(dev)), "dsir_match_argmin")
+    if prior is not None:
+        prior = prior.to(torch.int64).contiguous()
+        assert prior.shape == (B, J)
+    L.check(lib.dsir_match_argmin_hint(fs, fr, B, C, J, K, idx.data_ptr(), L.ptr(mind), L.ptr(prior), ws.data_ptr(), ws.numel(),
+                                       algo, L.stream_ptr(dev)), "dsir_match_argmin")
     if timing is not None:  # diagnostic: device-side span/cycles of the tcgen05 filter kernel; forces a stream sync
         import ctypes
         t = (ctypes.c_double * 3)()

@@ -97,6 +97,11 @@ int dsir_match_dense(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int
 size_t dsir_match_argmin_workspace_bytes(int B, int C, int J, int K, int algo);
 int dsir_match_argmin(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int64_t *idx, float *min_d, void *ws,
                       size_t ws_bytes, int algo, dsir_stream_t stream);
+/* the same with a HINT: prior_idx [B,J] int64 (may be NULL, may alias idx) = correspondences of a previous iteration of the
+ * loop (network/model.py:551-601).  The distance to the prior match bounds the row minimum from the start, which spares the
+ * filter its priming pass and most of its candidate updates; the result never depends on the hint. */
+int dsir_match_argmin_hint(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, int64_t *idx, float *min_d,
+                           const int64_t *prior_idx, void *ws, size_t ws_bytes, int algo, dsir_stream_t stream);
 
 /* diagnostic for the tcgen05 path (synchronises `stream`): rows of the LAST dsir_match_argmin call on this workspace
  * whose candidate list saturated and were recomputed exhaustively in fp32.  host_out is a HOST int32. */

@@ -749,3 +749,21 @@ def test_sinkhorn_implicit_tensor_core_sweeps():
         y_o = (P @ xr) / mass_o[:, :, None]
         assert torch.allclose(mass.cpu(), mass_o, rtol=5e-4, atol=1e-6)
         assert torch.allclose(y.cpu(), y_o, rtol=5e-4, atol=2e-4)
+
+
+def test_match_argmin_hint_never_changes_the_result():
+    """dsir_match_argmin_hint: a correct, a partly wrong, a random and an out-of-range prior all give the indices of the
+    unhinted call (the hint only tightens the filter)."""
+    b = synth.make_batch(2, 6000, 64, "kitti", config=2, first_pair=31)
+    fs, fr = cu(b["feat_src"]), cu(b["feat_ref"])
+    base, dmin = D.match_argmin(fs, fr, return_min=True, algo=D.MATCH_TC)
+    g = torch.Generator().manual_seed(4)
+    wrong = base.clone()
+    wrong[:, ::3] = cu(torch.randint(0, 6000, (2, 2000), generator=g))
+    for prior in (base, wrong, cu(torch.randint(0, 6000, (2, 6000), generator=g)), torch.full_like(base, -1), torch.full_like(base, 10**6)):
+        idx, dm = D.match_argmin(fs, fr, return_min=True, algo=D.MATCH_TC, prior=prior)
+        assert torch.equal(idx, base) and torch.equal(dm, dmin)
+    rnd_s, rnd_r = cu(synth.random_features(1, 64, 3000, 5)), cu(synth.random_features(1, 64, 3000, 6))   # small top-2 gaps
+    base = D.match_argmin(rnd_s, rnd_r, algo=D.MATCH_TC)
+    assert torch.equal(D.match_argmin(rnd_s, rnd_r, algo=D.MATCH_TC, prior=base), base)
+    assert torch.equal(D.match_argmin(rnd_s, rnd_r, algo=D.MATCH_TC, prior=torch.zeros_like(base)), base)
