@@ -255,7 +255,7 @@ __device__ __forceinline__ void release_acc(uint64_t *empty_bar, int lane) {
 template <bool LAST>
 __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint32_t taddr, float margin, float &thr,
                                          float (&cv)[TC_T], int (&ci)[TC_T], bool sample, float &best,
-                                         uint64_t *empty_bar = nullptr, int lane = 0, int dbg = 0) {
+                                         uint64_t *empty_bar = nullptr, int lane = 0) {
 #define F(i) __uint_as_float(v[i])
     const float a0 = fmin3(F(0), F(1), F(2)), a1 = fmin3(F(3), F(4), F(5)), a2 = fmin3(F(6), F(7), F(8));
     const float a3 = fmin3(F(9), F(10), F(11)), a4 = fmin3(F(12), F(13), F(14)), a5 = fmin3(F(15), F(16), F(17));
@@ -277,14 +277,13 @@ __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint
             qm |= (fminf(fmin3(F(4 * g), F(4 * g + 1), F(4 * g + 2)), F(4 * g + 3)) < thr) ? (1u << g) : 0u;
 #undef F
         unsigned um = __reduce_or_sync(0xffffffffu, qm);
-        if (dbg & 8) um = 0;           // experiment: locate only
 #pragma unroll 1
         while (um) {
             const int g = __ffs(um) - 1;
             um &= um - 1;
             float x[4];
             tmem_ld4_sync(taddr + 4 * g, x);   // bit-identical to v[4g .. 4g+3]
-            if (((qm >> g) & 1u) && !(dbg & 16)) {   // experiment bit 4: re-read only
+            if ((qm >> g) & 1u) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
                     if (x[e] < thr) cand_update(cv, ci, x[e], col0 + 4 * g + e, margin, thr);
@@ -502,16 +501,16 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                     tmem_wait32(va);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 1] = (unsigned int)clock64();
                     tmem_ld32(tbase + (g + 1) * 32, vb);
-                    filter32<false>(va, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci, sample, best, nullptr, 0, P.dbg_flags);
+                    filter32<false>(va, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci, sample, best);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 2] = (unsigned int)clock64();
                     tmem_wait32(vb);
                     if (g + 2 < TC_STEPS) tmem_ld32(tbase + (g + 2) * 32, va);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 3] = (unsigned int)clock64();
                     if (g + 2 < TC_STEPS)
-                        filter32<false>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best, nullptr, 0, P.dbg_flags);
+                        filter32<false>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best);
                     else   // last step: the accumulator is handed back from inside (right after the vote)
                         filter32<true>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best,
-                                       &tmem_empty[pa.stage * TC_RBS + r], lane, P.dbg_flags);
+                                       &tmem_empty[pa.stage * TC_RBS + r], lane);
                 }
                 if (tracing && useq < 256) P.trace[1024 + useq * 8 + 4] = (unsigned int)clock64();
                 if (t == us.ns - 1 && !dead) thr = best + margin;   // primed: every row has seen a value <= best
