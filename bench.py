@@ -159,6 +159,20 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # one process per GPU: keep the rank (and the pinned host buffers it is about to allocate: first touch) on the CPUs /
+        # NUMA node closest to its GPU, otherwise eight uploads fight over one socket's memory and root complex
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = [64 * w + bit for w, m in enumerate(words) for bit in range(64) if (m >> bit) & 1]
+            allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+        except Exception:
+            pass
+    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     assert D.lib().dsir_device_check() == 0
