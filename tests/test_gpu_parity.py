@@ -767,3 +767,29 @@ def test_match_argmin_hint_never_changes_the_result():
     base = D.match_argmin(rnd_s, rnd_r, algo=D.MATCH_TC)
     assert torch.equal(D.match_argmin(rnd_s, rnd_r, algo=D.MATCH_TC, prior=base), base)
     assert torch.equal(D.match_argmin(rnd_s, rnd_r, algo=D.MATCH_TC, prior=torch.zeros_like(base)), base)
+
+
+def test_c_abi_error_codes_on_device():
+    """The C ABI never throws: bad arguments, unsupported shapes and short workspaces come back as negative codes with a
+    message (dsir_strerror), and the mirror turns them into DeepSIRError."""
+    import ctypes
+    from deepsir_b200 import _lib as L
+    lib = D.lib()
+    fs, fr = cu(synth.random_features(1, 64, 700, 1)), cu(synth.random_features(1, 64, 600, 2))
+    (a, _k1), (b, _k2) = L.feat_cn(fs), L.feat_cn(fr)
+    idx = torch.empty(1, 700, dtype=torch.int64, device=DEV)
+    st = L.stream_ptr(torch.device(DEV))
+    ws = L.workspace(lib.dsir_match_argmin_workspace_bytes(1, 64, 700, 600, D.MATCH_TC), torch.device(DEV))
+    assert lib.dsir_match_argmin(a, b, 1, 64, 700, 600, None, None, ws.data_ptr(), ws.numel(), D.MATCH_TC, st) == -1      # null output
+    assert lib.dsir_match_argmin(a, b, 1, 64, 700, 600, idx.data_ptr(), None, ws.data_ptr(), 64, D.MATCH_TC, st) == -3   # workspace
+    assert lib.dsir_match_argmin(a, b, 1, 100, 700, 600, idx.data_ptr(), None, ws.data_ptr(), ws.numel(), D.MATCH_TC, st) == -2  # C > 64 on the tensor path
+    assert b"workspace" in lib.dsir_strerror(-3)
+    pts = cu(torch.rand(1, 10, 3))
+    with pytest.raises(D.DeepSIRError):
+        D.knn(pts, pts, 16)                                                       # fewer support points than k
+    with pytest.raises(D.DeepSIRError):
+        D.match_soft(fs, fr, cu(torch.rand(1, 600, 3)), cu(torch.tensor([10.0])), 0.5, topk=33)   # top-k > 32
+    with pytest.raises(D.DeepSIRError):
+        D.topk(cu(torch.rand(2, 50)), 51)                                          # k > N
+    assert lib.dsir_match_argmin(a, b, 1, 64, 700, 600, idx.data_ptr(), None, ws.data_ptr(), ws.numel(), D.MATCH_TC, st) == 0   # still usable
+    torch.cuda.synchronize()
