@@ -345,7 +345,7 @@ def main():
                             "frac": knn_bytes / (knn_ms / 1e3) / 1e9 / pk["hbm"], "ms_per_step": knn_ms,
                             "note": "HBM-bound by the scan/graph rule, but latency/instruction bound in practice "
                                     "(brute-force equivalent: 5.73 GFLOP per pair)"}}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU port is timed beside the N=1 run only
         torch.set_num_threads(os.cpu_count() or 1)
         n_pairs = 1
         cpu_step(host, n_pairs)                                    # warm (builds/loads the oracle lib, MKL init)
