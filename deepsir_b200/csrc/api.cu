@@ -183,7 +183,7 @@ float env_float(const char *name, float dflt) {
     const char *v = getenv(name);
     return v ? (float)atof(v) : dflt;
 }
-const float GRID_CELLS_PER_POINT = env_float("DSIR_GRID_CPP", 1.0f);
+const float GRID_CELLS_PER_POINT = env_float("DSIR_GRID_CPP", 0.7f);
 const float GRID_R0_CELLS = env_float("DSIR_GRID_R0", 1.0f);
 
 }  // namespace
