@@ -463,8 +463,10 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
             const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
             const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C);
             if (P.prior != nullptr && !dead) {
-                // x of the prior match from the same fp16 operands the tensor core sees (fp32 accumulation in another
-                // order: within eps <= margin / 2 of the accumulator value) -> an upper bound of the row minimum
+                // x of the prior match from the same fp16 operands the tensor core sees.  The two fp32 accumulations (80
+                // products each, different order) differ by less than the accumulation term of eps plus a quarter of it,
+                // i.e. by less than margin = 2.04 eps: x' + margin bounds the accumulator value of that column, hence the
+                // row minimum, from above, and everything within margin of the minimum is below x' + 2 margin.
                 const long long kp = P.prior[(size_t)b * P.J + j];
                 if (kp >= 0 && kp < P.K) {
                     const uint4 *pa = reinterpret_cast<const uint4 *>(P.a16 + ((size_t)b * P.J + j) * TC_CH);
@@ -482,7 +484,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                         }
                     }
                     const float sg = P.scale[b];
-                    thr = __fmaf_rn(P.nr[(size_t)b * P.K + kp], sg * sg, acc) + 1.5f * margin;
+                    thr = __fmaf_rn(P.nr[(size_t)b * P.K + kp], sg * sg, acc) + 2.0f * margin;
                 }
             }
             for (int t = 0; t < us.total(); ++t) {
