@@ -1,0 +1,60 @@
+"""Row-block sharding of one pair over 2 GPUs with NCCL: needs two devices, skipped otherwise.  The exchange
+logic itself is also covered on CPU with gloo (tests/test_dist_cpu.py)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    import deepsir_b200 as D
+    from deepsir_b200 import dist as DD, synth
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        N = 6000
+        b = synth.make_batch(2, N, 64, "kitti", config=4, first_pair=17)          # the same pairs on every rank
+        lo, hi = DD.row_block(N, world, rank)
+        xs = b["points_src"][:, :, :3].permute(0, 2, 1).contiguous()
+        xr = b["points_ref"][:, :, :3].permute(0, 2, 1).contiguous().to(dev)
+        fr = b["feat_ref"].to(dev)
+        w = b["weights"][:, :, 0].contiguous()
+        tr, pred, xyz, st = DD.align_rowblock(b["feat_src"][:, :, lo:hi].contiguous().to(dev), fr, xs[:, :, lo:hi].contiguous().to(dev),
+                                             xr, w[:, lo:hi].contiguous().to(dev), 3, gather_pred_rows=N)
+        T = torch.stack(tr)
+        ref = T.clone()
+        dist.broadcast(ref, 0)
+        same = torch.equal(ref, T)                                                 # every rank solves the same pose
+        if rank == 0:
+            tr1, pred1, _, _ = D.align_loop(b["feat_src"].to(dev), fr, xs.to(dev), xr, w.to(dev), 3)   # unsharded, one GPU
+            out.put(dict(T=T.cpu(), T1=torch.stack(tr1).cpu(), pred=torch.stack(pred).cpu(), pred1=torch.stack(pred1).cpu(), same=same))
+        else:
+            out.put(dict(same=same))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_rowblock_sharding_two_gpus_nccl():
+    import torch.multiprocessing as mp
+    from oracle import deepsir_oracle as O
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r["same"] for r in res)
+    r0 = next(r for r in res if "T" in r)
+    assert torch.equal(r0["pred"], r0["pred1"])                                    # gathered correspondences == unsharded
+    assert O.rotation_angle_deg(r0["T"][-1][:, :, :3], r0["T1"][-1][:, :, :3]).max() < 1e-3
+    assert (r0["T"][-1][:, :, 3] - r0["T1"][-1][:, :, 3]).abs().max() < 1e-4
