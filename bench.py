@@ -343,8 +343,9 @@ def main():
            "roofline_knn": {"bound": "hbm", "kernel": "knn pyramid (grid build + queries, both clouds of a step)",
                             "achieved": knn_bytes / (knn_ms / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                             "frac": knn_bytes / (knn_ms / 1e3) / 1e9 / pk["hbm"], "ms_per_step": knn_ms,
-                            "note": "HBM-bound by the scan/graph rule, but latency/instruction bound in practice "
-                                    "(brute-force equivalent: 5.73 GFLOP per pair)"}}
+                            "note": "HBM-bound by the scan/graph rule, but instruction bound in practice: ncu on the level-0 "
+                                    "query kernel shows issue slots 74 % busy, DRAM 1.5 % (profiles/ncu_digest_knn_r1f.txt); "
+                                    "brute-force equivalent: 5.73 GFLOP per pair"}}
     if not args.no_cpu_baseline and world == 1:      # the CPU port is timed beside the N=1 run only
         torch.set_num_threads(os.cpu_count() or 1)
         n_pairs = 1
