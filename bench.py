@@ -335,7 +335,7 @@ def main():
                                        "device resident; iterations 2-5 hint the match filter with the previous correspondences"},
            "roofline": {"bound": "tensor", "kernel": "match_tc_filter_kernel (tcgen05 fp16 distance + row-argmin filter)",
                         "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
-                        "traffic": 169.48e6,   # dram read+write per launch, ncu --set full (profiles/ncu_digest_filter_r1f.txt)
+                        "traffic": 167.13e6,   # dram read+write per launch, ncu --set full (profiles/ncu_digest_filter_r1f.txt)
                         "peak_source": f"{pk['src']} bf16_tflops_sustained (16-bit tensor-core inputs, fp32 accumulate; "
                                        "kernel timed inside the step by CUDA events on its stream)",
                         "ms_per_launch": filter_ms, "match_call_ms": match_ms,
@@ -344,7 +344,7 @@ def main():
                             "achieved": knn_bytes / (knn_ms / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                             "frac": knn_bytes / (knn_ms / 1e3) / 1e9 / pk["hbm"], "ms_per_step": knn_ms,
                             "note": "HBM-bound by the scan/graph rule, but instruction bound in practice: ncu on the level-0 "
-                                    "query kernel shows issue slots 74 % busy, DRAM 1.5 % (profiles/ncu_digest_knn_r1f.txt); "
+                                    "query kernel shows issue slots 76 % busy, DRAM 1.8 % (profiles/ncu_digest_knn_r1f.txt); "
                                     "brute-force equivalent: 5.73 GFLOP per pair"}}
     if not args.no_cpu_baseline and world == 1:      # the CPU port is timed beside the N=1 run only
         torch.set_num_threads(os.cpu_count() or 1)
