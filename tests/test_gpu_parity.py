@@ -793,3 +793,22 @@ def test_c_abi_error_codes_on_device():
         D.topk(cu(torch.rand(2, 50)), 51)                                          # k > N
     assert lib.dsir_match_argmin(a, b, 1, 64, 700, 600, idx.data_ptr(), None, ws.data_ptr(), ws.numel(), D.MATCH_TC, st) == 0   # still usable
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1), (1, 3, 1, 500), (2, 64, 300, 1), (3, 5, 129, 127), (1, 64, 513, 129), (70, 16, 40, 33)])
+def test_degenerate_sizes_all_paths(shape):
+    """One row, one column, one channel, sizes one off the tile edges, many tiny pairs; un-normalised features; both argmin
+    algorithms and the soft path."""
+    B, C, J, K = shape
+    g = torch.Generator().manual_seed(J * 1000 + K)
+    fs, fr = torch.randn(B, C, J, generator=g), torch.randn(B, C, K, generator=g)
+    d = O.match_features_V2(fs, fr)
+    ref = O.match_argmin(fs, fr)
+    for algo in (D.MATCH_FP32, D.MATCH_TC):
+        idx = D.match_argmin(cu(fs), cu(fr), algo=algo).cpu()
+        assert torch.allclose(torch.gather(d, 2, idx[:, :, None]), torch.gather(d, 2, ref[:, :, None]), atol=1e-5)
+    xyz = torch.rand(B, K, 3, generator=g)
+    beta = torch.full((B,), 2.0)
+    y, s, lse = D.match_soft(cu(fs), cu(fr), cu(xyz), cu(beta), 0.5)
+    w, yo, so, lo = O.soft_correspondence(fs, fr, xyz, beta, 0.5)
+    assert torch.allclose(lse.cpu(), lo, rtol=SOFT_RTOL, atol=1e-5) and torch.allclose(y.cpu(), yo, rtol=SOFT_RTOL, atol=1e-4)
