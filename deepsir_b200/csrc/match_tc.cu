@@ -35,6 +35,7 @@
 #include <cstdlib>
 
 #include "match_tc.cuh"
+#include "tc_common.cuh"
 
 namespace dsir {
 
@@ -66,98 +67,6 @@ constexpr float TC_PAD_NORM = 60000.0f;       // folded norm of padded reference
 constexpr uint32_t MAIN_TILE = 128 * TC_CH * 2;   // 16 KB: 128 rows x 64 halves, 128-byte swizzle
 constexpr uint32_t AUG_TILE = 128 * TC_AUG * 2;   //  4 KB: 128 rows x 16 halves, 32-byte swizzle
 
-// ---------------------------------------------------------------------------------------------------------
-// driver entry point for tensor-map encoding (no libcuda link dependency)
-// ---------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
-// [B][N][W] fp16, box = W channels x 128 rows; rows/batches beyond the extent read as zero
-bool make_half_tmap(CUtensorMap *m, const __half *base, int B, int N, int W, CUtensorMapSwizzle swz) {
-    EncodeTiledFn enc = get_encode_fn();
-    if (!enc) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)N, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)W * 2, (cuuint64_t)N * W * 2};
-    cuuint32_t box[3] = {(cuuint32_t)W, 128, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// tcgen05.mma / tcgen05.commit are executed by ONE elected lane, but the whole warp runs the surrounding (uniform) control
-// flow, so descriptors and addresses stay warp-uniform and the compiler needs no per-instruction election loop.
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile(
-        "{\n\t.reg .pred pe;\n\t"
-        "elect.sync _|pe, 0xffffffff;\n\t"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate
-__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, pe;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "elect.sync _|pe, 0xffffffff;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-// the wait names the destination registers so that no consumer can be scheduled above it
-__device__ __forceinline__ void tmem_wait32(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-}
 __device__ __forceinline__ float fmin3(float a, float b, float c) {   // FMNMX3 (sm_100+)
     float d;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -169,27 +78,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-// K-major shared-memory matrix descriptors (sm_100): 8-row groups `sbo` bytes apart, LBO unused (=1)
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo, uint32_t layout) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;             // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(sbo >> 4) << 32;    // stride byte offset
-    d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
-    d |= (uint64_t)layout << 61;        // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
-    return d;
-}
-
 // instruction descriptor: D=f32, A=B=f16, both K-major, N=128, M=128
 constexpr uint32_t TC_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
-struct PipeState {
-    int stage;
-    uint32_t phase;
-    __device__ __forceinline__ void advance(int n) {
-        if (++stage == n) { stage = 0; phase ^= 1u; }
-    }
-};
 
 // Bound on |x_hat_jk - x_jk| in scaled units, x = sigma^2 (|r|^2 - 2<s,r>), for fp16-rounded operands with fp32
 // accumulation; a = sigma |s_j|, R = sigma max_k |r_k| (both <= 1):
@@ -542,14 +432,6 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
     }
 }
 
-// sigma_b = 2^-e with 2^e > sqrt(max squared norm of the batch) (1 when the maximum is 0 or not finite)
-__device__ __forceinline__ float tc_sigma(float amax) {
-    if (!(amax > 0.f) || !(amax < INFINITY)) return 1.f;
-    int e = ilogbf(sqrtf(amax)) + 1;
-    e = e < -60 ? -60 : (e > 60 ? 60 : e);
-    return exp2f((float)-e);
-}
-
 // prep: [B,C,N] fp32 (any strides) -> fp16 tensor-core copy [B][N][64] = mul * sigma * f (point-major, channels C..63
 // zero), and for the reference side the folded-norm channels [B][Npad][16] = {hi, lo, lolo, 0..} of sigma^2 |r|^2
 // (TC_PAD_NORM beyond N).  One block = 32 points x 64 channels through a shared-memory transpose.  Block (0,0) also
@@ -851,7 +733,7 @@ bool match_tc_supported(const dsir_feat &fs, const dsir_feat &fr, int B, int C, 
     (void)fs; (void)fr;
     if (C < 1 || C > TC_CH) return false;
     if ((long long)B * J >= (1ll << 31) || (long long)B * K >= (1ll << 31)) return false;
-    return get_encode_fn() != nullptr;
+    return tc_encode_fn() != nullptr;
 }
 
 bool match_tc_profitable(int B, int C, int J, int K) {
@@ -888,10 +770,10 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
         DSIR_LAUNCH_CHECK();
     }
     CUtensorMap mapA, mapB, mapAaug, mapBaug;
-    if (!make_half_tmap(&mapA, a16, P.B, P.J, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_half_tmap(&mapB, b16, P.B, P.K, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_half_tmap(&mapAaug, aaug, 1, 128, TC_AUG, CU_TENSOR_MAP_SWIZZLE_32B) ||
-        !make_half_tmap(&mapBaug, baug, P.B, pl.Kpad, TC_AUG, CU_TENSOR_MAP_SWIZZLE_32B))
+    if (!make_f16_tmap(&mapA, a16, P.B, P.J, TC_CH, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_f16_tmap(&mapB, b16, P.B, P.K, TC_CH, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_f16_tmap(&mapAaug, aaug, 1, 128, TC_AUG, TC_AUG, CU_TENSOR_MAP_SWIZZLE_32B) ||
+        !make_f16_tmap(&mapBaug, baug, P.B, pl.Kpad, TC_AUG, TC_AUG, CU_TENSOR_MAP_SWIZZLE_32B))
         return DSIR_ERR_UNSUPPORTED;
 
     TcParams T{};

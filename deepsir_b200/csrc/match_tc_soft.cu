@@ -22,12 +22,10 @@
 //                t_e = -beta' (x_e + |s|^2 - alpha) (+ bias), step maximum, ONE rescale of the running state, then
 //                p_e = 2^(t_e - m) (MUFU.EX2) accumulated into the sum and the three weighted coordinates (FFMA2).
 // Partial states of the K-splits are merged by a small finalize kernel.
-#include <cuda.h>
-#include <cuda_fp16.h>
-
 #include <cstdlib>
 
 #include "match_tc.cuh"
+#include "tc_common.cuh"
 
 namespace dsir {
 
@@ -59,81 +57,6 @@ constexpr uint32_t SF_XT = 128 * 16;                         //  per unit: (x, y
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 static_assert(SF_RBS * SF_ACC * 128 == 512 && SF_HALVES == 1 && SF_RBS % SF_MMA_WARPS == 0, "TMEM / warp budget");
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn soft_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-// [B][N][W] fp16, box = bw channels x 128 rows; rows/batches beyond the extent read as zero
-bool make_f16_tmap(CUtensorMap *m, const __half *base, int B, int N, int W, int bw, CUtensorMapSwizzle swz) {
-    EncodeTiledFn enc = soft_encode_fn();
-    if (!enc) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)N, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)W * 2, (cuuint64_t)N * W * 2};
-    cuuint32_t box[3] = {(cuuint32_t)bw, 128, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile(
-        "{\n\t.reg .pred pe;\n\t"
-        "elect.sync _|pe, 0xffffffff;\n\t"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, pe;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "elect.sync _|pe, 0xffffffff;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :
-                 : "memory");
-}
 // explicit shared-space loads (the generic pointer arithmetic on the dynamic smem base would compile to generic LD)
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
@@ -167,25 +90,8 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo, uint32_t layout) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(sbo >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout << 61;        // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
-    return d;
-}
 // D = f32, A = B = f16, both K-major, N = 128, M = 128
 constexpr uint32_t SF_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(SF_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
-struct Pipe {
-    int stage;
-    uint32_t phase;
-    __device__ __forceinline__ void advance(int n) {
-        if (++stage == n) { stage = 0; phase ^= 1u; }
-    }
-};
 
 struct SoftParams {
     int B, J, K, C;
@@ -305,7 +211,7 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
     if (warp == SF_WARP_TMA) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
-            Pipe pb{0, 0}, px{0, 0};
+            PipeState pb{0, 0}, px{0, 0};
             uint32_t iphase = 0;
             bool first = true;
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
@@ -339,7 +245,7 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
     } else if (warp >= SF_WARP_MMA0 && warp < SF_WARP_MMA0 + SF_MMA_WARPS) {
         // =========================== MMA issuer (row blocks w, w + 2) ===========================
         const int w = warp - SF_WARP_MMA0;
-        Pipe pb{0, 0};
+        PipeState pb{0, 0};
         uint32_t iphase = 0, aphase = 0;
         const uint64_t descA0 = make_kmajor_desc(smem_u32(sA), 1024, 2);
         const uint64_t descB0 = make_kmajor_desc(smem_u32(sB), 1024, 2);
@@ -382,7 +288,7 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
         // =========================== epilogue: online softmax over the row ===========================
         const int q = warp & 3, r = warp >> 2;
         const int trow = q * 32 + lane;
-        Pipe px{0, 0};
+        PipeState px{0, 0};
         uint32_t aphase = 0;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
@@ -469,14 +375,6 @@ __global__ void soft_finalize_kernel(const float *__restrict__ part, int B, int 
     }
 }
 
-// sigma_b = 2^-e with 2^e > sqrt(max squared norm of the batch) (1 when the maximum is 0 or not finite)
-__device__ __forceinline__ float soft_sigma(float amax) {
-    if (!(amax > 0.f) || !(amax < INFINITY)) return 1.f;
-    int e = ilogbf(sqrtf(amax)) + 1;
-    e = e < -60 ? -60 : (e > 60 ? 60 : e);
-    return exp2f((float)-e);
-}
-
 // [B,C,N] fp32 (any strides) -> fp16 [B][N][2 CMAX] = hi(CMAX) | lo(CMAX) of  mul * sigma * f  (mul = -2 on the reference side,
 // exact), and for the reference side the folded-norm tile [B][Npad][16] = three-term fp16 split of sigma^2 |r|^2.
 // One block = 32 points; thread = (point, group of 4 channels).  Block (0,0) also writes the constant source-side norm
@@ -489,7 +387,7 @@ __global__ __launch_bounds__(256) void soft_prep_kernel(dsir_feat f, int C, int 
     __shared__ float tile[CMAX][33];
     const int b = blockIdx.y, n0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const float sigma = soft_sigma(amax[b]);
+    const float sigma = tc_sigma(amax[b]);
     const float *src = f.ptr + (size_t)b * f.batch_stride;
     for (int c = ty; c < CMAX; c += 8) {
         const int n = n0 + tx;
@@ -598,7 +496,7 @@ bool match_tc_soft_supported(int B, int C, int J, int K) {
     static const bool off = getenv("DSIR_SOFT_FP32") != nullptr;
     if (off) return false;
     if ((double)B * J * K < 2.0e6) return false;   // tiny problems: the prep launches dominate
-    return soft_encode_fn() != nullptr;
+    return tc_encode_fn() != nullptr;
 }
 
 size_t match_tc_soft_workspace_bytes(int B, int C, int J, int K) {
