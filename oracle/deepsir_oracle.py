@@ -337,12 +337,14 @@ def _kabsch_from_cov(cov, c_src, c_tgt, keep_double):
     v_neg[:, :, 2] *= -1
     r_neg = v_neg @ u.transpose(-1, -2)
     R = torch.where(torch.det(r_pos)[:, None, None] > 0, r_pos, r_neg)
+    dev = c_src.device
+    c_src, c_tgt = c_src.cpu(), c_tgt.cpu()        # :57 / :107: the solve stays on the host, the pose goes back to the device
     if not keep_double:
         R = R.float()
         t = -R @ c_src[:, :, None] + c_tgt[:, :, None]
     else:
         t = -R @ c_src.double()[:, :, None] + c_tgt.double()[:, :, None]
-    return torch.cat((R, t), dim=2).float(), s
+    return torch.cat((R, t), dim=2).float().to(dev), s
 
 
 def compute_rigid_transform_2(src, tgt, weights, return_sv=False):
