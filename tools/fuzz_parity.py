@@ -1,0 +1,183 @@
+#!/usr/bin/env python
+"""Time-bounded random-shape parity fuzz of the CUDA path against the CPU oracle (test infrastructure, like tests/).
+
+    python tools/fuzz_parity.py [--seconds 60] [--seed 0]
+
+Every trial draws a shape (sizes around the tile edges 32/128/512 included), a data distribution and a scale, runs one
+entry point through the host mirror and checks it with the bars of tests/test_gpu_parity.py:
+  argmin   every algo agrees bit-exactly with the others; rows whose fp64 top-2 gap is above fp32 round-off equal the fp64 truth
+  hint     match_argmin(prior=random indices) == match_argmin()
+  knn      indices and squared distances bit-exact against the brute-force oracle (uniform / planar / line / duplicated clouds)
+  soft     soft targets within 1e-4 relative of the oracle, lse within 5e-5 absolute (= relative error of the weights;
+           tensor-core and CUDA-core shapes, beta up to 12)
+  kabsch   pose within 1e-3 deg / 1e-4 m (scaled) of the oracle's fp64 LAPACK solve
+One line per failure with the seed that reproduces it; exit code 1 if anything failed.
+"""
+import argparse
+import os
+import random
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import deepsir_b200 as D                      # noqa: E402
+from deepsir_b200 import synth                # noqa: E402
+from oracle import deepsir_oracle as O        # noqa: E402
+
+DEV = "cuda:0"
+EDGES = [1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025]
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def size(rng, hi):
+    return rng.choice(EDGES) if rng.random() < 0.35 else rng.randint(1, hi)
+
+
+def fuzz_argmin(rng, seed):
+    B, C = rng.randint(1, 3), rng.choice([1, 3, 8, 20, 32, 33, 48, 64, 64, 64, 65, 80])
+    J, K = size(rng, 5000), size(rng, 5000)
+    scale = rng.choice([1e-3, 1.0, 1.0, 40.0])
+    fs = synth.random_features(B, C, J, seed) * scale
+    fr = synth.random_features(B, C, K, seed + 1) * scale
+    if K > 4 and rng.random() < 0.3:                      # exact duplicates: ties go to the lower index
+        fr[:, :, K // 2] = fr[:, :, 1]
+    if J > 2 and K > 2 and rng.random() < 0.3:            # planted exact matches
+        fs[:, :, 0] = fr[:, :, K - 1]
+    algos = (D.MATCH_FP32, D.MATCH_TC, D.MATCH_AUTO) if C <= 64 else (D.MATCH_FP32, D.MATCH_AUTO)   # the tcgen05 path takes C <= 64
+    got = {a: D.match_argmin(cu(fs), cu(fr), algo=a).cpu() for a in algos}
+    msg = []
+    if not all(torch.equal(got[D.MATCH_FP32], got[a]) for a in algos):
+        msg.append("algos disagree")
+    if K > 1:
+        i64, gap = O.match_top2_fp64(fs, fr)
+        clear = gap > 4e-6 * scale * scale * max(1.0, C / 16)
+        if not torch.equal(got[D.MATCH_AUTO][clear], i64[clear]):
+            msg.append(f"{(got[D.MATCH_AUTO][clear] != i64[clear]).sum().item()} clear rows differ from fp64 truth")
+    elif got[D.MATCH_AUTO].abs().sum() != 0:
+        msg.append("K=1 must return index 0")
+    prior = torch.randint(0, K, (B, J))
+    if not torch.equal(D.match_argmin(cu(fs), cu(fr), prior=cu(prior)).cpu(), got[D.MATCH_AUTO]):
+        msg.append("hinted result differs")
+    return f"argmin B{B} C{C} J{J} K{K} scale{scale}", msg
+
+
+def cloud(rng, g, n):
+    kind = rng.choice(["uniform", "kitti", "planar", "line", "dup", "lattice"])
+    if kind == "kitti":
+        p = synth.kitti_cloud(n, g)[:, :3]
+    else:
+        p = torch.rand(n, 3, generator=g) * rng.choice([1.0, 50.0])
+        if kind == "planar":
+            p[:, 2] = 0.25
+        elif kind == "line":
+            p[:, 1:] = 0.5
+        elif kind == "dup":
+            p[n // 2:] = p[:n - n // 2].clone()
+        elif kind == "lattice":
+            p = torch.round(p * 6)
+    return kind, p.contiguous()
+
+
+def fuzz_knn(rng, seed):
+    g = torch.Generator().manual_seed(seed)
+    k = rng.choice([1, 2, 4, 5, 8, 16, 16, 20, 32])
+    ns, nq = max(k, size(rng, 6000)), size(rng, 3000)
+    kind, sup = cloud(rng, g, ns)
+    qry = sup[:nq].clone() if rng.random() < 0.5 and nq <= ns else cloud(rng, g, nq)[1]
+    nq = qry.shape[0]
+    sup, qry = sup[None], qry[None]
+    i_o, d_o = O.knn(sup, qry, k)
+    msg = []
+    for algo in (D.KNN_GRID, D.KNN_AUTO):
+        i_g, d_g = D.knn(cu(sup), cu(qry), k, algo=algo)
+        if not torch.equal(i_g.cpu(), i_o):
+            msg.append(f"algo {algo}: {(i_g.cpu() != i_o).sum().item()} indices differ")
+        if not torch.equal(d_g.cpu(), d_o):
+            msg.append(f"algo {algo}: distances differ")
+    return f"knn {kind} Ns{ns} Nq{nq} k{k}", msg
+
+
+def fuzz_soft(rng, seed):
+    B, C = rng.randint(1, 3), rng.choice([3, 16, 20, 32, 32, 33, 48, 64, 72])
+    J, K = size(rng, 3000), max(2, size(rng, 3000))
+    b = synth.make_batch(B, max(J, K), C, "3dmatch", config=3, first_pair=seed % 1000)
+    fs, fr = b["feat_src"][:, :, :J].contiguous(), b["feat_ref"][:, :, :K].contiguous()
+    xyz = b["points_ref"][:, :K, :3].contiguous()
+    beta = torch.tensor([rng.uniform(1.0, 12.0) for _ in range(B)])
+    alpha = torch.tensor([rng.uniform(0.0, 0.8) for _ in range(B)])
+    w, y, s, lse = O.soft_correspondence(fs, fr, xyz, beta, alpha)
+    y_g, s_g, lse_g = D.match_soft(cu(fs), cu(fr), cu(xyz), cu(beta), cu(alpha))
+    msg = []
+    # w_jk = exp(a_jk - lse_j): an absolute lse error IS the relative error of every weight of the row (bar: 1e-4 relative)
+    if not torch.allclose(lse_g.cpu(), lse, rtol=1e-4, atol=5e-5):
+        msg.append(f"lse off by {(lse_g.cpu() - lse).abs().max().item():.3e}")
+    if not torch.allclose(y_g.cpu(), y, rtol=1e-4, atol=1e-4):
+        msg.append(f"soft targets off by {(y_g.cpu() - y).abs().max().item():.3e}")
+    if not torch.allclose(s_g.cpu(), s, rtol=1e-4, atol=1e-6):
+        msg.append(f"row mass off by {(s_g.cpu() - s).abs().max().item():.3e}")
+    return f"soft B{B} C{C} J{J} K{K}", msg
+
+
+def fuzz_kabsch(rng, seed):
+    g = torch.Generator().manual_seed(seed)
+    B, M = rng.randint(1, 4), max(3, size(rng, 20000))
+    scale = rng.choice([1.0, 50.0])
+    src = (torch.rand(B, M, 3, generator=g) - 0.5) * scale
+    T = synth.random_transforms(B, g) if hasattr(synth, "random_transforms") else None
+    if T is None:
+        q, _ = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))
+        q = q * torch.sign(torch.det(q))[:, None, None]
+        T = torch.cat([q, torch.randn(B, 3, 1, generator=g) * scale * 0.1], dim=2)
+    tgt = src @ T[:, :, :3].transpose(1, 2) + T[:, None, :, 3] + torch.randn(B, M, 3, generator=g) * 0.01 * scale
+    w = torch.rand(B, M, 1, generator=g)
+    if rng.random() < 0.3:
+        w[:, ::2] = 0
+    T_o, _ = O.compute_rigid_transform_2(src, tgt, w)
+    T_g, _ = D.compute_rigid_transform_2(cu(src), cu(tgt), cu(w))
+    T_g = T_g.cpu()
+    ang = O.rotation_angle_deg(T_g[:, :, :3], T_o[:, :, :3]).max().item()
+    dt = (T_g[:, :, 3] - T_o[:, :, 3]).norm(dim=1).max().item()
+    msg = []
+    if M >= 8 and ang > 1e-3:
+        msg.append(f"rotation off by {ang:.3e} deg")
+    if M >= 8 and dt > 1e-4 * scale:
+        msg.append(f"translation off by {dt:.3e}")
+    return f"kabsch B{B} M{M} scale{scale}", msg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=60.0)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    assert D.lib().dsir_device_check() == 0
+    fuzzers = [fuzz_argmin, fuzz_knn, fuzz_soft, fuzz_kabsch]
+    counts = {f.__name__: 0 for f in fuzzers}
+    failures = 0
+    t0 = time.time()
+    trial = 0
+    while time.time() - t0 < args.seconds:
+        f = fuzzers[trial % len(fuzzers)]
+        seed = args.seed * 1000003 + trial
+        rng = random.Random(seed)
+        try:
+            what, msg = f(rng, seed)
+        except Exception as e:                                    # an exception is a failure of the trial, with its seed
+            what, msg = f.__name__, [f"raised {type(e).__name__}: {e}"]
+        counts[f.__name__] += 1
+        if msg:
+            failures += 1
+            print(f"FAIL trial {trial} seed {seed}: {what}: {'; '.join(msg)}", flush=True)
+        trial += 1
+    print(f"fuzz: {trial} trials in {time.time() - t0:.0f} s {counts}, {failures} failure(s)", flush=True)
+    sys.exit(1 if failures else 0)
+
+
+if __name__ == "__main__":
+    main()
