@@ -11,6 +11,10 @@ entry point through the host mirror and checks it with the bars of tests/test_gp
   soft     soft targets within 1e-4 relative of the oracle, lse within 5e-5 absolute (= relative error of the weights;
            tensor-core and CUDA-core shapes, beta up to 12)
   kabsch   pose within 1e-3 deg / 1e-4 m (scaled) of the oracle's fp64 LAPACK solve
+  pyramid  nn_search levels (xyz, neigh_idx, sub_idx, interp_idx) bit-exact for random sizes, k and sub-sampling ratios
+  loop     align_loop (1-4 iterations): every iteration's correspondences bit-exact, poses within the bars
+  sinkhorn log-assignment within 1e-4 of matchnet.py:211-271 (slack and no slack)
+  topk     values and indices bit-exact against the lower-index-first top-k (heavy ties)
 One line per failure with the seed that reproduces it; exit code 1 if anything failed.
 """
 import argparse
@@ -151,13 +155,80 @@ def fuzz_kabsch(rng, seed):
     return f"kabsch B{B} M{M} scale{scale}", msg
 
 
+def fuzz_pyramid(rng, seed):
+    ratios = rng.choice([(4, 4, 4, 4), (4, 4, 4, 4), (2, 2), (4, 2, 4), (3,), (2, 2, 2, 2, 2)])
+    k = rng.choice([4, 8, 16, 16, 20])
+    prod = 1
+    for r in ratios:
+        prod *= r
+    n = max(k * prod, size(rng, 6000))                       # the coarsest level still holds k points
+    B = rng.randint(1, 2)
+    kind = rng.choice(["kitti", "oxford", "3dmatch"])
+    pts = synth.make_batch(B, n, 8, kind, config=1, first_pair=seed % 997)["points_src"]
+    o = O.nn_search_c(pts, k, ratios)
+    g = D.nn_search_cloud(cu(pts), k, ratios)
+    msg = [f"{name} differs" for name in ("xyz", "neigh_idx", "sub_idx", "interp_idx") if not torch.equal(g[name].cpu(), o[name])]
+    return f"pyramid {kind} B{B} N{n} k{k} ratios{ratios}", msg
+
+
+def fuzz_loop(rng, seed):
+    B, C, n, iters = rng.randint(1, 3), rng.choice([16, 32, 64]), max(64, size(rng, 3000)), rng.randint(1, 4)
+    kind = rng.choice(["kitti", "oxford"])
+    b = synth.make_batch(B, n, C, kind, config=5, first_pair=seed % 997)
+    xs = b["points_src"][:, :, :3].permute(0, 2, 1).contiguous()
+    xr = b["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
+    tr_o, pred_o, xyz_o = O.align_loop(b["feat_src"], b["feat_ref"], xs, xr, b["weights"], iters)
+    tr, pred, xyz, st = D.align_loop(cu(b["feat_src"]), cu(b["feat_ref"]), cu(xs), cu(xr), cu(b["weights"]), iters)
+    msg = []
+    if not torch.equal(torch.stack(pred).cpu(), torch.stack(pred_o)):
+        msg.append(f"{(torch.stack(pred).cpu() != torch.stack(pred_o)).sum().item()} correspondences differ")
+    for i in range(iters):
+        ang = O.rotation_angle_deg(tr[i].cpu()[:, :, :3], tr_o[i][:, :, :3]).max().item()
+        dt = (tr[i].cpu()[:, :, 3] - tr_o[i][:, :, 3]).norm(dim=1).max().item()
+        if ang > 1e-3 or dt > 1e-4:
+            msg.append(f"iteration {i}: pose off by {ang:.2e} deg / {dt:.2e} m")
+    if int(st.sum()) != 0:
+        msg.append("status != 0")
+    return f"loop {kind} B{B} C{C} N{n} iters{iters}", msg
+
+
+def fuzz_sinkhorn(rng, seed):
+    B, J, K = rng.randint(1, 3), size(rng, 700), size(rng, 700)
+    a = torch.randn(B, J, K, generator=torch.Generator().manual_seed(seed)) * rng.choice([0.5, 4.0, 10.0])
+    iters, slack = rng.randint(1, 8), rng.random() < 0.6
+    out = D.sinkhorn(cu(a), iters, slack).cpu()
+    ref = O.sinkhorn(a, iters, slack)
+    msg = [] if torch.allclose(out, ref, atol=1e-4, rtol=1e-4) else [f"log-assignment off by {(out - ref).abs().max().item():.2e}"]
+    return f"sinkhorn B{B} J{J} K{K} iters{iters} slack{slack}", msg
+
+
+def fuzz_topk(rng, seed):
+    n = size(rng, 30000)
+    k = min(rng.choice([1, n, max(1, n // 3), min(n, 17), min(n, 4096)]), 16384)      # dsir_topk_rows: k <= 16384
+    g = torch.Generator().manual_seed(seed)
+    s = torch.randint(0, rng.choice([3, 50, 100000]), (rng.randint(1, 3), n), generator=g).float() - 20.0
+    if rng.random() < 0.3:
+        s = s + torch.rand(s.shape, generator=g)
+    v, i = D.topk(cu(s), k)
+    vo, io = O.topk_lower_index(s, k)
+    msg = []
+    if not torch.equal(i.cpu(), io):
+        msg.append(f"{(i.cpu() != io).sum().item()} indices differ")
+    if not torch.equal(v.cpu(), vo):
+        msg.append("values differ")
+    return f"topk n{n} k{k}", msg
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--seed", type=int, default=0)
-    args = ap.parse_args()
     assert D.lib().dsir_device_check() == 0
-    fuzzers = [fuzz_argmin, fuzz_knn, fuzz_soft, fuzz_kabsch]
+    ap.add_argument("--only", default="", help="comma-separated fuzzer names (argmin,knn,soft,kabsch,pyramid,loop,sinkhorn,topk)")
+    args = ap.parse_args()
+    fuzzers = [fuzz_argmin, fuzz_knn, fuzz_soft, fuzz_kabsch, fuzz_pyramid, fuzz_loop, fuzz_sinkhorn, fuzz_topk]
+    if args.only:
+        fuzzers = [f for f in fuzzers if f.__name__[5:] in args.only.split(",")]
     counts = {f.__name__: 0 for f in fuzzers}
     failures = 0
     t0 = time.time()
