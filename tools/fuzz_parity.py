@@ -39,8 +39,11 @@ def cu(t):
     return t.to(DEV)
 
 
+SCALE = 1
+
+
 def size(rng, hi):
-    return rng.choice(EDGES) if rng.random() < 0.35 else rng.randint(1, hi)
+    return rng.choice(EDGES) * rng.choice([1, SCALE]) if rng.random() < 0.35 else rng.randint(1, hi * SCALE)
 
 
 def fuzz_argmin(rng, seed):
@@ -225,7 +228,10 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     assert D.lib().dsir_device_check() == 0
     ap.add_argument("--only", default="", help="comma-separated fuzzer names (argmin,knn,soft,kabsch,pyramid,loop,sinkhorn,topk)")
+    ap.add_argument("--scale", type=int, default=1, help="multiply the size range (fewer, larger trials)")
     args = ap.parse_args()
+    global SCALE
+    SCALE = args.scale
     fuzzers = [fuzz_argmin, fuzz_knn, fuzz_soft, fuzz_kabsch, fuzz_pyramid, fuzz_loop, fuzz_sinkhorn, fuzz_topk]
     if args.only:
         fuzzers = [f for f in fuzzers if f.__name__[5:] in args.only.split(",")]
