@@ -15,6 +15,8 @@ entry point through the host mirror and checks it with the bars of tests/test_gp
   loop     align_loop (1-4 iterations): every iteration's correspondences bit-exact, poses within the bars
   sinkhorn log-assignment within 1e-4 of matchnet.py:211-271 (slack and no slack)
   topk     values and indices bit-exact against the lower-index-first top-k (heavy ties)
+  consumers gather_neighbour / random_sample / nearest_interpolation bit-exact, relative_pos_encoding within 1e-5
+  metrics  find_correct_correspondence flags equal to np.isin over the reference's hash keys; one-sided chamfer distances
 One line per failure with the seed that reproduces it; exit code 1 if anything failed.
 """
 import argparse
@@ -222,20 +224,65 @@ def fuzz_topk(rng, seed):
     return f"topk n{n} k{k}", msg
 
 
+def fuzz_consumers(rng, seed):
+    """KNN consumers of the RandLA encoder (gather_neighbour, relative_pos_encoding, random_sample, nearest_interpolation)."""
+    g = torch.Generator().manual_seed(seed)
+    B, C, n, k = rng.randint(1, 3), rng.choice([1, 3, 8, 32, 33]), max(2, size(rng, 4000)), rng.choice([1, 4, 16])
+    m = size(rng, 4000)
+    feat = torch.randn(B, C, n, generator=g)
+    xyz = torch.randn(B, 3, n, generator=g) * 20
+    nb = torch.randint(0, n, (B, m, k), generator=g)
+    msg = []
+    if not torch.equal(D.gather_neighbour_V2(cu(feat), cu(nb)).cpu(), O.gather_neighbour_V2(feat, nb)):
+        msg.append("gather_neighbour_V2 differs")
+    nbx = torch.randint(0, n, (B, n, k), generator=g)
+    if not torch.allclose(D.relative_pos_encoding(cu(xyz), cu(nbx)).cpu(), O.relative_pos_encoding(xyz, nbx), atol=1e-5, rtol=1e-6):
+        msg.append("relative_pos_encoding differs")
+    if not torch.equal(D.random_sample(cu(feat)[:, :, :, None], cu(nb)).cpu(), O.random_sample(feat[:, :, :, None], nb)):
+        msg.append("random_sample differs")
+    it = torch.randint(0, n, (B, m, 1), generator=g)
+    if not torch.equal(D.nearest_interpolation(cu(feat)[:, :, :, None], cu(it)).cpu(), O.nearest_interpolation(feat[:, :, :, None], it)):
+        msg.append("nearest_interpolation differs")
+    return f"consumers B{B} C{C} N{n} M{m} k{k}", msg
+
+
+def fuzz_metrics(rng, seed):
+    g = torch.Generator().manual_seed(seed)
+    B, n = rng.randint(1, 3), size(rng, 1500)
+    hs = rng.choice([n + 1, 4096, 20000])
+    pos = [torch.randint(0, max(n, 2), (rng.randint(0, 3 * n), 2), generator=g, dtype=torch.int32) for _ in range(B)]
+    pred = torch.randint(0, max(n, 2), (B, n, 2), generator=g, dtype=torch.int32)
+    for b in range(B):                                              # plant some true pairs
+        take = min(len(pos[b]), n) // 2
+        pred[b, :take] = pos[b][:take]
+    c = D.metrics.find_correct_correspondence([cu(p) for p in pos], cu(pred), hash_seed=hs).cpu()
+    co = torch.from_numpy(O.find_correct_correspondence([p.numpy() for p in pos], pred.numpy(), hash_seed=hs))
+    msg = [] if torch.equal(c.bool(), co.bool()) else [f"{(c.bool() != co.bool()).sum().item()} membership flags differ"]
+    a, bb = torch.randn(B, max(n, 1), 3, generator=g) * 10, torch.randn(B, max(size(rng, 1500), 1), 3, generator=g) * 10
+    d_g = D.metrics.nn_sqdist(cu(a), cu(bb))
+    d_o = O.nn_sqdist(a, bb)
+    d_g = d_g[0] if isinstance(d_g, tuple) else d_g
+    d_o = d_o[0] if isinstance(d_o, tuple) else d_o
+    if not torch.allclose(d_g.cpu(), d_o, rtol=1e-6, atol=1e-6):
+        msg.append("nn_sqdist differs")
+    return f"metrics B{B} N{n} seed{hs}", msg
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--seed", type=int, default=0)
     assert D.lib().dsir_device_check() == 0
-    ap.add_argument("--only", default="", help="comma-separated fuzzer names (argmin,knn,soft,kabsch,pyramid,loop,sinkhorn,topk)")
+    ap.add_argument("--only", default="", help="comma-separated fuzzer names (argmin,knn,soft,kabsch,pyramid,loop,sinkhorn,topk,consumers,metrics)")
     ap.add_argument("--scale", type=int, default=1, help="multiply the size range (fewer, larger trials)")
     args = ap.parse_args()
     global SCALE
     SCALE = args.scale
-    fuzzers = [fuzz_argmin, fuzz_knn, fuzz_soft, fuzz_kabsch, fuzz_pyramid, fuzz_loop, fuzz_sinkhorn, fuzz_topk]
+    fuzzers = [fuzz_argmin, fuzz_knn, fuzz_soft, fuzz_kabsch, fuzz_pyramid, fuzz_loop, fuzz_sinkhorn, fuzz_topk, fuzz_consumers, fuzz_metrics]
     if args.only:
         fuzzers = [f for f in fuzzers if f.__name__[5:] in args.only.split(",")]
     counts = {f.__name__: 0 for f in fuzzers}
+    secs = {f.__name__: 0.0 for f in fuzzers}
     failures = 0
     t0 = time.time()
     trial = 0
@@ -243,16 +290,19 @@ def main():
         f = fuzzers[trial % len(fuzzers)]
         seed = args.seed * 1000003 + trial
         rng = random.Random(seed)
+        t_trial = time.time()
         try:
             what, msg = f(rng, seed)
         except Exception as e:                                    # an exception is a failure of the trial, with its seed
             what, msg = f.__name__, [f"raised {type(e).__name__}: {e}"]
         counts[f.__name__] += 1
+        secs[f.__name__] += time.time() - t_trial
         if msg:
             failures += 1
             print(f"FAIL trial {trial} seed {seed}: {what}: {'; '.join(msg)}", flush=True)
         trial += 1
-    print(f"fuzz: {trial} trials in {time.time() - t0:.0f} s {counts}, {failures} failure(s)", flush=True)
+    per = {k[5:]: f"{counts[k]} trials / {secs[k]:.1f} s" for k in counts}
+    print(f"fuzz: {trial} trials in {time.time() - t0:.0f} s {per}, {failures} failure(s)", flush=True)
     sys.exit(1 if failures else 0)
 
 
