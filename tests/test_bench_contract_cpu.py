@@ -29,3 +29,13 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_tools_scripts_compile():
+    """The measurement / fuzz scripts under tools/ are not imported by any CPU test: at least they must parse."""
+    import glob
+    import py_compile
+    scripts = sorted(glob.glob(os.path.join(ROOT, "tools", "*.py")))
+    assert scripts
+    for path in scripts:
+        py_compile.compile(path, doraise=True)
