@@ -5,7 +5,7 @@ network/matchnet.py, network/model.py, network/tools.py, common/math/se3_torch.p
 torch_points_kernels.knn contract) over the C-ABI library libdeepsir_b200.so.  CUDA only.
 """
 from ._lib import DeepSIRError, build, lib, LIB_PATH, EXPORTS  # noqa: F401
-from ._lib import KNN_AUTO, KNN_BRUTE, KNN_GRID, MATCH_AUTO, MATCH_FP32, MATCH_TC  # noqa: F401
+from ._lib import KNN_AUTO, KNN_BRUTE, KNN_GRID, KNN_TREE, MATCH_AUTO, MATCH_FP32, MATCH_TC  # noqa: F401
 from .match import (square_distance, square_distance_V2, match_features, match_features_V2, feat_dist,  # noqa: F401
                     match_argmin, match_soft, sinkhorn_implicit, compute_affinity, gather_neighbour_V3)
 from .kabsch import (compute_rigid_transform, compute_rigid_transform_2, kabsch_gather, kabsch_moments,  # noqa: F401

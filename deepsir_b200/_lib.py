@@ -14,14 +14,14 @@ import sys
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libdeepsir_b200.so")
+LIB_PATH = os.environ.get("DSIR_B200_LIB") or os.path.join(_PKG, "libdeepsir_b200.so")   # override: development builds only
 CSRC = os.path.join(_PKG, "csrc")
-SOURCES = ["api.cu", "knn.cu", "knn_grid.cu", "match_fp32.cu", "match_tc.cu", "match_tc_soft.cu", "kabsch.cu", "graph.cu", "keypoint.cu", "metrics.cu"]
+SOURCES = ["api.cu", "knn.cu", "knn_grid.cu", "knn_tree.cu", "match_fp32.cu", "match_tc.cu", "match_tc_soft.cu", "kabsch.cu", "graph.cu", "keypoint.cu", "metrics.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
 OK = 0
-KNN_AUTO, KNN_BRUTE, KNN_GRID = 0, 1, 2
+KNN_AUTO, KNN_BRUTE, KNN_GRID, KNN_TREE = 0, 1, 2, 3
 MATCH_AUTO, MATCH_FP32, MATCH_TC = 0, 1, 2
 METRIC_L2, METRIC_EUCLIDEAN, METRIC_ACOS_DOT, METRIC_SQDIFF, METRIC_CITYBLOCK, METRIC_SQDIFF_SQRT = range(6)
 

@@ -172,10 +172,18 @@ bool take_grid_slot(Workspace &W, int B, int n, GridSlot *s) {
     return W.ok();
 }
 
-bool use_grid(int algo, int Ns) {
-    if (algo == DSIR_KNN_BRUTE) return false;
-    if (algo == DSIR_KNN_GRID) return true;
-    return Ns >= KNN_GRID_MIN_POINTS;
+// spatial structure of one support cloud: brute force (none), uniform grid (knn_grid.cu), bucket tree (knn_tree.cu)
+enum { SP_BRUTE = 0, SP_GRID = 1, SP_TREE = 2 };
+// `Nmax` = the largest cloud that has to be indexed in the same call (support and queries share one structure type)
+int knn_structure(int algo, int Ns, int Nmax, int k) {
+    if (algo == DSIR_KNN_BRUTE) return SP_BRUTE;
+    if (algo == DSIR_KNN_GRID) return SP_GRID;
+    if (algo == DSIR_KNN_TREE) return k <= KNN_TREE_MAX_K ? SP_TREE : SP_GRID;   // the caller checks the size limit
+    // AUTO: the grid.  Measured on the C2 cloud (profiles/knn_tree_r2.md): the bucket tree's Morton leaves make a warp scan
+    // 25 leaves for its 32 queries (a kd-ordered partition would need 12) and the level-0 self-kNN takes 1.02 ms per 32
+    // clouds against 0.46 ms for the grid, so the tree stays an explicit choice (DSIR_KNN_TREE).
+    (void)Nmax;
+    return Ns < KNN_GRID_MIN_POINTS ? SP_BRUTE : SP_GRID;
 }
 
 // tunables (overridable for experiments through DSIR_GRID_CPP / DSIR_GRID_R0)
@@ -189,10 +197,11 @@ const float GRID_R0_CELLS = env_float("DSIR_GRID_R0", 1.0f);
 }  // namespace
 
 size_t dsir_knn_workspace_bytes(int B, int Ns, int Nq, int k, int algo) {
-    (void)k;
     if (B <= 0 || Ns <= 0) return 256;
     size_t bytes = ws_block((size_t)B * Ns * sizeof(float4)) + 256;
-    if (use_grid(algo, Ns)) bytes += grid_slot_bytes(B, Ns) + (Nq > 0 ? grid_slot_bytes(B, Nq) + ws_block((size_t)B * Nq * sizeof(float4)) : 0);
+    const int sp = knn_structure(algo, Ns, Ns > Nq ? Ns : Nq, k);
+    if (sp == SP_GRID) bytes += grid_slot_bytes(B, Ns) + (Nq > 0 ? grid_slot_bytes(B, Nq) + ws_block((size_t)B * Nq * sizeof(float4)) : 0);
+    if (sp == SP_TREE) bytes += knn_tree_slot_bytes(B, Ns) + (Nq > 0 ? knn_tree_slot_bytes(B, Nq) + ws_block((size_t)B * Nq * sizeof(float4)) : 0);
     return bytes;
 }
 
@@ -200,16 +209,38 @@ int dsir_knn_xyz(const float *support, int sup_stride, const float *query, int q
                  int k, int64_t *idx, float *dist2, void *ws, size_t ws_bytes, int algo, dsir_stream_t stream) {
     if (!support || !query || !idx || B <= 0 || Ns <= 0 || Nq < 0 || sup_stride < 3 || qry_stride < 3 || k <= 0)
         return DSIR_ERR_BAD_ARG;
-    if (algo < DSIR_KNN_AUTO || algo > DSIR_KNN_GRID) return DSIR_ERR_BAD_ARG;
+    if (algo < DSIR_KNN_AUTO || algo > DSIR_KNN_TREE) return DSIR_ERR_BAD_ARG;
     if (k > 32) return DSIR_ERR_UNSUPPORTED;
     if (Ns < k) return DSIR_ERR_KNN_TOO_FEW;
+    const int sp = knn_structure(algo, Ns, Ns > Nq ? Ns : Nq, k);
+    if (sp == SP_TREE && (Ns > KNN_TREE_MAX_POINTS || Nq > KNN_TREE_MAX_POINTS)) return DSIR_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     Workspace W(ws, ws_bytes);
     float4 *sup4 = W.take<float4>((size_t)B * Ns);
     if (!W.ok()) return DSIR_ERR_WORKSPACE;
     int rc = launch_pack_xyz4(support, sup_stride, (long long)B * Ns, sup4, st);
     if (rc) return rc;
-    if (!use_grid(algo, Ns)) {
+    if (sp == SP_TREE) {
+        // bucket tree over the support; the queries get their own tree so that every warp owns 32 neighbouring queries
+        // (for a self-query the two trees coincide)
+        const bool self = (query == support) && Nq == Ns && qry_stride == sup_stride;
+        if (Nq == 0) return DSIR_OK;
+        KnnTreeView ts, tq;
+        if (!knn_tree_take_slot(W, B, Ns, &ts)) return DSIR_ERR_WORKSPACE;
+        if ((rc = launch_knn_tree_build(sup4, Ns, &ts, 1, B, st))) return rc;
+        tq = ts;
+        if (!self) {
+            float4 *q4 = W.take<float4>((size_t)B * Nq);
+            if (!W.ok() || !knn_tree_take_slot(W, B, Nq, &tq)) return DSIR_ERR_WORKSPACE;
+            if ((rc = launch_pack_xyz4(query, qry_stride, (long long)B * Nq, q4, st))) return rc;
+            if ((rc = launch_knn_tree_build(q4, Nq, &tq, 1, B, st))) return rc;
+        }
+        KnnTreeQueryParams Q{};
+        Q.sup = ts; Q.qry = tq; Q.self = self ? 1 : 0; Q.k = k;
+        Q.idx = idx; Q.idx_bs = (long long)Nq * k; Q.dist2 = dist2;
+        return launch_knn_tree_query(Q, B, st);
+    }
+    if (sp == SP_BRUTE) {
         KnnBruteParams P{};
         P.sup4 = sup4; P.sup_bs = Ns;
         P.query = query; P.qry_bs = (long long)Nq * qry_stride; P.qry_stride = qry_stride;
@@ -257,27 +288,31 @@ static int pyramid_levels(int N, const int *ratios, int L, PyramidLevels *lv) {
     return DSIR_OK;
 }
 
-// distinct support sizes of a pyramid that get a grid: n[0], n[1], ..., and the last sub-cloud m[L-1]
-static int pyramid_grid_sizes(const PyramidLevels &lv, int algo, int *sizes) {
+// distinct support sizes of a pyramid that get a spatial structure (one type per pyramid, decided by the largest
+// cloud): n[0], n[1], ..., and the last sub-cloud m[L-1]
+static int pyramid_grid_sizes(const PyramidLevels &lv, int algo, int k, int *sizes, int *sp_out) {
     int ng = 0;
+    const int sp = knn_structure(algo, lv.n[0] >= KNN_TREE_MIN_POINTS ? lv.n[0] : KNN_TREE_MIN_POINTS, lv.n[0], k);
+    *sp_out = sp;
+    if (sp == SP_BRUTE) return 0;
     for (int l = 0; l <= lv.L; ++l) {
         int n = l < lv.L ? lv.n[l] : lv.m[lv.L - 1];
         bool dup = false;
         for (int g = 0; g < ng; ++g) dup = dup || sizes[g] == n;
-        if (!dup && n > 0 && use_grid(algo, n)) sizes[ng++] = n;
+        const bool indexed = (algo == DSIR_KNN_GRID || algo == DSIR_KNN_TREE) ? true : n >= KNN_TREE_MIN_POINTS;
+        if (!dup && n > 0 && indexed) sizes[ng++] = n;
     }
     return ng;
 }
 
 size_t dsir_knn_pyramid_workspace_bytes(int B, int N, int k, const int *ratios, int L, int algo) {
-    (void)k;
     if (B <= 0 || N <= 0) return 256;
     size_t bytes = ws_block((size_t)B * N * sizeof(float4)) + 256;
     PyramidLevels lv;
     if (ratios && pyramid_levels(N, ratios, L, &lv) == DSIR_OK) {
-        int sizes[DSIR_MAX_LEVELS + 1];
-        int ng = pyramid_grid_sizes(lv, algo, sizes);
-        for (int g = 0; g < ng; ++g) bytes += grid_slot_bytes(B, sizes[g]);
+        int sizes[DSIR_MAX_LEVELS + 1], sp = SP_BRUTE;
+        int ng = pyramid_grid_sizes(lv, algo, k, sizes, &sp);
+        for (int g = 0; g < ng; ++g) bytes += sp == SP_TREE ? knn_tree_slot_bytes(B, sizes[g]) : grid_slot_bytes(B, sizes[g]);
     }
     return bytes;
 }
@@ -286,8 +321,9 @@ int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *r
                      int64_t *neigh, int64_t *sub, int64_t *interp, void *ws, size_t ws_bytes, int algo,
                      dsir_stream_t stream) {
     if (!pts || !ratios || !neigh || !sub || !interp || B <= 0 || N <= 0 || pt_stride < 3 || k <= 0) return DSIR_ERR_BAD_ARG;
-    if (algo < DSIR_KNN_AUTO || algo > DSIR_KNN_GRID) return DSIR_ERR_BAD_ARG;
+    if (algo < DSIR_KNN_AUTO || algo > DSIR_KNN_TREE) return DSIR_ERR_BAD_ARG;
     if (k > 32) return DSIR_ERR_UNSUPPORTED;
+    if (algo == DSIR_KNN_TREE && N > KNN_TREE_MAX_POINTS) return DSIR_ERR_UNSUPPORTED;
     PyramidLevels lv;
     int rc = pyramid_levels(N, ratios, L, &lv);
     if (rc) return rc;
@@ -301,10 +337,15 @@ int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *r
     if (xyz_cat && (rc = launch_pyramid_xyz(pts, pt_stride, B, N, lv, xyz_cat, st))) return rc;
 
     // one build launch for every grid of the pyramid (every level cloud is a prefix of the packed cloud)
-    int sizes[DSIR_MAX_LEVELS + 1];
-    const int ng = pyramid_grid_sizes(lv, algo, sizes);
+    int sizes[DSIR_MAX_LEVELS + 1], sp = SP_BRUTE;
+    const int ng = pyramid_grid_sizes(lv, algo, k, sizes, &sp);
     GridSlot slots[DSIR_MAX_LEVELS + 1];
-    if (ng > 0) {
+    KnnTreeView trees[DSIR_MAX_LEVELS + 1];
+    if (ng > 0 && sp == SP_TREE) {
+        for (int g = 0; g < ng; ++g)
+            if (!knn_tree_take_slot(W, B, sizes[g], &trees[g])) return DSIR_ERR_WORKSPACE;
+        if ((rc = launch_knn_tree_build(pts4, N, trees, ng, B, st))) return rc;
+    } else if (ng > 0) {
         KnnGridBuildParams BP{};
         BP.pts4 = pts4; BP.pts_bs = N; BP.gmax = KNN_GRID_GMAX; BP.cells_per_point = GRID_CELLS_PER_POINT;
         for (int g = 0; g < ng; ++g) {
@@ -314,8 +355,15 @@ int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *r
         if ((rc = launch_knn_grid_build(BP, ng, B, st))) return rc;
     }
     auto find_slot = [&](int n) -> const GridSlot * {
+        if (sp != SP_GRID) return nullptr;
         for (int g = 0; g < ng; ++g)
             if (slots[g].n == n) return &slots[g];
+        return nullptr;
+    };
+    auto find_tree = [&](int n) -> const KnnTreeView * {
+        if (sp != SP_TREE) return nullptr;
+        for (int g = 0; g < ng; ++g)
+            if (trees[g].n == n) return &trees[g];
         return nullptr;
     };
 
@@ -345,12 +393,19 @@ int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *r
     for (int l = 0; l < L; ++l) {
         const GridSlot *gl = find_slot(lv.n[l]);   // grid over the level cloud (support of the self-kNN, query order)
         const GridSlot *gm = find_slot(lv.m[l]);   // grid over the sub-cloud (support of the 1-NN up-sampling)
+        const KnnTreeView *tl = find_tree(lv.n[l]), *tm = find_tree(lv.m[l]);
         st = l == 0 ? st_main : st_self;
         int64_t *nb = neigh + (size_t)lv.off[l] * k;
         int64_t *pool = sub + (size_t)lv.offsub[l] * k;
         int64_t *up = interp + lv.off[l];
         // ---- self-kNN of the level cloud (data_base.py:165); rows < m[l] are also the pooling indices (:168) ----
-        if (gl) {
+        if (tl) {
+            KnnTreeQueryParams Q{};
+            Q.sup = *tl; Q.qry = *tl; Q.self = 1; Q.k = k;
+            Q.idx = nb; Q.idx_bs = (long long)lv.sumN * k;
+            Q.idx2 = pool; Q.idx2_bs = (long long)lv.sumSub * k; Q.idx2_rows = lv.m[l];
+            if ((rc = launch_knn_tree_query(Q, B, st))) { join(); return rc; }
+        } else if (gl) {
             KnnGridQueryParams Q{};
             Q.hdr = gl->hdr; Q.cell_start = gl->cell_start; Q.sorted = gl->sorted; Q.gmax = KNN_GRID_GMAX; Q.Ns = lv.n[l];
             Q.q_sorted = gl->sorted; Q.q_sorted_bs = lv.n[l];
@@ -369,7 +424,12 @@ int dsir_knn_pyramid(const float *pts, int pt_stride, int B, int N, const int *r
         }
         // ---- 1-NN of every level point into the sub-cloud (data_base.py:170) ----
         st = st_up;
-        if (gm) {
+        if (tm && tl) {
+            KnnTreeQueryParams Q{};
+            Q.sup = *tm; Q.qry = *tl; Q.self = 0; Q.k = 1;
+            Q.idx = up; Q.idx_bs = lv.sumN;
+            if ((rc = launch_knn_tree_query(Q, B, st))) { join(); return rc; }
+        } else if (gm) {
             KnnGridQueryParams Q{};
             Q.hdr = gm->hdr; Q.cell_start = gm->cell_start; Q.sorted = gm->sorted; Q.gmax = KNN_GRID_GMAX; Q.Ns = lv.m[l];
             if (gl) { Q.q_sorted = gl->sorted; Q.q_sorted_bs = lv.n[l]; }

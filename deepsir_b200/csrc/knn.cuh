@@ -93,3 +93,53 @@ int launch_knn_grid_build(const KnnGridBuildParams &P, int ngrids, int B, cudaSt
 int launch_knn_grid_query(const KnnGridQueryParams &P, int B, cudaStream_t st);
 
 }  // namespace dsir
+
+// ---------------------------------------------------------------------------------------------------
+// bucket-tree variant (knn_tree.cu): Morton-ordered leaves of 32 points, one warp per query leaf
+// ---------------------------------------------------------------------------------------------------
+namespace dsir {
+
+constexpr int KNN_TREE_MIN_POINTS = 512;     // below this the brute-force kernel is used
+constexpr int KNN_TREE_MAX_POINTS = 24576;   // the build sorts one cloud in the shared memory of one CTA
+constexpr int KNN_TREE_MAX_K = 16;           // sorted register list of the query kernel; larger k -> grid path
+
+struct KnnLeaf {   // 512 bytes: one cp.async.bulk per leaf
+    float nx[32], ny[32], nz[32];   // NEGATED coordinates (dx = q + nx is exactly q - x); padding slots hold -inf
+    int idx[32];                    // original index; 0x7fffffff in padding slots
+};
+
+struct KnnTreeView {
+    const KnnLeaf *leaves;   // [B][nleaf]
+    const float *box;        // [B][6][nlpad]: lo.x, lo.y, lo.z, hi.x, hi.y, hi.z per leaf
+    const float *sbox;       // [B][6][32]: the same per supernode (32 consecutive leaves)
+    int n, nleaf, nlpad, nsuper;
+};
+
+struct KnnTreeBuildParams {
+    const float4 *pts4;   // [B][pts_bs] packed xyz0; tree g is built over the first n[g] points of every cloud
+    long long pts_bs;
+    int n[DSIR_MAX_LEVELS + 1];
+    KnnLeaf *leaves[DSIR_MAX_LEVELS + 1];
+    float *box[DSIR_MAX_LEVELS + 1];
+    float *sbox[DSIR_MAX_LEVELS + 1];
+    int cap;              // shared-memory capacity in points (>= every n[g])
+};
+
+struct KnnTreeQueryParams {
+    KnnTreeView sup, qry;   // support tree; query tree (its leaves are the warps' query groups)
+    int self;               // query tree == support tree: every warp starts with its own leaf
+    int k;
+    int64_t *idx;           // idx[b*idx_bs + q*k + p], q = ORIGINAL query index
+    long long idx_bs;
+    float *dist2;           // same addressing, nullable
+    int64_t *idx2;          // optional second copy of rows q < idx2_rows (the pyramid's pooling indices)
+    long long idx2_bs;
+    int idx2_rows;
+};
+
+size_t knn_tree_slot_bytes(int B, int n);
+bool knn_tree_take_slot(Workspace &W, int B, int n, KnnTreeView *v);
+int launch_knn_tree_build(const float4 *pts4, long long pts_bs, const KnnTreeView *trees, int ntrees, int B, cudaStream_t st);
+int launch_knn_tree_query(const KnnTreeQueryParams &P, int B, cudaStream_t st);
+
+}  // namespace dsir

@@ -12,8 +12,6 @@
 //           cube is ONE contiguous run of sorted points.
 //   query   one thread per query, queries taken in the cell order of their own grid so that the lanes of a warp
 //           are spatial neighbours (same cells -> L1 hits, little divergence); sorted top-k in registers.
-#include <cstdlib>
-
 #include "knn.cuh"
 
 namespace dsir {
@@ -399,7 +397,7 @@ __global__ __launch_bounds__(128) void knn_grid_query_heap_kernel(KnnGridQueryPa
     int p0;
     {
         int pos = t;                                   // self-kNN in cell order: the query is support point t
-        if (P.q_sorted != S) {
+        if (P.q_sorted + (size_t)b * P.q_sorted_bs != S) {   // not a self query (the query IS support point t otherwise)
             const int cxq = cell_of(qx, H.lo[0], H.inv_h, H.gx);
             pos = cs[(czq * H.gy + cyq) * H.gx + cxq];
         }
@@ -531,14 +529,9 @@ int launch_knn_grid_query(const KnnGridQueryParams &P, int B, cudaStream_t st) {
     if (P.Ns < P.k) return DSIR_ERR_KNN_TOO_FEW;
     if (P.Nq <= 0 || B <= 0) return DSIR_OK;
     dim3 grid((P.Nq + 127) / 128, B);
-    static const bool reg_list = getenv("DSIR_KNN_REGLIST") != nullptr;   // experiments: sorted register list for every k
     if (P.k == 1) knn_grid_query_kernel<1><<<grid, 128, 0, st>>>(P);
     else if (P.k <= 4) knn_grid_query_kernel<4><<<grid, 128, 0, st>>>(P);
-    else if (reg_list) {
-        if (P.k <= 8) knn_grid_query_kernel<8><<<grid, 128, 0, st>>>(P);
-        else if (P.k <= 16) knn_grid_query_kernel<16><<<grid, 128, 0, st>>>(P);
-        else knn_grid_query_kernel<32><<<grid, 128, 0, st>>>(P);
-    } else if (P.k <= 8) knn_grid_query_heap_kernel<8><<<grid, 128, 0, st>>>(P);
+    else if (P.k <= 8) knn_grid_query_heap_kernel<8><<<grid, 128, 0, st>>>(P);
     else if (P.k <= 16) knn_grid_query_heap_kernel<16><<<grid, 128, 0, st>>>(P);
     else knn_grid_query_heap_kernel<32><<<grid, 128, 0, st>>>(P);
     DSIR_LAUNCH_CHECK();

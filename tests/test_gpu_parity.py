@@ -29,7 +29,7 @@ def assert_pose_close(T_gpu, T_ref, scale=1.0):
 
 
 # ------------------------------------------------------------------------------------------- KNN
-@pytest.mark.parametrize("algo", [D.KNN_BRUTE, D.KNN_GRID, D.KNN_AUTO])
+@pytest.mark.parametrize("algo", [D.KNN_BRUTE, D.KNN_GRID, D.KNN_TREE, D.KNN_AUTO])
 def test_knn_random_cloud_bit_exact(algo):
     g = torch.Generator().manual_seed(3)
     sup = torch.stack([synth.kitti_cloud(2500, g) for _ in range(2)])
@@ -42,7 +42,7 @@ def test_knn_random_cloud_bit_exact(algo):
         assert torch.equal(d_g.cpu(), d_o), k
 
 
-@pytest.mark.parametrize("algo", [D.KNN_BRUTE, D.KNN_GRID, D.KNN_AUTO])
+@pytest.mark.parametrize("algo", [D.KNN_BRUTE, D.KNN_GRID, D.KNN_TREE, D.KNN_AUTO])
 def test_knn_ties_duplicates_and_errors(algo):
     ax = torch.arange(9, dtype=torch.float32)
     lat = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, -1, 3).contiguous()
@@ -59,7 +59,7 @@ def test_knn_ties_duplicates_and_errors(algo):
         D.knn(cu(lat[:, :10]), cu(lat), 16, algo=algo)
 
 
-@pytest.mark.parametrize("algo", [D.KNN_BRUTE, D.KNN_GRID, D.KNN_AUTO])
+@pytest.mark.parametrize("algo", [D.KNN_BRUTE, D.KNN_GRID, D.KNN_TREE, D.KNN_AUTO])
 def test_knn_pyramid_matches_nn_search(algo):
     b = synth.make_batch(2, 4096, 8, "kitti", config=1)
     for key in ("points_src", "points_ref"):
@@ -87,14 +87,16 @@ def test_knn_grid_degenerate_clouds():
         c = c.contiguous()
         for k in (1, 16, 32):
             i_o, d_o = O.knn(c, c, k)
-            i_g, d_g = D.knn(cu(c), cu(c), k, algo=D.KNN_GRID)
-            assert torch.equal(i_g.cpu(), i_o) and torch.equal(d_g.cpu(), d_o), (name, k)
+            for algo in (D.KNN_GRID, D.KNN_TREE):
+                i_g, d_g = D.knn(cu(c), cu(c), k, algo=algo)
+                assert torch.equal(i_g.cpu(), i_o) and torch.equal(d_g.cpu(), d_o), (name, k, algo)
     # queries far outside the support's bounding box
     sup = torch.randn(1, 800, 3, generator=g).contiguous()
     qry = (torch.randn(1, 300, 3, generator=g) * 50).contiguous()
     i_o, d_o = O.knn(sup, qry, 8)
-    i_g, d_g = D.knn(cu(sup), cu(qry), 8, algo=D.KNN_GRID)
-    assert torch.equal(i_g.cpu(), i_o) and torch.equal(d_g.cpu(), d_o)
+    for algo in (D.KNN_GRID, D.KNN_TREE):
+        i_g, d_g = D.knn(cu(sup), cu(qry), 8, algo=algo)
+        assert torch.equal(i_g.cpu(), i_o) and torch.equal(d_g.cpu(), d_o)
 
 
 def test_knn_full_size_properties():
