@@ -99,16 +99,101 @@ def make_inputs(batch, first_pair):
                 weights=b["weights"][:, :, 0].contiguous())
 
 
+REF_COPY = os.path.join(ROOT, "baseline", "_ref")
+_ref_mods = None
+
+
+def reference_modules():
+    """The reference's own modules from baseline/_ref (unmodified copy shipped by __graft_entry__.build()), or None."""
+    global _ref_mods
+    if _ref_mods is None:
+        _ref_mods = False
+        if os.path.isdir(os.path.join(REF_COPY, "network")):
+            import warnings
+            warnings.filterwarnings("ignore")
+            if REF_COPY not in sys.path:
+                sys.path.insert(0, REF_COPY)
+            try:
+                from network import model as M
+                _ref_mods = M
+            except Exception:
+                _ref_mods = False
+    return _ref_mods or None
+
+
 def cpu_step(host, n_pairs):
-    """The reference path on the CPU (oracle port): nn_search on both clouds (kd-tree, all cores) + match/argmin
-    (6000-row chunks, MKL sgemm) + gather + Kabsch (fp64 LAPACK SVD) + transform + compose, for the first n_pairs pairs."""
+    """One step of the C2 workload on the host CPU for the first n_pairs pairs.  With baseline/_ref present this is the
+    REFERENCE's own code: match_features_V2 + .min in 6000-row chunks (network/model.py:558-569), gather_neighbour_V3
+    (:571), compute_rigid_transform_2 incl. its fp64 LAPACK SVD (:588, :22-66), se3_torch.transform (:590) — the statements
+    of one registration iteration, on the synthetic features; otherwise the oracle port of the same statements.  The KNN
+    pyramids: the reference's torch_points_kernels.knn is not installable here, so both variants use the kd-tree stand-in
+    (scipy cKDTree, all cores — the algorithm class of its nanoflann) through the oracle's nn_search restatement."""
     from oracle import deepsir_oracle as O
     s = slice(0, n_pairs)
-    O.nn_search_kdtree(host["points_src"][s], KNN_K, RATIOS)      # kd-tree like the reference's torch_points_kernels.knn
+    O.nn_search_kdtree(host["points_src"][s], KNN_K, RATIOS)
     O.nn_search_kdtree(host["points_ref"][s], KNN_K, RATIOS)
     xs = host["points_src"][s, :, :3].permute(0, 2, 1).contiguous()
     xr = host["points_ref"][s, :, :3].permute(0, 2, 1).contiguous()
-    O.align_loop(host["feat_src"][s], host["feat_ref"][s], xs, xr, host["weights"][s, :, None], 1)
+    M = reference_modules()
+    if M is None:
+        O.align_loop(host["feat_src"][s], host["feat_ref"][s], xs, xr, host["weights"][s, :, None], 1)
+        return
+    with torch.no_grad():
+        feat_src, feat_ref = host["feat_src"][s], host["feat_ref"][s]
+        stride, N = 6000, feat_src.shape[2]
+        indexs = []
+        for n in range((N + stride - 1) // stride):
+            mm = M.match_features_V2(feat_src[:, :, n * stride:(n + 1) * stride], feat_ref)
+            indexs.append(mm.min(dim=2, keepdim=False)[1])
+        indexs = torch.cat(indexs, dim=1)
+        xyz_ref_new = M.gather_neighbour_V3(xr, indexs)
+        a = xs.permute(0, 2, 1).contiguous()
+        bnew = xyz_ref_new.permute(0, 2, 1).contiguous()
+        R_t, _ = M.compute_rigid_transform_2(a, bnew, weights=host["weights"][s, :, None])
+        M.se3_torch.transform(R_t.detach(), a)
+
+
+def cpu_kind():
+    return "reference" if reference_modules() is not None else "port"
+
+
+def cpu_sample_text(reps, n_pairs, cores):
+    if reference_modules() is not None:
+        return (f"{reps} x {n_pairs} pair of the C2 workload on the host: the reference's own match_features_V2 + min "
+                f"(6000-row chunks), gather_neighbour_V3, compute_rigid_transform_2 (fp64 LAPACK SVD), se3_torch.transform from "
+                f"baseline/_ref; KNN pyramids by the kd-tree stand-in (scipy cKDTree; torch_points_kernels is not installable), "
+                f"{cores} threads")
+    return (f"{reps} x {n_pairs} pair of the C2 workload on the host: oracle port (torch-CPU MKL sgemm/LAPACK + scipy "
+            f"cKDTree KNN), {cores} threads")
+
+
+def c1_reference_forward():
+    """BASELINE.json configs[0]: the reference's Network.forward_align_4 (network/model.py:520-607, test.py:399-402) on one
+    synthetic 4096-point KITTI-shaped pair, batch 1, 5 iterations, on the CPU; seeded random-init weights (the shipped
+    checkpoint is a missing blob).  Returns seconds per pair (median of 3), or None without baseline/_ref."""
+    M = reference_modules()
+    if M is None:
+        return None
+    import arguments
+    from deepsir_b200 import synth
+    from oracle import deepsir_oracle as O
+    args = arguments.eval_arguments().parse_args([])
+    torch.manual_seed(0)
+    net = M.Network(args).eval()
+    b = synth.make_batch(1, 4096, 64, "kitti", config=1)
+    data = {"points_src": b["points_src"], "points_ref": b["points_ref"]}
+    ts = []
+    with torch.no_grad():
+        for _ in range(4):
+            t0 = time.perf_counter()
+            d = dict(data)
+            for key in ("points_src", "points_ref"):           # loader-side KNN (data_base.py:153-183): kd-tree stand-in
+                g = O.nn_search_kdtree(d[key], KNN_K, RATIOS)
+                for name in ("xyz", "neigh_idx", "sub_idx", "interp_idx"):
+                    d[key + "_" + name] = g[name]
+            net(d, (args.num_reg_iter, False))
+            ts.append(time.perf_counter() - t0)
+    return statistics.median(ts[1:])
 
 
 def torch_gpu_step(devt, xs0, xr0, n_pairs):
@@ -138,9 +223,8 @@ def run_reference(args, rank, world):
            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "sample": f"{n_pairs} pair per step on the host CPU"},
-           "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
-                            "sample": f"{n_pairs} pair/step x {args.steps} steps of the C2 workload, oracle port "
-                                      f"(torch-CPU MKL + scipy cKDTree KNN), {cores} threads"},
+           "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": cpu_kind(),
+                            "sample": cpu_sample_text(args.steps, n_pairs, cores)},
            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -366,9 +450,14 @@ def main():
             reps += 1
         dt = time.perf_counter() - t_0
         cores = os.cpu_count() or 1
-        out["cpu_baseline"] = {"value": n_pairs * reps / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-                               "sample": f"{reps} x {n_pairs} pair of the C2 workload on the host: oracle port "
-                                         f"(torch-CPU MKL sgemm/LAPACK + scipy cKDTree KNN), {cores} threads"}
+        out["cpu_baseline"] = {"value": n_pairs * reps / dt, "unit": "pairs/s", "cores": cores, "kind": cpu_kind(),
+                               "sample": cpu_sample_text(reps, n_pairs, cores)}
+        c1 = c1_reference_forward()
+        if c1 is not None:
+            out["cpu_baseline"]["c1_forward_align_4"] = {
+                "value": 1.0 / c1, "unit": "pairs/s", "s_per_pair": c1,
+                "sample": "BASELINE configs[0]: the reference's Network.forward_align_4 (5 iterations, RandLA-Net + MLPs "
+                          "included, seeded random-init weights) + kd-tree KNN pyramids on one synthetic 4096-point pair, CPU"}
         # "stock PyTorch on the same B200" (third column): reported beside the CPU port, never the product path
         torch.cuda.empty_cache()
         n_t = 8
