@@ -21,6 +21,8 @@ struct MatchParams {
     int reuse_prep;
     // optional [B,J] correspondences of the previous iteration (argmin only): a hint that tightens the filter, never changes the result
     const int64_t *prior_idx;
+    // optional [B] flags: when set, only batch elements with a non-zero flag are computed (CTAs of the others leave at once)
+    const unsigned char *only_flagged;
 };
 
 enum { MATCH_MODE_ARGMIN = 0, MATCH_MODE_DENSE = 1, MATCH_MODE_SOFT = 2 };

@@ -59,6 +59,7 @@ __global__ __launch_bounds__(MT, 2) void match_fp32_kernel(MatchParams P) {
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int b = blockIdx.y;
+    if (P.only_flagged != nullptr && P.only_flagged[b] == 0) return;   // (block-uniform, before any barrier)
     const int j0 = blockIdx.x * TM;
     const float *fsb = P.fs.ptr + (size_t)b * P.fs.batch_stride;
     const float *frb = P.fr.ptr + (size_t)b * P.fr.batch_stride;

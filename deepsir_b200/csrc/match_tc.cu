@@ -57,6 +57,13 @@ constexpr int TC_STEPS = TC_BN / TC_HALVES / 32;       // 32-column steps per wa
 static_assert(TC_RBS * TC_ACC_STAGES == 4 && TC_EPI_WARPS == 16 && TC_RBS % TC_MMA_WARPS == 0, "TMEM / warp budget");
 // The issue arbiter of an SM sub-partition prefers the HIGHEST warp id, so the control warps sit above the 16 epilogue
 // warps.  Warp 16 allocates TMEM and then produces (TMA); warps 17.. issue MMAs (whole warp, one elected lane).
+// clock64() stamps in the MMA / epilogue loops and the DSIR_TC_DEBUG experiment switches exist only in builds made with
+// -DDSIR_TC_TRACE (tools/build_variant.sh); the shipped library carries neither.
+#ifdef DSIR_TC_TRACE
+constexpr bool TC_TRACE = true;
+#else
+constexpr bool TC_TRACE = false;
+#endif
 constexpr int TC_WARP_TMA = TC_EPI_WARPS, TC_WARP_MMA0 = TC_EPI_WARPS + 1;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_MMA_WARPS) * 32;
 constexpr int TC_LISTS = TC_HALVES;           // candidate lists per (row, split)
@@ -142,9 +149,16 @@ __device__ __forceinline__ void release_acc(uint64_t *empty_bar, int lane) {
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar);
 }
+// Without the folded norm (TcParams::xm >= 0) the zero-filled reference rows beyond K read x' = 0 instead of a huge padded
+// norm: the unit that holds them masks those columns to +inf before the minimum tree (and the slow path checks the column).
+__device__ __forceinline__ void mask_cols(uint32_t (&v)[32], int col0, int K) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (col0 + i >= K) v[i] = 0x7f800000u;
+}
 template <bool LAST>
 __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint32_t taddr, float margin, float &thr,
-                                         float (&cv)[TC_T], int (&ci)[TC_T], bool sample, float &best,
+                                         float (&cv)[TC_T], int (&ci)[TC_T], bool sample, float &best, int kmax,
                                          uint64_t *empty_bar = nullptr, int lane = 0) {
 #define F(i) __uint_as_float(v[i])
     const float a0 = fmin3(F(0), F(1), F(2)), a1 = fmin3(F(3), F(4), F(5)), a2 = fmin3(F(6), F(7), F(8));
@@ -158,13 +172,13 @@ __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint
         best = fminf(best, mm);
         return;
     }
-    const bool slow = __any_sync(0xffffffffu, mm < thr);
+    const bool slow = __any_sync(0xffffffffu, mm <= thr);   // inclusive, like the refine step's `v <= gmin + margin`
     if (LAST && !slow) release_acc(empty_bar, lane);
     if (slow) {
         unsigned qm = 0;       // which aligned column quads hold a value below the threshold
 #pragma unroll
         for (int g = 0; g < 8; ++g)
-            qm |= (fminf(fmin3(F(4 * g), F(4 * g + 1), F(4 * g + 2)), F(4 * g + 3)) < thr) ? (1u << g) : 0u;
+            qm |= (fminf(fmin3(F(4 * g), F(4 * g + 1), F(4 * g + 2)), F(4 * g + 3)) <= thr) ? (1u << g) : 0u;
 #undef F
         unsigned um = __reduce_or_sync(0xffffffffu, qm);
 #pragma unroll 1
@@ -176,7 +190,7 @@ __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint
             if ((qm >> g) & 1u) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (x[e] < thr) cand_update(cv, ci, x[e], col0 + 4 * g + e, margin, thr);
+                    if (x[e] <= thr && col0 + 4 * g + e < kmax) cand_update(cv, ci, x[e], col0 + 4 * g + e, margin, thr);
             }
         }
         if (LAST) release_acc(empty_bar, lane);
@@ -205,6 +219,8 @@ struct TcParams {
     const float *ns;        // [B,J] exact squared norms
     const float *rmax;      // [B] max reference squared norm
     const float *scale;     // [B] sigma (power of two)
+    const float *xm;        // [B] >= 0: the folded-norm K-step is SKIPPED for this batch element and every margin is widened by
+                            //     this amount (sigma^2 x spread of the reference norms); < 0: norm folded in (see tc_spread_kernel)
     float *cand_val;        // [B][Jpad][S][T]  (scaled units)
     int *cand_idx;
     int prime_div;            // priming pass over every prime_div-th unit (0 = none)
@@ -275,12 +291,13 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                     tma_load_3d(sA + r * MAIN_TILE, &mapA, 0, rb * TC_BM + r * 128, b, full_a);
                 if (first) tma_load_3d(sAaug, &mapAaug, 0, 0, 0, full_a);   // constant 1,1,1,0.. tile, loaded once
                 first = false;
+                const bool aug = P.xm[b] < 0.f;
                 for (int t = 0; t < us.total(); ++t) {
                     const int u = us.unit(t);
                     while (!mbar_try_wait(&empty_b[pb.stage], pb.phase ^ 1u)) __nanosleep(32);
-                    mbar_expect_tx(&full_b[pb.stage], MAIN_TILE + AUG_TILE);
+                    mbar_expect_tx(&full_b[pb.stage], MAIN_TILE + (aug ? AUG_TILE : 0u));
                     tma_load_3d(sB + pb.stage * MAIN_TILE, &mapB, 0, u * TC_BN, b, &full_b[pb.stage]);
-                    tma_load_3d(sBaug + pb.stage * AUG_TILE, &mapBaug, 0, u * TC_BN, b, &full_b[pb.stage]);
+                    if (aug) tma_load_3d(sBaug + pb.stage * AUG_TILE, &mapBaug, 0, u * TC_BN, b, &full_b[pb.stage]);
                     pb.advance(TC_STAGES);
                 }
                 iphase ^= 1u;
@@ -292,7 +309,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
             const int w = warp - TC_WARP_MMA0;
             PipeState pb{0, 0}, pa{0, 0};
             uint32_t iphase = 0;
-            const bool tracing = (P.dbg_flags & 2) && blockIdx.x == 0 && lane == 0;
+            const bool tracing = TC_TRACE && (P.dbg_flags & 2) && blockIdx.x == 0 && lane == 0;
             int useq = 0;
             const uint64_t descA0 = make_kmajor_desc(smem_u32(sA), 1024, 2);
             const uint64_t descAaug = make_kmajor_desc(smem_u32(sAaug), 256, 6);
@@ -300,6 +317,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
             const uint64_t descBaug0 = make_kmajor_desc(smem_u32(sBaug), 256, 6);
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
                 const UnitSched us(it % P.S, P.S, P.U, P.prime_div);
+                const bool aug = P.xm[it / (P.S * P.RB)] < 0.f;
                 mbar_wait(full_a, iphase);
                 for (int t = 0; t < us.total(); ++t) {
                     mbar_wait(&full_b[pb.stage], pb.phase);
@@ -315,7 +333,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
 #pragma unroll
                         for (int ks = 0; ks < NKS; ++ks)     // +32 bytes (16 halves) inside the 128-byte swizzle row
                             mma_f16(d_tmem, descA + (uint64_t)(ks * 2), descB + (uint64_t)(ks * 2), TC_IDESC, ks > 0 ? 1u : 0u);
-                        mma_f16(d_tmem, descAaug, descBaug, TC_IDESC, 1u);   // + sigma^2 |r_k|^2
+                        if (aug) mma_f16(d_tmem, descAaug, descBaug, TC_IDESC, 1u);   // + sigma^2 |r_k|^2
                         tc_commit(&tmem_full[pa.stage * TC_RBS + r]);   // accumulator ready for its epilogue warps
                         if (tracing && useq < 256 && r < 2) P.trace[(useq * 2 + r) * 2 + 1] = (unsigned int)clock64();
                     }
@@ -335,7 +353,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
         const int r = (warp >> 2) / TC_HALVES;        // row block
         const int trow = q * 32 + lane;               // row inside the 128-row block
         PipeState pa{0, 0};
-        const bool tracing = (P.dbg_flags & 2) && blockIdx.x == 0 && warp == 0 && lane == 0;
+        const bool tracing = TC_TRACE && (P.dbg_flags & 2) && blockIdx.x == 0 && warp == 0 && lane == 0;
         int useq = 0;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
@@ -348,10 +366,12 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
             const int j = rb * TC_BM + r * 128 + trow;
             // Rows beyond J (zero-filled by the TMA) would tie on EVERY column (x = sigma^2 |r_k|^2) and drag their warp
             // through the slow path at every step; their lists are never read, so they never look at anything.
-            const bool dead = j >= P.J || (P.dbg_flags & 1);
+            const bool dead = j >= P.J || (TC_TRACE && (P.dbg_flags & 1));
             float thr = dead ? -INFINITY : INFINITY;
             const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
-            const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C);
+            const float xmb = P.xm[b];
+            const bool aug = xmb < 0.f;
+            const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C) + fmaxf(xmb, 0.f);
             if (P.prior != nullptr && !dead) {
                 // x of the prior match from the same fp16 operands the tensor core sees.  The two fp32 accumulations (80
                 // products each, different order) differ by less than the accumulation term of eps plus a quarter of it,
@@ -374,7 +394,7 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                         }
                     }
                     const float sg = P.scale[b];
-                    thr = __fmaf_rn(P.nr[(size_t)b * P.K + kp], sg * sg, acc) + 2.0f * margin;
+                    thr = (aug ? __fmaf_rn(P.nr[(size_t)b * P.K + kp], sg * sg, acc) : acc) + 2.0f * margin;
                 }
             }
             for (int t = 0; t < us.total(); ++t) {
@@ -393,15 +413,17 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                     tmem_wait32(va);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 1] = (unsigned int)clock64();
                     tmem_ld32(tbase + (g + 1) * 32, vb);
-                    filter32<false>(va, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci, sample, best);
+                    if (!aug && col0 + (g + 1) * 32 > P.K) mask_cols(va, col0 + g * 32, P.K);
+                    filter32<false>(va, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci, sample, best, P.K);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 2] = (unsigned int)clock64();
                     tmem_wait32(vb);
                     if (g + 2 < TC_STEPS) tmem_ld32(tbase + (g + 2) * 32, va);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 3] = (unsigned int)clock64();
+                    if (!aug && col0 + (g + 2) * 32 > P.K) mask_cols(vb, col0 + (g + 1) * 32, P.K);
                     if (g + 2 < TC_STEPS)
-                        filter32<false>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best);
+                        filter32<false>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best, P.K);
                     else   // last step: the accumulator is handed back from inside (right after the vote)
-                        filter32<true>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best,
+                        filter32<true>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best, P.K,
                                        &tmem_empty[pa.stage * TC_RBS + r], lane);
                 }
                 if (tracing && useq < 256) P.trace[1024 + useq * 8 + 4] = (unsigned int)clock64();
@@ -491,6 +513,33 @@ __global__ __launch_bounds__(256) void tc_prep_kernel(dsir_feat f, int C, int N,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// With (nearly) constant reference norms - the features are L2-normalised upstream, network/model.py:233-234 - the
+// term sigma^2 |r_k|^2 shifts a whole row of x by a constant and cannot change the argmin: the filter then works on
+// x' = -2 sigma^2 <s_j, r_k> (4 MMAs per tile instead of 5, no norm tile traffic) and widens every margin by the spread
+// sigma^2 (max_k |r_k|^2 - min_k |r_k|^2): a column whose x is within margin of the row minimum of x has its x' within
+// margin + spread of the minimum of x'.  Exactness is untouched (the refine step re-scores with the exact norms).
+// Chosen per batch element on the device; beyond TC_NOAUG_SPREAD (2^-14, ~6 % of the smallest margin of unit features)
+// the norm stays folded in.  One block per batch element.
+// ---------------------------------------------------------------------------------------------------------
+constexpr float TC_NOAUG_SPREAD = 6.1035e-5f;
+__global__ __launch_bounds__(256) void tc_spread_kernel(const float *__restrict__ nr, int K, const float *__restrict__ rmax,
+                                                        const float *__restrict__ amax, float *__restrict__ xm) {
+    __shared__ float s_min[8];
+    const int b = blockIdx.x;
+    float m = INFINITY;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) m = fminf(m, nr[(size_t)b * K + k]);
+    m = warp_min(m);
+    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fminf(m, s_min[w]);
+        const float sg = tc_sigma(amax[b]);
+        const float spread = __fmul_rn(__fmul_rn(sg, sg), rmax[b] - m) * 1.0001f;
+        xm[b] = (spread >= 0.f && spread <= TC_NOAUG_SPREAD) ? spread : -1.f;   // NaN / inf norms keep the folded norm
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // refine: one thread per source row.  Candidates within margin of the row's approximate minimum are the only
 // columns that can hold the exact fp32 minimum.  A single such candidate IS the answer (no arithmetic needed unless
 // the caller wants the distance); several are re-scored with the exact fp32 op order of match_fp32.cu, reading the
@@ -499,7 +548,7 @@ __global__ __launch_bounds__(256) void tc_prep_kernel(dsir_feat f, int C, int N,
 struct RefineParams {
     int B, J, K, C, S, Jpad;
     dsir_feat fs, fr;
-    const float *ns, *nr, *rmax, *scale;
+    const float *ns, *nr, *rmax, *scale, *xm;
     const float *cand_val;
     const int *cand_idx;
     int64_t *idx;
@@ -529,7 +578,7 @@ __global__ __launch_bounds__(256) void match_tc_refine_kernel(RefineParams P) {
     const float4 *cvp = reinterpret_cast<const float4 *>(P.cand_val + ((size_t)b * P.Jpad + j) * ncand);
     const int4 *cip = reinterpret_cast<const int4 *>(P.cand_idx + ((size_t)b * P.Jpad + j) * ncand);
     const float nsj = P.ns[(size_t)b * P.J + j];
-    const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C);   // candidate values are in scaled units
+    const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C) + fmaxf(P.xm[b], 0.f);   // candidate values are in scaled units
     // pass 1: approximate row minimum over the valid candidates
     float gmin = INFINITY;
     for (int s = 0; s < nlist; ++s) {
@@ -587,7 +636,7 @@ __global__ __launch_bounds__(256) void match_tc_exact_kernel(RefineParams P) {
         const bool valid = k >= 0 && k < P.K && v < 1e38f;
         const float gmin = warp_min(valid ? v : INFINITY);
         const float nsj = P.ns[(size_t)b * P.J + j];
-        const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C);
+        const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C) + fmaxf(P.xm[b], 0.f);
         const bool take = valid && v <= gmin + margin;
         float d = INFINITY;
         int kk = 0x7fffffff;
@@ -682,7 +731,7 @@ __global__ void match_tc_rescue_finalize_kernel(RefineParams P, const unsigned l
 
 struct TcPlan {
     int NKS, RB, U, S, Jpad, Kpad;
-    size_t off_a16, off_b16, off_baug, off_aaug, off_rmax, off_amax, off_scale, off_cval, off_cidx, off_count,
+    size_t off_a16, off_b16, off_baug, off_aaug, off_rmax, off_amax, off_scale, off_xm, off_cval, off_cidx, off_count,
         off_rows, off_erows, off_keys, off_dbg, off_trace, total;
 };
 
@@ -711,6 +760,7 @@ TcPlan make_plan(int B, int C, int J, int K) {
     p.off_rmax = take((size_t)B * 4);
     p.off_amax = take((size_t)B * 4);
     p.off_scale = take((size_t)B * 4);
+    p.off_xm = take((size_t)B * 4);
     p.off_cval = take((size_t)B * p.Jpad * S * TC_LISTS * TC_T * 4);
     p.off_cidx = take((size_t)B * p.Jpad * S * TC_LISTS * TC_T * 4);
     p.off_count = take(256);
@@ -753,6 +803,7 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     __half *a16 = (__half *)(base + pl.off_a16), *b16 = (__half *)(base + pl.off_b16);
     __half *baug = (__half *)(base + pl.off_baug), *aaug = (__half *)(base + pl.off_aaug);
     float *rmax = (float *)(base + pl.off_rmax), *amax = (float *)(base + pl.off_amax), *scale = (float *)(base + pl.off_scale);
+    float *xm = (float *)(base + pl.off_xm);
     float *cval = (float *)(base + pl.off_cval);
     int *cidx = (int *)(base + pl.off_cidx), *count = (int *)(base + pl.off_count), *rows = (int *)(base + pl.off_rows);
 
@@ -768,6 +819,8 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
         DSIR_LAUNCH_CHECK();
         tc_prep_kernel<<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, amax, P.nr, -2.0f, b16, baug, nullptr, nullptr);
         DSIR_LAUNCH_CHECK();
+        tc_spread_kernel<<<P.B, 256, 0, st>>>(P.nr, P.K, rmax, amax, xm);
+        DSIR_LAUNCH_CHECK();
     }
     CUtensorMap mapA, mapB, mapAaug, mapBaug;
     if (!make_f16_tmap(&mapA, a16, P.B, P.J, TC_CH, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
@@ -778,11 +831,15 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
 
     TcParams T{};
     T.B = P.B; T.J = P.J; T.K = P.K; T.C = P.C; T.RB = pl.RB; T.U = pl.U; T.S = pl.S;
-    T.Jpad = pl.Jpad; T.Kpad = pl.Kpad; T.ns = P.ns; T.rmax = rmax; T.scale = scale; T.cand_val = cval; T.cand_idx = cidx;
+    T.Jpad = pl.Jpad; T.Kpad = pl.Kpad; T.ns = P.ns; T.rmax = rmax; T.scale = scale; T.xm = xm; T.cand_val = cval; T.cand_idx = cidx;
     T.dbg = (unsigned long long *)(base + pl.off_dbg);
     T.trace = (unsigned int *)(base + pl.off_trace);
+    T.dbg_flags = 0;
+    T.prime_div = 8;
+#ifdef DSIR_TC_TRACE
     { const char *e = getenv("DSIR_TC_DEBUG"); T.dbg_flags = e ? atoi(e) : 0; }
     { const char *e = getenv("DSIR_TC_PRIME"); T.prime_div = e ? atoi(e) : 8; }
+#endif
     T.prior = P.prior_idx; T.a16 = a16; T.b16 = b16; T.nr = P.nr;
     if (T.prior) T.prime_div = 0;
     const int items = P.B * pl.RB * pl.S;
@@ -807,7 +864,7 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
 
     RefineParams R{};
     R.B = P.B; R.J = P.J; R.K = P.K; R.C = P.C; R.S = pl.S; R.Jpad = pl.Jpad;
-    R.fs = P.fs; R.fr = P.fr; R.ns = P.ns; R.nr = P.nr; R.rmax = rmax; R.scale = scale; R.cand_val = cval; R.cand_idx = cidx;
+    R.fs = P.fs; R.fr = P.fr; R.ns = P.ns; R.nr = P.nr; R.rmax = rmax; R.scale = scale; R.xm = xm; R.cand_val = cval; R.cand_idx = cidx;
     R.idx = P.idx; R.min_d = P.min_d; R.rescue_count = count; R.exact_count = count + 1; R.rescue_rows = rows;
     R.exact_rows = (int *)(base + pl.off_erows);
     R.rescue_keys = (unsigned long long *)(base + pl.off_keys);
@@ -865,6 +922,7 @@ int match_tc_filter_timing(const void *ws, int B, int C, int J, int K, double *o
 //   [ 1024 + useq*8 + k ]      epilogue warp 0: k=0 full seen, 1 first 32 columns in registers, 2 first step done,
 //                              3 second 32 columns in registers, 4 second step done, 5 accumulator released
 int match_tc_filter_trace(const void *ws, int B, int C, int J, int K, unsigned int *out, cudaStream_t st) {
+    if (!TC_TRACE) return DSIR_ERR_UNSUPPORTED;   // only in -DDSIR_TC_TRACE builds
     const TcPlan pl = make_plan(B, C, J, K);
     const char *base = (const char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     DSIR_CUDA_TRY(cudaMemcpyAsync(out, base + pl.off_trace, 4096 * 4, cudaMemcpyDeviceToHost, st));

@@ -101,6 +101,7 @@ struct SoftParams {
     const float *scale;      // [B] sigma (power of two): the accumulator holds sigma^2 (|r|^2 - 2<s,r>)
     const float *xtile;      // [B][U][512]: per unit (x, y)[128] | z[128] | bias * log2e [128]
     float *part;             // [B][Jpad][S][8]: m, l, sx, sy, sz (log2 domain)
+    const unsigned char *exact;   // [B] 1: this batch element is served by the exact fp32 kernel instead (see soft_pick_kernel)
 };
 
 // one 16-column step of the online softmax of one row: v = accumulator values x_jk = |r_k|^2 - 2<s_j,r_k>.
@@ -216,6 +217,7 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
             bool first = true;
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
                 const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
+                if (P.exact[b]) continue;                       // (every role skips the same items)
                 const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
                 mbar_wait(empty_a, iphase ^ 1u);
                 mbar_expect_tx(full_a, SF_RBS * SF_CHUNKS * SF_TILE + (first ? SF_AUGT : 0u));
@@ -255,6 +257,7 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
         constexpr uint32_t HI = 0, LO = Cfg::LO_OFF;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int sp = it % P.S;
+            if (P.exact[it / (P.S * P.RB)]) continue;
             const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
             mbar_wait(full_a, iphase);
             for (int u = u0; u < u1; ++u) {
@@ -292,6 +295,7 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
         uint32_t aphase = 0;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int sp = it % P.S, rb = (it / P.S) % P.RB, b = it / (P.S * P.RB);
+            if (P.exact[b]) continue;
             const int u0 = (int)((long long)sp * P.U / P.S), u1 = (int)((long long)(sp + 1) * P.U / P.S);
             const int j = rb * SF_BM + r * 128 + trow;
             const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
@@ -351,10 +355,11 @@ __global__ __launch_bounds__(SF_THREADS, 1) void match_tc_soft_kernel(const __gr
 
 // merge the partial (max, sum, weighted sums) of a row: lse = ln sum_k exp(a_jk), y = sum_k w_jk r_k / sum_k w_jk
 __global__ void soft_finalize_kernel(const float *__restrict__ part, int B, int J, int Jpad, int nparts, float *__restrict__ lse,
-                                     float *__restrict__ y_soft) {
+                                     float *__restrict__ y_soft, const unsigned char *__restrict__ exact) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (long long)B * J) return;
     const int b = (int)(row / J), j = (int)(row % J);
+    if (exact[b]) return;   // written by the fp32 kernel
     const float *p = part + ((size_t)b * Jpad + j) * nparts * 8;
     float m = -INFINITY;
     for (int i = 0; i < nparts; ++i) m = fmaxf(m, p[i * 8]);
@@ -446,8 +451,19 @@ __global__ void soft_xtile_kernel(const float *__restrict__ xyz, const float *__
 
 struct SoftPlan {
     int RB, U, S, Jpad, Kpad;
-    size_t off_ns, off_nr, off_a, off_b, off_baug, off_aaug, off_amax, off_scale, off_xyzc, off_bias, off_part, total;
+    size_t off_ns, off_nr, off_a, off_b, off_baug, off_aaug, off_amax, off_scale, off_xyzc, off_bias, off_part, off_exact, total;
 };
+
+// The two-half fp16 split leaves |delta d| ~ 1-2e-6 * max|f|^2 on a distance, i.e. a relative error of beta * |delta d| on
+// every weight of the row.  Per batch element: beyond beta * max|f|^2 = SOFT_TC_BOUND the 1e-4 bar is not guaranteed and
+// the element is handed to the exact fp32 kernel - decided on the device, no host synchronisation, no knob.
+constexpr float SOFT_TC_BOUND = 32.f;
+__global__ void soft_pick_kernel(const float *__restrict__ amax, const float *__restrict__ beta, int B, unsigned char *__restrict__ exact) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float v = fabsf(beta[b]) * amax[b];
+    exact[b] = (v <= SOFT_TC_BOUND) ? 0 : 1;   // NaN / inf -> exact kernel
+}
 
 SoftPlan make_soft_plan(int B, int C, int J, int K) {
     const int SF_CH = C > 32 ? SoftCfg<true>::CH : SoftCfg<false>::CH;
@@ -478,6 +494,7 @@ SoftPlan make_soft_plan(int B, int C, int J, int K) {
     p.off_xyzc = take((size_t)B * p.Kpad * 16);
     p.off_bias = take(256);
     p.off_part = take((size_t)B * p.Jpad * S * 8 * 4);
+    p.off_exact = take((size_t)B);
     p.total = off + 1024;
     return p;
 }
@@ -493,8 +510,6 @@ constexpr size_t soft_smem_bytes() {
 bool match_tc_soft_supported(int B, int C, int J, int K) {
     if (C < 1 || C > SoftCfg<true>::CMAX) return false;
     if ((long long)B * J >= (1ll << 31) || (long long)B * K >= (1ll << 31)) return false;
-    static const bool off = getenv("DSIR_SOFT_FP32") != nullptr;
-    if (off) return false;
     if ((double)B * J * K < 2.0e6) return false;   // tiny problems: the prep launches dominate
     return tc_encode_fn() != nullptr;
 }
@@ -515,6 +530,7 @@ int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaSt
     float *amax = (float *)(base + pl.off_amax), *scale = (float *)(base + pl.off_scale);
     float *xtile = (float *)(base + pl.off_xyzc);
     float *part = (float *)(base + pl.off_part);
+    unsigned char *exact = (unsigned char *)(base + pl.off_exact);
     int rc;
     if (!P.reuse_prep) {   // (a sweep of Sinkhorn re-uses the operands of its previous sweep: only the bias changes)
         DSIR_CUDA_TRY(cudaMemsetAsync(amax, 0, (size_t)P.B * 4, st));
@@ -528,6 +544,8 @@ int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaSt
         else soft_prep_kernel<false><<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, 1, amax, nr, bexp, baug, nullptr, nullptr);
         DSIR_LAUNCH_CHECK();
     }
+    soft_pick_kernel<<<cdiv(P.B, 128), 128, 0, st>>>(amax, P.beta, P.B, exact);
+    DSIR_LAUNCH_CHECK();
     soft_xtile_kernel<<<dim3(cdiv(pl.Kpad, 256), P.B), 256, 0, st>>>(P.y_soft ? P.xyz_ref : nullptr, P.col_bias, P.K, pl.Kpad, xtile);
     DSIR_LAUNCH_CHECK();
     CUtensorMap mapA, mapB, mapAaug, mapBaug;
@@ -538,7 +556,7 @@ int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaSt
         return DSIR_ERR_UNSUPPORTED;
     SoftParams T{};
     T.B = P.B; T.J = P.J; T.K = P.K; T.C = P.C; T.RB = pl.RB; T.U = pl.U; T.S = pl.S; T.Jpad = pl.Jpad; T.Kpad = pl.Kpad;
-    T.ns = ns; T.beta = P.beta; T.alpha = P.alpha; T.scale = scale; T.xtile = xtile; T.part = part;
+    T.ns = ns; T.beta = P.beta; T.alpha = P.alpha; T.scale = scale; T.xtile = xtile; T.part = part; T.exact = exact;
     const int items = P.B * pl.RB * pl.S;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -557,9 +575,12 @@ int launch_match_tc_soft(const MatchParams &P, void *ws, size_t ws_bytes, cudaSt
 #undef DSIR_SOFT_LAUNCH
     DSIR_LAUNCH_CHECK();
     const long long rows = (long long)P.B * P.J;
-    soft_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(part, P.B, P.J, pl.Jpad, pl.S, P.lse, P.y_soft);
+    soft_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(part, P.B, P.J, pl.Jpad, pl.S, P.lse, P.y_soft, exact);
     DSIR_LAUNCH_CHECK();
-    return DSIR_OK;
+    // batch elements beyond the accuracy bound of the split: the exact fp32 kernel, whose CTAs leave at once elsewhere
+    MatchParams E = P;
+    E.ns = ns; E.nr = nr; E.only_flagged = exact;
+    return launch_match_fp32(E, MATCH_MODE_SOFT, st);
 }
 
 }  // namespace dsir

@@ -88,6 +88,19 @@ def forward_align_4(self, data, opt=None):
     return transforms, endpoints
 
 
+def _compute_rigid_transform_2(src, tgt, weights):
+    """Leaf-level binding: the reference's loop does `invalid_gradient or cur_invalid_gradient` on a real bool
+    (model.py:596); the lazy device flag is resolved here (one sync per iteration, where the reference has its own:
+    the fp64 SVD on the host, model.py:47)."""
+    T, flag = _K.compute_rigid_transform_2(src, tgt, weights)
+    return T, bool(flag)
+
+
+def _compute_rigid_transform(src, tgt, weights):
+    T, flag = _K.compute_rigid_transform(src, tgt, weights)
+    return T, bool(flag)
+
+
 def patch(ref_root=None, level="loop"):
     """Rebind the hot-path names inside the reference's `network.model` (imported from sys.path or `ref_root`).
     Returns the module.  Idempotent."""
@@ -100,8 +113,8 @@ def patch(ref_root=None, level="loop"):
         _saved["forward_align_4"] = mod.Network.forward_align_4
     mod.match_features_V2 = _M.match_features_V2
     mod.gather_neighbour_V3 = _M.gather_neighbour_V3
-    mod.compute_rigid_transform_2 = _K.compute_rigid_transform_2
-    mod.compute_rigid_transform = _K.compute_rigid_transform
+    mod.compute_rigid_transform_2 = _compute_rigid_transform_2
+    mod.compute_rigid_transform = _compute_rigid_transform
     mod.se3_torch = _se3
     mod.Network.forward_align_4 = forward_align_4 if level == "loop" else _saved["forward_align_4"]
     return mod

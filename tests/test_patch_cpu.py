@@ -22,7 +22,7 @@ def test_patch_rebinds_and_restores():
     fwd = M.Network.forward_align_4
     assert P.patch() is M
     assert M.match_features_V2 is D.match_features_V2 and M.gather_neighbour_V3 is D.gather_neighbour_V3
-    assert M.compute_rigid_transform_2 is D.compute_rigid_transform_2 and M.se3_torch is D.se3_torch
+    assert M.compute_rigid_transform_2 is P._compute_rigid_transform_2 and M.se3_torch is D.se3_torch
     assert M.Network.forward_align_4 is P.forward_align_4
     P.patch(level="leaf")                       # idempotent; the leaf level keeps the reference's own loop
     assert M.Network.forward_align_4 is fwd and M.match_features_V2 is D.match_features_V2
