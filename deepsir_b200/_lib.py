@@ -175,6 +175,11 @@ def require_cuda(*tensors: torch.Tensor) -> torch.device:
             dev = t.device
         elif t.device != dev:
             raise DeepSIRError("all tensors must live on the same CUDA device")
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        # the library launches on the process's CURRENT device (one process per GPU): make it explicit instead of failing
+        # later with an invalid-resource-handle
+        raise DeepSIRError(f"tensors live on cuda:{dev.index} but the current device is cuda:{torch.cuda.current_device()}: "
+                           "call torch.cuda.set_device() (one process per GPU)")
     return dev
 
 

@@ -149,16 +149,9 @@ __device__ __forceinline__ void release_acc(uint64_t *empty_bar, int lane) {
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar);
 }
-// Without the folded norm (TcParams::xm >= 0) the zero-filled reference rows beyond K read x' = 0 instead of a huge padded
-// norm: the unit that holds them masks those columns to +inf before the minimum tree (and the slow path checks the column).
-__device__ __forceinline__ void mask_cols(uint32_t (&v)[32], int col0, int K) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-        if (col0 + i >= K) v[i] = 0x7f800000u;
-}
 template <bool LAST>
 __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint32_t taddr, float margin, float &thr,
-                                         float (&cv)[TC_T], int (&ci)[TC_T], bool sample, float &best, int kmax,
+                                         float (&cv)[TC_T], int (&ci)[TC_T], bool sample, float &best,
                                          uint64_t *empty_bar = nullptr, int lane = 0) {
 #define F(i) __uint_as_float(v[i])
     const float a0 = fmin3(F(0), F(1), F(2)), a1 = fmin3(F(3), F(4), F(5)), a2 = fmin3(F(6), F(7), F(8));
@@ -190,7 +183,7 @@ __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint
             if ((qm >> g) & 1u) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (x[e] <= thr && col0 + 4 * g + e < kmax) cand_update(cv, ci, x[e], col0 + 4 * g + e, margin, thr);
+                    if (x[e] <= thr) cand_update(cv, ci, x[e], col0 + 4 * g + e, margin, thr);
             }
         }
         if (LAST) release_acc(empty_bar, lane);
@@ -413,17 +406,15 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                     tmem_wait32(va);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 1] = (unsigned int)clock64();
                     tmem_ld32(tbase + (g + 1) * 32, vb);
-                    if (!aug && col0 + (g + 1) * 32 > P.K) mask_cols(va, col0 + g * 32, P.K);
-                    filter32<false>(va, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci, sample, best, P.K);
+                    filter32<false>(va, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci, sample, best);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 2] = (unsigned int)clock64();
                     tmem_wait32(vb);
                     if (g + 2 < TC_STEPS) tmem_ld32(tbase + (g + 2) * 32, va);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 3] = (unsigned int)clock64();
-                    if (!aug && col0 + (g + 2) * 32 > P.K) mask_cols(vb, col0 + (g + 1) * 32, P.K);
                     if (g + 2 < TC_STEPS)
-                        filter32<false>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best, P.K);
+                        filter32<false>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best);
                     else   // last step: the accumulator is handed back from inside (right after the vote)
-                        filter32<true>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best, P.K,
+                        filter32<true>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best,
                                        &tmem_empty[pa.stage * TC_RBS + r], lane);
                 }
                 if (tracing && useq < 256) P.trace[1024 + useq * 8 + 4] = (unsigned int)clock64();
@@ -519,7 +510,8 @@ __global__ __launch_bounds__(256) void tc_prep_kernel(dsir_feat f, int C, int N,
 // sigma^2 (max_k |r_k|^2 - min_k |r_k|^2): a column whose x is within margin of the row minimum of x has its x' within
 // margin + spread of the minimum of x'.  Exactness is untouched (the refine step re-scores with the exact norms).
 // Chosen per batch element on the device; beyond TC_NOAUG_SPREAD (2^-14, ~6 % of the smallest margin of unit features)
-// the norm stays folded in.  One block per batch element.
+// the norm stays folded in - and so it does when K is not a multiple of the 128-column unit: the zero-filled reference rows
+// beyond K rely on their huge padded norm to stay out of the candidate lists.  One block per batch element.
 // ---------------------------------------------------------------------------------------------------------
 constexpr float TC_NOAUG_SPREAD = 6.1035e-5f;
 __global__ __launch_bounds__(256) void tc_spread_kernel(const float *__restrict__ nr, int K, const float *__restrict__ rmax,
@@ -535,7 +527,10 @@ __global__ __launch_bounds__(256) void tc_spread_kernel(const float *__restrict_
         for (int w = 1; w < 8; ++w) m = fminf(m, s_min[w]);
         const float sg = tc_sigma(amax[b]);
         const float spread = __fmul_rn(__fmul_rn(sg, sg), rmax[b] - m) * 1.0001f;
-        xm[b] = (spread >= 0.f && spread <= TC_NOAUG_SPREAD) ? spread : -1.f;   // NaN / inf norms keep the folded norm
+        xm[b] = (spread >= 0.f && spread <= TC_NOAUG_SPREAD && K % TC_BN == 0) ? spread : -1.f;   // NaN / inf norms keep the folded norm
+#ifdef DSIR_TC_FORCE_AUG   // development builds: always fold the norm in (A/B of the 4-MMA mode)
+        xm[b] = -1.f;
+#endif
     }
 }
 

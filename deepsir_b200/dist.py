@@ -101,3 +101,46 @@ def align_rowblock(feat_src_local, feat_ref, xyz_src_local, xyz_ref, weights_loc
         preds.append(gather_rows(idx, gather_pred_rows, group) if gather_pred_rows else idx)
         stats.append(st)
     return transforms, preds, xyz, stats
+
+
+class GraphedRowBlock:
+    """`num_iter` iterations of align_rowblock for FIXED shapes, captured once in a CUDA graph and replayed: the rank's
+    ~20 small launches and the NCCL all_reduce of the moments become one graph launch, which is what a 16384-row block
+    (0.3 ms of match work per rank at C4 on 8 GPUs) needs to keep scaling.  Inputs are static copies; `step()` replays and
+    returns (T [B,3,4] cumulative, idx [B,Jl], xyz_src_local) as static tensors.  Falls back to eager execution when the
+    capture is refused (`self.graphed` says which)."""
+
+    def __init__(self, feat_src_local, feat_ref, xyz_src_local, xyz_ref, weights_local, num_iter=1, group=None):
+        self.args = [t.detach().clone().contiguous() for t in (feat_src_local, feat_ref, xyz_src_local, xyz_ref, weights_local)]
+        self.num_iter, self.group = num_iter, group
+        dev = self.args[0].device
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):            # warm-up outside the capture (NCCL channels, stream pools, attributes)
+            for _ in range(3):
+                self._run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph, self.graphed = None, False
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self.out = self._run()
+            self.graph, self.graphed = g, True
+        except Exception as e:                   # noqa: BLE001 - report and run eagerly
+            self.error = repr(e)
+            torch.cuda.synchronize(dev)
+            self.out = self._run()
+
+    def _run(self):
+        fs, fr, xs, xr, w = self.args
+        tr, pred, xyz, st = align_rowblock(fs, fr, xs, xr, w, self.num_iter, group=self.group)
+        return tr[-1], pred[-1], xyz
+
+    def step(self):
+        if self.graphed:
+            self.graph.replay()
+        else:
+            self.out = self._run()
+        return self.out

@@ -34,8 +34,9 @@ def nn_search_cloud(points, num_knn=16, sub_sampling_ratio=(4, 4, 4, 4), algo=L.
     dev = L.require_cuda(points)
     if points.dtype != torch.float32:
         raise L.DeepSIRError("nn_search expects float32 points")
-    p = points if points.is_contiguous() else points.contiguous()
-    B, N, S = p.shape
+    p = _rows_view(points)
+    B, N = p.shape[0], p.shape[1]
+    S = p.stride(1) if N > 1 else p.shape[2]
     ratios = [int(r) for r in sub_sampling_ratio]
     Lv = len(ratios)
     sumN, sumSub, n = 0, 0, N
@@ -58,6 +59,15 @@ def nn_search_cloud(points, num_knn=16, sub_sampling_ratio=(4, 4, 4, 4), algo=L.
     return dict(xyz=xyz, neigh_idx=neigh, sub_idx=sub, interp_idx=interp)
 
 
+def _rows_view(points):
+    """[B,N,C>=3] tensor whose rows the library can address with one point stride: contiguous, or an inner slice such as
+    data['points_src'][:, :, :3] (data_base.py:159) - passed by stride, not copied; anything else is made contiguous."""
+    B, N, C = points.shape
+    if points.stride(2) == 1 and (N <= 1 or (points.stride(1) >= C and (B <= 1 or points.stride(0) == N * points.stride(1)))):
+        return points
+    return points.contiguous()
+
+
 _side_streams = {}
 
 
@@ -74,6 +84,8 @@ def nn_search_pair(points_src, points_ref, num_knn=16, sub_sampling_ratio=(4, 4,
     # caching allocator to track); only the kernels of the reference pyramid run on the side stream, between a fork
     # (side waits for everything enqueued so far) and a join (the caller's stream waits for the side stream).
     keep = []
+    # a copy made here (non-viewable input) is enqueued on the caller's stream BEFORE the fork, so the side stream sees it
+    points_src, points_ref = _rows_view(points_src), _rows_view(points_ref)
     side.wait_stream(cur)                                                       # fork
     g_ref = nn_search_cloud(points_ref, num_knn, sub_sampling_ratio, algo, _stream=side, _keep=keep)
     g_src = nn_search_cloud(points_src, num_knn, sub_sampling_ratio, algo)

@@ -24,6 +24,9 @@ class RegistrationPipeline:
     weights [B,N].  `run(batches)` yields, in order, dicts with host tensors
     T [B,3,4] (final cumulative transform), pred [B,N] int32 (last correspondences, the `pred_pairs` of
     network/model.py:599-601) and status [iters,B]; with keep_graph=True also the device KNN tensors of the batch.
+    The host tensors of a yielded dict come from a ring of pinned buffers and are re-used depth + 2 batches later.
+    A batch may carry features that are ALREADY on the device (feat_src / feat_ref as CUDA tensors - behind
+    Network.forward they are produced there): only the host tensors are uploaded.
     """
 
     def __init__(self, device=None, num_knn=16, sub_sampling_ratio=(4, 4, 4, 4), iters=1, depth=2, keep_graph=False):
@@ -32,14 +35,29 @@ class RegistrationPipeline:
             raise L.DeepSIRError("RegistrationPipeline runs on a CUDA device only")
         self.k, self.ratios, self.iters, self.depth, self.keep_graph = num_knn, tuple(sub_sampling_ratio), iters, depth, keep_graph
         self.copy_stream = torch.cuda.Stream(self.dev)
+        # pinned result buffers: a ring of depth + 2 sets, allocated once per shape (cudaHostAlloc is far too slow for the
+        # steady-state loop).  A yielded set is overwritten depth + 2 batches later: copy what must outlive that.
+        self._ring, self._ring_shape, self._ring_pos = [], None, 0
+
+    def _host_out(self, B, N):
+        if self._ring_shape != (B, N):
+            self._ring = [dict(T=torch.empty(B, 3, 4, dtype=torch.float32, pin_memory=True),
+                               pred=torch.empty(B, N, dtype=torch.int32, pin_memory=True),
+                               status=torch.empty(self.iters, B, dtype=torch.int32, pin_memory=True))
+                          for _ in range(self.depth + 2)]
+            self._ring_shape, self._ring_pos = (B, N), 0
+        out = dict(self._ring[self._ring_pos])
+        self._ring_pos = (self._ring_pos + 1) % len(self._ring)
+        return out
 
     def _upload(self, host, compute):
         with torch.cuda.stream(self.copy_stream):
-            d = {k: v.to(self.dev, non_blocking=True) for k, v in host.items()}
+            d = {k: (v if v.is_cuda else v.to(self.dev, non_blocking=True)) for k, v in host.items()}
             up = torch.cuda.Event()
             up.record(self.copy_stream)
-        for v in d.values():
-            v.record_stream(compute)   # the compute stream reads them: keep the allocator from recycling early
+        for k, v in d.items():
+            if not host[k].is_cuda:
+                v.record_stream(compute)   # the compute stream reads them: keep the allocator from recycling early
         return d, up
 
     def _compute(self, d, up, compute):
@@ -49,9 +67,7 @@ class RegistrationPipeline:
         xr = d["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
         tr, pred, _, status = align_loop(d["feat_src"], d["feat_ref"], xs, xr, d["weights"], self.iters)
         B, N = pred[-1].shape
-        out = dict(T=torch.empty(B, 3, 4, dtype=torch.float32, pin_memory=True),
-                   pred=torch.empty(B, N, dtype=torch.int32, pin_memory=True),
-                   status=torch.empty(self.iters, B, dtype=torch.int32, pin_memory=True))
+        out = self._host_out(B, N)
         out["T"].copy_(tr[-1], non_blocking=True)
         out["pred"].copy_(pred[-1].to(torch.int32), non_blocking=True)
         out["status"].copy_(status, non_blocking=True)

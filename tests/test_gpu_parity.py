@@ -72,6 +72,22 @@ def test_knn_pyramid_matches_nn_search(algo):
     assert d["points_src_neigh_idx"].dtype == torch.int64 and d["points_ref_interp_idx"].shape == (2, 5440, 1)
 
 
+def test_nn_search_pair_strided_views_and_side_stream():
+    """data['points_src'][:, :, :3] (the slice DataBase.nn_search makes, data_base.py:159) is an inner-sliced view: it is
+    passed by stride; a view that cannot be addressed with one point stride is copied BEFORE the fork of the side stream
+    (otherwise the reference pyramid could read an unfinished copy)."""
+    b = synth.make_batch(3, 3000, 8, "kitti", config=1, first_pair=21)
+    wide_s = torch.cat([b["points_src"], torch.randn(3, 3000, 2)], 2)            # [B,N,6]
+    wide_r = torch.cat([b["points_ref"], torch.randn(3, 3000, 2)], 2)
+    g_s, g_r = D.nn_search_pair(cu(b["points_src"][:, :, :3].contiguous()), cu(b["points_ref"][:, :, :3].contiguous()))
+    v_s, v_r = D.nn_search_pair(cu(wide_s)[:, :, :3], cu(wide_r)[:, :, :3])      # strided views, no copy
+    t_s, t_r = D.nn_search_pair(cu(wide_s).permute(0, 2, 1).contiguous().permute(0, 2, 1)[:, :, :3],
+                                cu(wide_r)[:, ::1, :3].flip(1).flip(1))            # needs a copy
+    for name in ("xyz", "neigh_idx", "sub_idx", "interp_idx"):
+        assert torch.equal(v_s[name], g_s[name]) and torch.equal(v_r[name], g_r[name]), name
+        assert torch.equal(t_s[name], g_s[name]) and torch.equal(t_r[name], g_r[name]), name
+
+
 def test_knn_grid_degenerate_clouds():
     """Grid path on shapes that stress the cell sizing: tiny clouds, all points identical, collinear points,
     points on a plane, a far outlier (huge bounding box), k = 32."""
