@@ -278,7 +278,7 @@ def measure_rowblock(D, dist, dev, rank, world, ev, barrier, n=131072, steps=10)
         ang = O.rotation_angle_deg(Ts[0].cpu()[:, :, :3], tr[-1].cpu()[:, :, :3]).max().item()
         dtr = (Ts[0].cpu()[:, :, 3] - tr[-1].cpu()[:, :, 3]).norm(dim=1).max().item()
         res = {"workload": f"C4: one {n} x {n} D={FEAT_D} pair, source rows sharded over {world} ranks, NCCL all_reduce of fp64 "
-                           "moments, iteration captured in a CUDA graph" + ("" if g.graphed else " (capture refused: eager)"),
+                           "moments, the rank's kernels of an iteration captured in two CUDA graphs around the eager all_reduce" + ("" if g.graphed else " (capture refused: eager)"),
                "ms_per_pair": ms_n, "pairs_per_s": 1e3 / ms_n, "ms_per_pair_n1": ms_1, "eff_vs_n1": ms_1 / (world * ms_n),
                "T_identical_across_ranks": bool(identical), "vs_unsharded_deg": ang, "vs_unsharded_m": dtr,
                "graphed": bool(g.graphed), "scaling": "strong"}

@@ -104,43 +104,63 @@ def align_rowblock(feat_src_local, feat_ref, xyz_src_local, xyz_ref, weights_loc
 
 
 class GraphedRowBlock:
-    """`num_iter` iterations of align_rowblock for FIXED shapes, captured once in a CUDA graph and replayed: the rank's
-    ~20 small launches and the NCCL all_reduce of the moments become one graph launch, which is what a 16384-row block
-    (0.3 ms of match work per rank at C4 on 8 GPUs) needs to keep scaling.  Inputs are static copies; `step()` replays and
-    returns (T [B,3,4] cumulative, idx [B,Jl], xyz_src_local) as static tensors.  Falls back to eager execution when the
-    capture is refused (`self.graphed` says which)."""
+    """`num_iter` iterations of align_rowblock for FIXED shapes with the rank's kernels captured in CUDA graphs: per
+    iteration ONE graph for match + gather + moments and ONE for solve + transform + compose, the NCCL all_reduce of the
+    [B,17] moments issued eagerly between the two (collectives stay outside the graphs: a graph that holds NCCL kernels
+    was measured to stall the process-group teardown for minutes).  A 16384-row block is 0.3 ms of match work per rank at
+    C4 on 8 GPUs - the ~20 small launches of an eager iteration no longer fit beside it.  Inputs are static copies;
+    `step()` returns (T [B,3,4] cumulative, idx [B,Jl] of the last iteration, xyz_src_local) as static tensors.  Falls
+    back to eager execution when the capture is refused (`self.graphed` says which)."""
 
-    def __init__(self, feat_src_local, feat_ref, xyz_src_local, xyz_ref, weights_local, num_iter=1, group=None):
-        self.args = [t.detach().clone().contiguous() for t in (feat_src_local, feat_ref, xyz_src_local, xyz_ref, weights_local)]
-        self.num_iter, self.group = num_iter, group
-        dev = self.args[0].device
+    def __init__(self, feat_src_local, feat_ref, xyz_src_local, xyz_ref, weights_local, num_iter=1, group=None, ops=None):
+        self.fs, self.fr, self.xyz0, self.xr, self.w = [t.detach().clone().contiguous() for t in
+                                                        (feat_src_local, feat_ref, xyz_src_local, xyz_ref, weights_local)]
+        self.w = self.w.reshape(self.w.shape[0], -1)
+        self.num_iter, self.group, self.ops = num_iter, group, ops or LibraryOps
+        dev = self.fs.device
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):            # warm-up outside the capture (NCCL channels, stream pools, attributes)
             for _ in range(3):
-                self._run()
+                self.out = self._eager()
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph, self.graphed = None, False
+        self.graphed, self.segA, self.segB, self.mom = False, [], [], []
         try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self.out = self._run()
-            self.graph, self.graphed = g, True
+            pool = torch.cuda.graph_pool_handle()
+            xyz, Tprev = None, None
+            for it in range(num_iter):
+                gA = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gA, pool=pool):
+                    x_in = self.xyz0.clone() if it == 0 else xyz
+                    idx = self.ops.match_argmin(self.fs, self.fr)
+                    mom = self.ops.moments(x_in, self.xr, idx, self.w)
+                gB = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gB, pool=pool):
+                    T, st = self.ops.solve(mom)
+                    xyz = self.ops.transform(T, x_in)
+                    Tprev = T if it == 0 else self.ops.compose(T, Tprev)
+                self.segA.append(gA); self.segB.append(gB); self.mom.append(mom)
+            self._static = (Tprev, idx, xyz)
+            self.graphed = True
         except Exception as e:                   # noqa: BLE001 - report and run eagerly
             self.error = repr(e)
+            self.graphed = False
             torch.cuda.synchronize(dev)
-            self.out = self._run()
 
-    def _run(self):
-        fs, fr, xs, xr, w = self.args
-        tr, pred, xyz, st = align_rowblock(fs, fr, xs, xr, w, self.num_iter, group=self.group)
+    def _eager(self):
+        tr, pred, xyz, st = align_rowblock(self.fs, self.fr, self.xyz0, self.xr, self.w, self.num_iter, group=self.group,
+                                           ops=self.ops)
         return tr[-1], pred[-1], xyz
 
     def step(self):
-        if self.graphed:
-            self.graph.replay()
-        else:
-            self.out = self._run()
+        if not self.graphed:
+            self.out = self._eager()
+            return self.out
+        for gA, gB, mom in zip(self.segA, self.segB, self.mom):
+            gA.replay()
+            all_reduce_moments(mom, self.group)   # in place on the static tensor, ordered on the current stream
+            gB.replay()
+        self.out = self._static
         return self.out

@@ -27,15 +27,26 @@ def _worker(rank, world, port, out):
         tr, pred, xyz, st = DD.align_rowblock(b["feat_src"][:, :, lo:hi].contiguous().to(dev), fr, xs[:, :, lo:hi].contiguous().to(dev),
                                              xr, w[:, lo:hi].contiguous().to(dev), 3, gather_pred_rows=N)
         T = torch.stack(tr)
+        # the same three iterations captured in a CUDA graph (NCCL all_reduce inside the graph) and replayed twice
+        g = DD.GraphedRowBlock(b["feat_src"][:, :, lo:hi].contiguous().to(dev), fr, xs[:, :, lo:hi].contiguous().to(dev), xr,
+                               w[:, lo:hi].contiguous().to(dev), num_iter=3)
+        g.step()
+        Tg, idxg, _ = g.step()
+        torch.cuda.synchronize()
+        graph_ok = torch.equal(Tg, tr[-1]) and torch.equal(idxg, pred[-1][:, lo:hi])
+        graphed = g.graphed
+        del g, Tg, idxg
         ref = T.clone()
         dist.broadcast(ref, 0)
         same = torch.equal(ref, T)                                                 # every rank solves the same pose
         if rank == 0:
             tr1, pred1, _, _ = D.align_loop(b["feat_src"].to(dev), fr, xs.to(dev), xr, w.to(dev), 3)   # unsharded, one GPU
-            out.put(dict(T=T.cpu(), T1=torch.stack(tr1).cpu(), pred=torch.stack(pred).cpu(), pred1=torch.stack(pred1).cpu(), same=same))
+            out.put(dict(T=T.cpu(), T1=torch.stack(tr1).cpu(), pred=torch.stack(pred).cpu(), pred1=torch.stack(pred1).cpu(), same=same,
+                         graph_ok=graph_ok, graphed=graphed))
         else:
-            out.put(dict(same=same))
+            out.put(dict(same=same, graph_ok=graph_ok, graphed=graphed))
     finally:
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
@@ -54,7 +65,28 @@ def test_rowblock_sharding_two_gpus_nccl():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(r["same"] for r in res)
+    assert all(r["graph_ok"] for r in res), "graph replay differs from the eager row-block loop"
+    print("row-block iteration captured in a CUDA graph:", [r["graphed"] for r in res])
     r0 = next(r for r in res if "T" in r)
     assert torch.equal(r0["pred"], r0["pred1"])                                    # gathered correspondences == unsharded
     assert O.rotation_angle_deg(r0["T"][-1][:, :, :3], r0["T1"][-1][:, :, :3]).max() < 1e-3
     assert (r0["T"][-1][:, :, 3] - r0["T1"][-1][:, :, 3]).abs().max() < 1e-4
+
+
+def test_graphed_rowblock_single_rank_equals_the_loop():
+    """The graph-captured row-block iteration (two graphs per iteration around the all_reduce, here a no-op) replays to the
+    same poses and correspondences as the unsharded library loop."""
+    import deepsir_b200 as D
+    from deepsir_b200 import dist as DD, synth
+    dev = "cuda:0"
+    b = synth.make_batch(2, 5000, 64, "kitti", config=4, first_pair=5)
+    xs = b["points_src"][:, :, :3].permute(0, 2, 1).contiguous().to(dev)
+    xr = b["points_ref"][:, :, :3].permute(0, 2, 1).contiguous().to(dev)
+    fs, fr, w = b["feat_src"].to(dev), b["feat_ref"].to(dev), b["weights"][:, :, 0].contiguous().to(dev)
+    g = DD.GraphedRowBlock(fs, fr, xs, xr, w, num_iter=3)
+    assert g.graphed, getattr(g, "error", "")
+    g.step()
+    T, idx, xyz = g.step()                      # replayed twice: the graph restarts from the initial source cloud
+    tr, pred, xyz1, st = D.align_loop(fs, fr, xs, xr, w, 3)
+    assert torch.equal(idx, pred[-1])
+    assert torch.allclose(T, tr[-1], atol=1e-6) and torch.allclose(xyz, xyz1, atol=1e-4)
