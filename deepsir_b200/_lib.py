@@ -105,6 +105,9 @@ _SIGS = {
     "dsir_sinkhorn_workspace_bytes": (_c.c_size_t, [_c.c_int] * 3),
     "dsir_sinkhorn": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                  _c.c_size_t, _c.c_void_p]),
+    "dsir_log_optimal_transport_workspace_bytes": (_c.c_size_t, [_c.c_int] * 3),
+    "dsir_log_optimal_transport": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
+                                              _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "dsir_kabsch_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int]),
     "dsir_kabsch": (_c.c_int, [Points, Points, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
                                _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),

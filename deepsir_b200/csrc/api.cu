@@ -671,6 +671,21 @@ size_t dsir_sinkhorn_workspace_bytes(int B, int J, int K) {
     return ws_block((size_t)B * J * sizeof(float)) + ws_block((size_t)B * K * sizeof(float)) + 256;
 }
 
+size_t dsir_log_optimal_transport_workspace_bytes(int B, int M, int N) {
+    if (B <= 0 || M <= 0 || N <= 0) return 256;
+    return ws_block((size_t)B * (M + 1) * sizeof(float)) + ws_block((size_t)B * (N + 1) * sizeof(float)) + 256;
+}
+
+int dsir_log_optimal_transport(const float *scores, int B, int M, int N, const float *alpha, int iters, float *out, void *ws,
+                               size_t ws_bytes, dsir_stream_t stream) {
+    if (!scores || !alpha || !out || B <= 0 || M <= 0 || N <= 0 || iters < 0) return DSIR_ERR_BAD_ARG;
+    Workspace W(ws, ws_bytes);
+    float *u = W.take<float>((size_t)B * (M + 1));
+    float *v = W.take<float>((size_t)B * (N + 1));
+    if (!W.ok()) return DSIR_ERR_WORKSPACE;
+    return launch_log_ot(scores, B, M, N, alpha, iters, out, u, v, (cudaStream_t)stream);
+}
+
 int dsir_sinkhorn(const float *log_alpha, int B, int J, int K, int n_iters, int slack, float *out, void *ws, size_t ws_bytes,
                   dsir_stream_t stream) {
     if (!log_alpha || !out || B <= 0 || J <= 0 || K <= 0 || n_iters < 0) return DSIR_ERR_BAD_ARG;

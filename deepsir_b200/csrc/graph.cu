@@ -144,7 +144,90 @@ __global__ void sinkhorn_apply_kernel(const float *__restrict__ A, int J, int K,
     out[o] = A[o] - u[(size_t)b * J + j] - v[(size_t)b * K + k];
 }
 
+// ---------------------------------------------------------------- log_optimal_transport (network/matchnet.py:827-856)
+// SuperGlue's dustbin OT on the scores S [B,M,N]: couplings Z = [[S, alpha], [alpha, alpha]] of shape [M+1, N+1], marginals
+// log_mu = (norm x M, log N + norm), log_nu = (norm x N, log M + norm), norm = -log(M + N); `iters` times
+//     u = log_mu - LSE_k(Z + v),   v = log_nu - LSE_j(Z + u);    result Z + u + v - norm.
+// The augmented matrix is never built: the dustbin row / column are the constant alpha plus the potentials.
+__device__ __forceinline__ void lse_add(float &m, float &s, float x) {
+    if (x > m) { s = s * __expf(m - x) + 1.f; m = x; }
+    else if (x > -INFINITY) s += __expf(x - m);
+    else if (x != x) { m = x; s = x; }
+}
+// u[j], j in [0, M]: one warp per row of the augmented matrix
+__global__ void logot_row_kernel(const float *__restrict__ S, int M, int N, const float *__restrict__ alpha_p, const float *__restrict__ v,
+                                 float *__restrict__ u, float norm) {
+    const float alpha = alpha_p[0];
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (j > M) return;
+    const float *vb = v + (size_t)b * (N + 1);
+    float m = -INFINITY, s = 0.f;
+    if (j < M) {
+        const float *row = S + ((size_t)b * M + j) * N;
+        for (int k = lane; k < N; k += 32) lse_add(m, s, row[k] + vb[k]);
+        if (lane == 0) lse_add(m, s, alpha + vb[N]);
+    } else {
+        for (int k = lane; k <= N; k += 32) lse_add(m, s, alpha + vb[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        lse_merge(m, s, m2, s2);
+    }
+    if (lane == 0) u[(size_t)b * (M + 1) + j] = (j < M ? norm : __logf((float)N) + norm) - (m + __logf(s));
+}
+// v[k], k in [0, N]: a block owns 32 columns of the augmented matrix, 8 row lanes
+__global__ __launch_bounds__(256) void logot_col_kernel(const float *__restrict__ S, int M, int N, const float *__restrict__ alpha_p,
+                                                        const float *__restrict__ u, float *__restrict__ v, float norm) {
+    __shared__ float sm[8][33], ss[8][33];
+    const float alpha = alpha_p[0];
+    const int b = blockIdx.y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + tx;
+    const float *Sb = S + (size_t)b * M * N;
+    const float *ub = u + (size_t)b * (M + 1);
+    float m = -INFINITY, s = 0.f;
+    if (k < N) {
+        for (int j = ty; j < M; j += 8) lse_add(m, s, Sb[(size_t)j * N + k] + ub[j]);
+        if (ty == 0) lse_add(m, s, alpha + ub[M]);
+    } else if (k == N) {
+        for (int j = ty; j <= M; j += 8) lse_add(m, s, alpha + ub[j]);
+    }
+    sm[ty][tx] = m; ss[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && k <= N) {
+        for (int r = 1; r < 8; ++r) lse_merge(m, s, sm[r][tx], ss[r][tx]);
+        v[(size_t)b * (N + 1) + k] = (k < N ? norm : __logf((float)M) + norm) - (m + __logf(s));
+    }
+}
+__global__ void logot_apply_kernel(const float *__restrict__ S, int M, int N, const float *__restrict__ alpha_p, const float *__restrict__ u,
+                                   const float *__restrict__ v, float norm, float *__restrict__ out) {
+    const float alpha = alpha_p[0];
+    const int b = blockIdx.z, j = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > N) return;
+    const float z = (j < M && k < N) ? S[((size_t)b * M + j) * N + k] : alpha;
+    out[((size_t)b * (M + 1) + j) * (N + 1) + k] = z + u[(size_t)b * (M + 1) + j] + v[(size_t)b * (N + 1) + k] - norm;
+}
+
 }  // namespace
+
+int launch_log_ot(const float *scores, int B, int M, int N, const float *alpha, int iters, float *out, float *u, float *v, cudaStream_t st) {
+    const float norm = -logf((float)M + (float)N);
+    DSIR_CUDA_TRY(cudaMemsetAsync(u, 0, (size_t)B * (M + 1) * sizeof(float), st));
+    DSIR_CUDA_TRY(cudaMemsetAsync(v, 0, (size_t)B * (N + 1) * sizeof(float), st));
+    for (int it = 0; it < iters; ++it) {
+        logot_row_kernel<<<dim3(cdiv(M + 1, 8), B), 256, 0, st>>>(scores, M, N, alpha, v, u, norm);
+        DSIR_LAUNCH_CHECK();
+        logot_col_kernel<<<dim3(cdiv(N + 1, 32), B), 256, 0, st>>>(scores, M, N, alpha, u, v, norm);
+        DSIR_LAUNCH_CHECK();
+    }
+    logot_apply_kernel<<<dim3(cdiv(N + 1, 256), M + 1, B), 256, 0, st>>>(scores, M, N, alpha, u, v, norm, out);
+    DSIR_LAUNCH_CHECK();
+    return DSIR_OK;
+}
 
 int launch_gather_neighbours(const float *in, int B, int C, int N, const int64_t *idx, int M, int k, float *out, cudaStream_t st) {
     const long long MK = (long long)M * k;

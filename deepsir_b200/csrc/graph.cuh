@@ -9,4 +9,6 @@ int launch_pool_max(const float *in, int B, int C, int N, const int64_t *idx, in
 int launch_sinkhorn(const float *log_alpha, int B, int J, int K, int n_iters, int slack, float *out, float *u, float *v,
                     cudaStream_t st);
 
+int launch_log_ot(const float *scores, int B, int M, int N, const float *alpha, int iters, float *out, float *u, float *v, cudaStream_t st);
+
 }  // namespace dsir

@@ -91,3 +91,22 @@ def sinkhorn(log_alpha, n_iters=5, slack=True, eps=-1):
             break
         prev = cur
     return out
+
+
+def log_optimal_transport(scores, alpha, iters: int):
+    """network/matchnet.py:836-856 (with log_sinkhorn_iterations :827-833).  scores [B,M,N], alpha: the learned dustbin
+    score (0-d / 1-element tensor or float) -> [B,M+1,N+1] log couplings (times M+N).  The augmented matrix with the
+    dustbin row and column is never built."""
+    dev = L.require_cuda(scores)
+    B, M, N = scores.shape
+    s = scores.contiguous()
+    if s.dtype != torch.float32:
+        raise L.DeepSIRError("log_optimal_transport expects float32 scores")
+    a = alpha.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous() if isinstance(alpha, torch.Tensor) \
+        else torch.full((1,), float(alpha), dtype=torch.float32, device=dev)
+    out = torch.empty(B, M + 1, N + 1, dtype=torch.float32, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.dsir_log_optimal_transport_workspace_bytes(B, M, N), dev)
+    L.check(lib.dsir_log_optimal_transport(s.data_ptr(), B, M, N, a.data_ptr(), int(iters), out.data_ptr(), ws.data_ptr(),
+                                           ws.numel(), L.stream_ptr(dev)), "dsir_log_optimal_transport")
+    return out

@@ -197,6 +197,60 @@ def sinkhorn_implicit(feat_src, feat_ref, xyz_ref, beta, alpha=0.5, n_iters=5, s
     return y, torch.exp(lse_r - u), u, v
 
 
+def log_optimal_transport_implicit(feat_src, feat_ref, xyz_ref, beta, alpha, bin_score, iters=5):
+    """log_optimal_transport (network/matchnet.py:836-856) on the NEVER-MATERIALISED scores s_jk = -beta (d_jk - alpha)
+    (compute_affinity, matchnet.py:195-208).  The dustbin row / column of the augmented couplings are the constant
+    `bin_score` plus the potentials, so every half-iteration is one fused tcgen05 distance + log-sum-exp sweep
+    (dsir_match_soft_sweep with a column bias) and a few vector operations on [B,M+1] / [B,N+1]:
+        u_j = log_mu_j - logaddexp(LSE_k(s_jk + v_k), bin + v_N)   (j < M),   u_M = log_mu_M - (bin + LSE(v))
+        v_k = log_nu_k - logaddexp(LSE_j(s_jk + u_j), bin + u_M)   (k < N),   v_N = log_nu_N - (bin + LSE(u))
+    Returns (y_soft [B,M,3] = sum_k P_jk r_k / sum_k P_jk over the real columns, rowmass [B,M] = sum_{k<N} P_jk,
+    u [B,M+1], v [B,N+1]) with log P_jk = s_jk + u_j + v_k - norm, norm = -log(M+N) - i.e. log_optimal_transport(...)[:, :M, :N]
+    without ever forming it."""
+    import math
+    dev = L.require_cuda(feat_src, feat_ref, xyz_ref, beta)
+    B, C, M = feat_src.shape
+    N = feat_ref.shape[2]
+    lib = L.lib()
+    (fs, _a), (fr, _b) = L.feat_cn(feat_src), L.feat_cn(feat_ref)
+    beta_t = beta.to(torch.float32).contiguous()
+    alpha_t = torch.full((B,), float(alpha), dtype=torch.float32, device=dev) if isinstance(alpha, float) \
+        else alpha.to(torch.float32).contiguous()
+    bin_t = bin_score.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:1] if isinstance(bin_score, torch.Tensor) \
+        else torch.full((1,), float(bin_score), dtype=torch.float32, device=dev)
+    xyz_c = xyz_ref.contiguous()
+    ws_row = L.workspace(lib.dsir_match_soft_workspace_bytes(B, C, M, N), dev)
+    ws_col = L.workspace(lib.dsir_match_soft_workspace_bytes(B, C, N, M), dev)
+    lse_r = torch.empty(B, M, dtype=torch.float32, device=dev)
+    lse_c = torch.empty(B, N, dtype=torch.float32, device=dev)
+
+    def sweep(row, bias, reuse, y=None):
+        a, b2, n1, n2, ws, out = (fs, fr, M, N, ws_row, lse_r) if row else (fr, fs, N, M, ws_col, lse_c)
+        bias = bias.contiguous()
+        L.check(lib.dsir_match_soft_sweep(a, b2, B, C, n1, n2, beta_t.data_ptr(), alpha_t.data_ptr(), bias.data_ptr(),
+                                          xyz_c.data_ptr() if y is not None else None, L.ptr(y), out.data_ptr(), int(reuse),
+                                          ws.data_ptr(), ws.numel(), L.stream_ptr(dev)), "dsir_match_soft_sweep")
+        return out
+
+    norm = -math.log(M + N)
+    log_mu = torch.full((B, M + 1), norm, dtype=torch.float32, device=dev)
+    log_mu[:, M] = math.log(N) + norm
+    log_nu = torch.full((B, N + 1), norm, dtype=torch.float32, device=dev)
+    log_nu[:, N] = math.log(M) + norm
+    u = torch.zeros(B, M + 1, dtype=torch.float32, device=dev)
+    v = torch.zeros(B, N + 1, dtype=torch.float32, device=dev)
+    for it in range(iters):
+        r = sweep(True, v[:, :N], it > 0)                                          # LSE_k(s_jk + v_k), k < N
+        u = torch.cat([log_mu[:, :M] - torch.logaddexp(r, bin_t + v[:, N:]),
+                       log_mu[:, M:] - (bin_t + torch.logsumexp(v, dim=1, keepdim=True))], dim=1)
+        c = sweep(False, u[:, :M], it > 0)                                         # LSE_j(s_jk + u_j), j < M
+        v = torch.cat([log_nu[:, :N] - torch.logaddexp(c, bin_t + u[:, M:]),
+                       log_nu[:, N:] - (bin_t + torch.logsumexp(u, dim=1, keepdim=True))], dim=1)
+    y = torch.empty(B, M, 3, dtype=torch.float32, device=dev)
+    r = sweep(True, v[:, :N], iters > 0, y=y)
+    return y, torch.exp(r + u[:, :M] - norm), u, v
+
+
 def gather_neighbour_V3(inputs, neigh_idx):
     """network/tools.py:211-221.  inputs [B,C,N], neigh_idx [B,M] int64 -> [B,C,M]."""
     dev = L.require_cuda(inputs, neigh_idx)

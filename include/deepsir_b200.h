@@ -159,6 +159,12 @@ int dsir_pool_max(const float *in, int B, int C, int N, const int64_t *idx, int 
 /* sinkhorn (network/matchnet.py:211-271): log_alpha [B,J,K] -> out [B,J,K] after n_iters row/column normalisations in
  * the log domain, with or without the slack row/column; out may alias log_alpha.  ws >= dsir_sinkhorn_workspace_bytes. */
 size_t dsir_sinkhorn_workspace_bytes(int B, int J, int K);
+/* log_optimal_transport + log_sinkhorn_iterations (network/matchnet.py:827-856, SuperGlue's dustbin OT): scores [B,M,N],
+ * learned dustbin score alpha (ONE float on the device: the reference's nn.Parameter), `iters` Sinkhorn iterations in the log domain with marginals (1 x M, N) / (1 x N, M) over
+ * M + N -> out [B,M+1,N+1] = Z + u + v - norm.  The augmented coupling matrix is never built. */
+size_t dsir_log_optimal_transport_workspace_bytes(int B, int M, int N);
+int dsir_log_optimal_transport(const float *scores, int B, int M, int N, const float *alpha, int iters, float *out, void *ws,
+                               size_t ws_bytes, dsir_stream_t stream);
 int dsir_sinkhorn(const float *log_alpha, int B, int J, int K, int n_iters, int slack, float *out, void *ws, size_t ws_bytes,
                   dsir_stream_t stream);
 

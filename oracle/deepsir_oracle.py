@@ -208,6 +208,31 @@ def sinkhorn(log_alpha, n_iters=5, slack=True, eps=-1):
     return la
 
 
+def log_sinkhorn_iterations(Z, log_mu, log_nu, iters):
+    """network/matchnet.py:827-833."""
+    u, v = torch.zeros_like(log_mu), torch.zeros_like(log_nu)
+    for _ in range(iters):
+        u = log_mu - torch.logsumexp(Z + v.unsqueeze(1), dim=2)
+        v = log_nu - torch.logsumexp(Z + u.unsqueeze(2), dim=1)
+    return Z + u.unsqueeze(2) + v.unsqueeze(1)
+
+
+def log_optimal_transport(scores, alpha, iters):
+    """network/matchnet.py:836-856: dustbin row/column with score alpha, marginals (1 x m, n) / (1 x n, m) over m + n,
+    result multiplied by m + n (Z - norm)."""
+    b, m, n = scores.shape
+    alpha = torch.as_tensor(alpha, dtype=scores.dtype)
+    bins0 = alpha.expand(b, m, 1)
+    bins1 = alpha.expand(b, 1, n)
+    corner = alpha.expand(b, 1, 1)
+    couplings = torch.cat([torch.cat([scores, bins0], -1), torch.cat([bins1, corner], -1)], 1)
+    ms, ns = torch.tensor(float(m), dtype=scores.dtype), torch.tensor(float(n), dtype=scores.dtype)
+    norm = -(ms + ns).log()
+    log_mu = torch.cat([norm.expand(m), ns.log()[None] + norm])[None].expand(b, -1)
+    log_nu = torch.cat([norm.expand(n), ms.log()[None] + norm])[None].expand(b, -1)
+    return log_sinkhorn_iterations(couplings, log_mu, log_nu, iters) - norm
+
+
 # --------------------------------------------------------------------------------------
 # SE(3) (common/math/se3_torch.py)
 # --------------------------------------------------------------------------------------

@@ -208,6 +208,23 @@ def keypoint_eval():
          err_r_deg=m["err_r_deg"], err_t=m["err_t"], succ=m["succ"], chamfer_dist=m["chamfer_dist"], rte_rre=rr)
 
 
+def log_ot():
+    """log_optimal_transport / log_sinkhorn_iterations (network/matchnet.py:827-856) from the reference itself."""
+    os.makedirs(OUT, exist_ok=True)
+    g = torch.Generator().manual_seed(13)
+    sc = torch.randn(2, 41, 57, generator=g) * 2.5
+    fs = torch.nn.functional.normalize(torch.randn(2, 32, 120, generator=g), dim=1)
+    fr = torch.nn.functional.normalize(torch.randn(2, 32, 140, generator=g), dim=1)
+    beta, alpha = torch.tensor([10.0, 6.0]), torch.tensor([0.5, 0.4])
+    aff = R_match.compute_affinity(beta, R_match.match_features_V2(fs, fr), alpha)
+    save("log_ot", scores=sc, bin1=torch.tensor(1.0), bin2=torch.tensor(-0.7),
+         out_bin1_it20=R_match.log_optimal_transport(sc, torch.tensor(1.0), 20),
+         out_bin2_it3=R_match.log_optimal_transport(sc, torch.tensor(-0.7), 3),
+         out_it0=R_match.log_optimal_transport(sc, torch.tensor(0.25), 0),
+         feat_src=fs, feat_ref=fr, beta=beta, alpha=alpha,
+         out_affinity_it5=R_match.log_optimal_transport(aff, torch.tensor(0.3), 5))
+
+
 def R_model_label_weights():
     return [3, 1, 1, 3, 2, 0, 0, 0, 6, 5, 6, 4, 7, 7, 6, 8, 4, 9, 9]   # network/model.py:146-149
 
@@ -217,7 +234,10 @@ if __name__ == "__main__":
         graph()
     elif len(sys.argv) > 1 and sys.argv[1] == "keypoint":
         keypoint_eval()
+    elif len(sys.argv) > 1 and sys.argv[1] == "log_ot":
+        log_ot()
     else:
         main()
         graph()
         keypoint_eval()
+        log_ot()

@@ -19,7 +19,10 @@ def test_reference_arm_prints_one_json_line():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # "reference" when baseline/_ref (the reference's own functions) was shipped by build(), else the oracle port
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    ref_present = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "network"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_present else "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
 

@@ -788,6 +788,41 @@ def test_sinkhorn_implicit_tensor_core_sweeps():
         assert torch.allclose(y.cpu(), y_o, rtol=5e-4, atol=2e-4)
 
 
+def test_log_optimal_transport_golden(golden):
+    """log_optimal_transport + log_sinkhorn_iterations (network/matchnet.py:827-856): the reference's own outputs."""
+    z = golden("log_ot")
+    for key, alpha, it in (("out_bin1_it20", z["bin1"], 20), ("out_bin2_it3", -0.7, 3), ("out_it0", 0.25, 0)):
+        out = D.log_optimal_transport(cu(z["scores"]), cu(alpha) if isinstance(alpha, torch.Tensor) else alpha, it)
+        assert out.shape == (2, 42, 58)
+        assert torch.allclose(out.cpu(), z[key], rtol=1e-5, atol=1e-4), key
+    g = torch.Generator().manual_seed(5)
+    sc = torch.randn(3, 700, 513, generator=g) * 4                           # ragged sizes, sharper scores
+    assert torch.allclose(D.log_optimal_transport(cu(sc), 0.5, 7).cpu(), O.log_optimal_transport(sc, 0.5, 7), rtol=1e-5, atol=1e-4)
+
+
+def test_log_optimal_transport_implicit_tensor_core_sweeps():
+    """The same OT on the never-materialised affinity (fused tcgen05 sweeps, dustbin row / column handled as vectors):
+    potentials, row masses and soft targets equal those of the reference's log_optimal_transport on the materialised matrix."""
+    b = synth.make_batch(2, 1500, 32, "3dmatch", config=3, first_pair=13)
+    fs, fr = b["feat_src"], b["feat_ref"][:, :, :1300].contiguous()
+    xr = b["points_ref"][:, :1300, :3].contiguous()
+    beta, alpha = torch.tensor([10.0, 6.0]), torch.tensor([0.5, 0.4])
+    aff = O.compute_affinity(beta, O.match_features_V2(fs, fr), alpha)
+    M, N = 1500, 1300
+    for bin_score, iters in ((0.3, 5), (-1.0, 2)):
+        Z = O.log_optimal_transport(aff, bin_score, iters)                   # [B, M+1, N+1], times (M + N)
+        P = torch.exp(Z[:, :M, :N])
+        mass_o = P.sum(dim=2)
+        y_o = (P @ xr) / mass_o[:, :, None]
+        y, mass, u, v = D.log_optimal_transport_implicit(cu(fs), cu(fr), cu(xr), cu(beta), cu(alpha), bin_score, iters)
+        assert u.shape == (2, M + 1) and v.shape == (2, N + 1)
+        assert torch.allclose(mass.cpu(), mass_o, rtol=5e-4, atol=1e-6)
+        assert torch.allclose(y.cpu(), y_o, rtol=5e-4, atol=2e-4)
+        # the potentials reproduce the dustbin column of the reference's result: Z[j, N] = bin + u_j + v_N - norm
+        norm = -np.log(M + N)
+        assert torch.allclose((bin_score + u[:, :M] + v[:, N:] - norm).cpu(), Z[:, :M, N], rtol=1e-4, atol=5e-4)
+
+
 def test_match_argmin_hint_never_changes_the_result():
     """dsir_match_argmin_hint: a correct, a partly wrong, a random and an out-of-range prior all give the indices of the
     unhinted call (the hint only tightens the filter)."""

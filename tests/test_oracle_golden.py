@@ -204,3 +204,14 @@ def test_keypoint_and_eval_oracle_matches_reference_fixture(golden):
     raw = torch.cat([O.se3_transform(g["transform_gt"], src), ref], dim=1)
     ch = O.chamfer(src, ref, raw, g["transform_pred"], g["transform_gt"])
     assert torch.allclose(ch, g["chamfer_dist"], rtol=1e-6, atol=1e-8)
+
+
+def test_log_optimal_transport_oracle_matches_reference_fixture(golden):
+    """network/matchnet.py:827-856 restated in the oracle == the reference's own outputs (oracle/make_golden.py log_ot)."""
+    z = golden("log_ot")
+    for key, alpha, it in (("out_bin1_it20", 1.0, 20), ("out_bin2_it3", -0.7, 3), ("out_it0", 0.25, 0)):
+        out = O.log_optimal_transport(z["scores"], alpha, it)
+        assert out.shape == z[key].shape == (2, 42, 58)
+        assert torch.allclose(out, z[key], rtol=0, atol=2e-6), key
+    aff = O.compute_affinity(z["beta"], O.match_features_V2(z["feat_src"], z["feat_ref"]), z["alpha"])
+    assert torch.allclose(O.log_optimal_transport(aff, 0.3, 5), z["out_affinity_it5"], atol=5e-6)
