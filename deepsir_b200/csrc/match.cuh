@@ -29,6 +29,8 @@ enum { MATCH_MODE_ARGMIN = 0, MATCH_MODE_DENSE = 1, MATCH_MODE_SOFT = 2 };
 
 int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, cudaStream_t st);
 int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, int *max_a, int *max_b, cudaStream_t st);
+// min_a [B]: per-batch minimum of the norms (atomicMin on the float bits; initialise with bytes 0x7f)
+int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, int *max_a, int *max_b, int *min_a, cudaStream_t st);
 int launch_match_fp32(const MatchParams &P, int mode, cudaStream_t st);
 int launch_row_topk(const float *dist, int B, int Jc, int K, const float *beta, const float *alpha, const float *bias, const float *lse,
                     long long lse_bs, int j0, int topk, int64_t *out_idx, float *out_w, long long out_bs, cudaStream_t st);

@@ -17,7 +17,8 @@ constexpr int PITCH = TM + 4;
 
 // squared norms (fma chain over channels ascending) and, optionally, the per-batch maximum (atomicMax on the float bits
 // of the non-negative norms; a NaN compares above every finite value) into max_a[b] and max_b[b]
-__global__ void sqnorm_kernel(dsir_feat f, int C, int N, float *__restrict__ out, int *__restrict__ max_a, int *__restrict__ max_b) {
+__global__ void sqnorm_kernel(dsir_feat f, int C, int N, float *__restrict__ out, int *__restrict__ max_a, int *__restrict__ max_b,
+                              int *__restrict__ min_a) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     int b = blockIdx.y;
     float acc = 0.f;
@@ -38,13 +39,22 @@ __global__ void sqnorm_kernel(dsir_feat f, int C, int N, float *__restrict__ out
             if (max_b) atomicMax(&max_b[b], bits);
         }
     }
+    if (min_a) {   // per-batch minimum (lanes beyond N do not take part)
+        int bits = n < N ? __float_as_int(acc) : 0x7f7f7f7f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bits = min(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+        if ((threadIdx.x & 31) == 0) atomicMin(&min_a[b], bits);
+    }
 }
 
-int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, int *max_a, int *max_b, cudaStream_t st) {
+int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, int *max_a, int *max_b, int *min_a, cudaStream_t st) {
     dim3 grid(cdiv(N, 256), B);
-    sqnorm_kernel<<<grid, 256, 0, st>>>(f, C, N, out, max_a, max_b);
+    sqnorm_kernel<<<grid, 256, 0, st>>>(f, C, N, out, max_a, max_b, min_a);
     DSIR_LAUNCH_CHECK();
     return DSIR_OK;
+}
+int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, int *max_a, int *max_b, cudaStream_t st) {
+    return launch_sqnorm(f, B, C, N, out, max_a, max_b, nullptr, st);
 }
 int launch_sqnorm(dsir_feat f, int B, int C, int N, float *out, cudaStream_t st) {
     return launch_sqnorm(f, B, C, N, out, nullptr, nullptr, st);

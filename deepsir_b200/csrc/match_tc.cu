@@ -213,7 +213,7 @@ struct TcParams {
     const float *rmax;      // [B] max reference squared norm
     const float *scale;     // [B] sigma (power of two)
     const float *xm;        // [B] >= 0: the folded-norm K-step is SKIPPED for this batch element and every margin is widened by
-                            //     this amount (sigma^2 x spread of the reference norms); < 0: norm folded in (see tc_spread_kernel)
+                            //     this amount (sigma^2 x spread of the reference norms); < 0: norm folded in (see TC_NOAUG_SPREAD)
     float *cand_val;        // [B][Jpad][S][T]  (scaled units)
     int *cand_idx;
     int prime_div;            // priming pass over every prime_div-th unit (0 = none)
@@ -445,6 +445,19 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// With (nearly) constant reference norms - the features are L2-normalised upstream, network/model.py:233-234 - the
+// term sigma^2 |r_k|^2 shifts a whole row of x by a constant and cannot change the argmin: the filter then works on
+// x' = -2 sigma^2 <s_j, r_k> (4 MMAs per tile instead of 5, no norm tile traffic) and widens every margin by the spread
+// sigma^2 (max_k |r_k|^2 - min_k |r_k|^2): a column whose x is within margin of the row minimum of x has its x' within
+// margin + spread of the minimum of x'.  Exactness is untouched (the refine step re-scores with the exact norms).
+// Chosen per batch element on the device; beyond TC_NOAUG_SPREAD (2^-14, ~6 % of the smallest margin of unit features)
+// the norm stays folded in - and so it does when K is not a multiple of the 128-column unit: the zero-filled reference rows
+// beyond K rely on their huge padded norm to stay out of the candidate lists.  The per-batch minimum / maximum of the norms
+// come out of the norm kernel (atomics); the first block of the reference-side prep kernel writes the decision.
+// ---------------------------------------------------------------------------------------------------------
+constexpr float TC_NOAUG_SPREAD = 6.1035e-5f;
+
 // prep: [B,C,N] fp32 (any strides) -> fp16 tensor-core copy [B][N][64] = mul * sigma * f (point-major, channels C..63
 // zero), and for the reference side the folded-norm channels [B][Npad][16] = {hi, lo, lolo, 0..} of sigma^2 |r|^2
 // (TC_PAD_NORM beyond N).  One block = 32 points x 64 channels through a shared-memory transpose.  Block (0,0) also
@@ -452,7 +465,8 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
 __global__ __launch_bounds__(256) void tc_prep_kernel(dsir_feat f, int C, int N, int Npad, const float *__restrict__ amax,
                                                       const float *__restrict__ nrm, float mul, __half *__restrict__ out16,
                                                       __half *__restrict__ aug, __half *__restrict__ aug_const,
-                                                      float *__restrict__ scale_out) {
+                                                      float *__restrict__ scale_out, const float *__restrict__ rmin = nullptr,
+                                                      const float *__restrict__ rmax = nullptr, float *__restrict__ xm_out = nullptr) {
     __shared__ float tile[TC_CH][33];
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * 32;
@@ -501,36 +515,13 @@ __global__ __launch_bounds__(256) void tc_prep_kernel(dsir_feat f, int C, int N,
             aug_const[t] = __float2half_rn((t % TC_AUG) < 3 ? 1.f : 0.f);
     }
     if (scale_out && blockIdx.x == 0 && threadIdx.x == 0) scale_out[b] = sigma;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// With (nearly) constant reference norms - the features are L2-normalised upstream, network/model.py:233-234 - the
-// term sigma^2 |r_k|^2 shifts a whole row of x by a constant and cannot change the argmin: the filter then works on
-// x' = -2 sigma^2 <s_j, r_k> (4 MMAs per tile instead of 5, no norm tile traffic) and widens every margin by the spread
-// sigma^2 (max_k |r_k|^2 - min_k |r_k|^2): a column whose x is within margin of the row minimum of x has its x' within
-// margin + spread of the minimum of x'.  Exactness is untouched (the refine step re-scores with the exact norms).
-// Chosen per batch element on the device; beyond TC_NOAUG_SPREAD (2^-14, ~6 % of the smallest margin of unit features)
-// the norm stays folded in - and so it does when K is not a multiple of the 128-column unit: the zero-filled reference rows
-// beyond K rely on their huge padded norm to stay out of the candidate lists.  One block per batch element.
-// ---------------------------------------------------------------------------------------------------------
-constexpr float TC_NOAUG_SPREAD = 6.1035e-5f;
-__global__ __launch_bounds__(256) void tc_spread_kernel(const float *__restrict__ nr, int K, const float *__restrict__ rmax,
-                                                        const float *__restrict__ amax, float *__restrict__ xm) {
-    __shared__ float s_min[8];
-    const int b = blockIdx.x;
-    float m = INFINITY;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) m = fminf(m, nr[(size_t)b * K + k]);
-    m = warp_min(m);
-    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) m = fminf(m, s_min[w]);
-        const float sg = tc_sigma(amax[b]);
-        const float spread = __fmul_rn(__fmul_rn(sg, sg), rmax[b] - m) * 1.0001f;
-        xm[b] = (spread >= 0.f && spread <= TC_NOAUG_SPREAD && K % TC_BN == 0) ? spread : -1.f;   // NaN / inf norms keep the folded norm
+    if (xm_out && blockIdx.x == 0 && threadIdx.x == 0) {   // fold the norm in, or skip its K-step (see TC_NOAUG_SPREAD)
+        const float spread = __fmul_rn(__fmul_rn(sigma, sigma), rmax[b] - rmin[b]) * 1.0001f;
+        float x = (spread >= 0.f && spread <= TC_NOAUG_SPREAD && N % TC_BN == 0) ? spread : -1.f;   // NaN / inf norms keep the folded norm
 #ifdef DSIR_TC_FORCE_AUG   // development builds: always fold the norm in (A/B of the 4-MMA mode)
-        xm[b] = -1.f;
+        x = -1.f;
 #endif
+        xm_out[b] = x;
     }
 }
 
@@ -726,7 +717,7 @@ __global__ void match_tc_rescue_finalize_kernel(RefineParams P, const unsigned l
 
 struct TcPlan {
     int NKS, RB, U, S, Jpad, Kpad;
-    size_t off_a16, off_b16, off_baug, off_aaug, off_rmax, off_amax, off_scale, off_xm, off_cval, off_cidx, off_count,
+    size_t off_a16, off_b16, off_baug, off_aaug, off_rmax, off_amax, off_scale, off_xm, off_rmin, off_cval, off_cidx, off_count,
         off_rows, off_erows, off_keys, off_dbg, off_trace, total;
 };
 
@@ -756,6 +747,7 @@ TcPlan make_plan(int B, int C, int J, int K) {
     p.off_amax = take((size_t)B * 4);
     p.off_scale = take((size_t)B * 4);
     p.off_xm = take((size_t)B * 4);
+    p.off_rmin = take((size_t)B * 4);
     p.off_cval = take((size_t)B * p.Jpad * S * TC_LISTS * TC_T * 4);
     p.off_cidx = take((size_t)B * p.Jpad * S * TC_LISTS * TC_T * 4);
     p.off_count = take(256);
@@ -798,7 +790,7 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     __half *a16 = (__half *)(base + pl.off_a16), *b16 = (__half *)(base + pl.off_b16);
     __half *baug = (__half *)(base + pl.off_baug), *aaug = (__half *)(base + pl.off_aaug);
     float *rmax = (float *)(base + pl.off_rmax), *amax = (float *)(base + pl.off_amax), *scale = (float *)(base + pl.off_scale);
-    float *xm = (float *)(base + pl.off_xm);
+    float *xm = (float *)(base + pl.off_xm), *rmin = (float *)(base + pl.off_rmin);
     float *cval = (float *)(base + pl.off_cval);
     int *cidx = (int *)(base + pl.off_cidx), *count = (int *)(base + pl.off_count), *rows = (int *)(base + pl.off_rows);
 
@@ -808,13 +800,13 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
         // rmax and amax are adjacent 256-byte blocks: one memset clears both
         DSIR_CUDA_TRY(cudaMemsetAsync(rmax, 0, pl.off_scale - pl.off_rmax, st));
         // exact squared norms (fma chains, shared with the fp32 kernel) + per-batch maxima for sigma and the margin
-        if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, const_cast<float *>(P.nr), (int *)rmax, (int *)amax, st))) return rc;
+        DSIR_CUDA_TRY(cudaMemsetAsync(rmin, 0x7f, (size_t)P.B * 4, st));
+        if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, const_cast<float *>(P.nr), (int *)rmax, (int *)amax, (int *)rmin, st))) return rc;
         if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, const_cast<float *>(P.ns), (int *)amax, nullptr, st))) return rc;
         tc_prep_kernel<<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, amax, nullptr, 1.0f, a16, nullptr, aaug, scale);
         DSIR_LAUNCH_CHECK();
-        tc_prep_kernel<<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, amax, P.nr, -2.0f, b16, baug, nullptr, nullptr);
-        DSIR_LAUNCH_CHECK();
-        tc_spread_kernel<<<P.B, 256, 0, st>>>(P.nr, P.K, rmax, amax, xm);
+        tc_prep_kernel<<<dim3(pl.Kpad / 32, P.B), 256, 0, st>>>(P.fr, P.C, P.K, pl.Kpad, amax, P.nr, -2.0f, b16, baug, nullptr, nullptr,
+                                                                rmin, rmax, xm);
         DSIR_LAUNCH_CHECK();
     }
     CUtensorMap mapA, mapB, mapAaug, mapBaug;
