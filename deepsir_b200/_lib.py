@@ -109,11 +109,13 @@ _SIGS = {
     "dsir_log_optimal_transport": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
                                               _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "dsir_kabsch_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int]),
-    "dsir_kabsch": (_c.c_int, [Points, Points, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
+    "dsir_kabsch": (_c.c_int, [Points, Points, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
                                _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
-    "dsir_kabsch_moments": (_c.c_int, [Points, Points, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int,
+    "dsir_kabsch_moments": (_c.c_int, [Points, Points, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
                                        _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "dsir_kabsch_from_moments": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "dsir_soft_targets": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
+                                     _c.c_void_p, _c.c_void_p]),
     "dsir_kabsch_soft": (_c.c_int, [Points, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                     _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "dsir_se3_apply": (_c.c_int, [_c.c_void_p, _c.c_int64, Points, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int64,

@@ -703,35 +703,35 @@ size_t dsir_kabsch_workspace_bytes(int B, int M) {
 }
 
 static int kabsch_common(dsir_points src, dsir_points tgt, const float *w, int64_t w_bs, const int64_t *gather, int B,
-                         int M, double **partials, int *nblk, void *ws, size_t ws_bytes, cudaStream_t st) {
+                         int M, int n_tgt, double **partials, int *nblk, void *ws, size_t ws_bytes, cudaStream_t st) {
     if (!src.ptr || !tgt.ptr || B <= 0 || M <= 0) return DSIR_ERR_BAD_ARG;
     Workspace W(ws, ws_bytes);
     *nblk = kabsch_num_blocks(M);
     *partials = W.take<double>((size_t)B * (*nblk) * KB_NMOM);
     if (!W.ok()) return DSIR_ERR_WORKSPACE;
     KabschParams P{};
-    P.src = src; P.tgt = tgt; P.w = w; P.w_bs = w_bs; P.gather = gather; P.B = B; P.M = M; P.partials = *partials;
+    P.src = src; P.tgt = tgt; P.w = w; P.w_bs = w_bs; P.gather = gather; P.B = B; P.M = M; P.n_tgt = n_tgt; P.partials = *partials;
     return launch_kabsch_moments(P, *nblk, st);
 }
 
 int dsir_kabsch(dsir_points src, dsir_points tgt, const float *w, int64_t w_batch_stride, const int64_t *gather,
-                int B, int M, float *T, int32_t *status, double *moments, void *ws, size_t ws_bytes,
+                int B, int M, int n_tgt, float *T, int32_t *status, double *moments, void *ws, size_t ws_bytes,
                 dsir_stream_t stream) {
     if (!T) return DSIR_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     double *partials; int nblk;
-    int rc = kabsch_common(src, tgt, w, w_batch_stride, gather, B, M, &partials, &nblk, ws, ws_bytes, st);
+    int rc = kabsch_common(src, tgt, w, w_batch_stride, gather, B, M, n_tgt, &partials, &nblk, ws, ws_bytes, st);
     if (rc) return rc;
     return launch_kabsch_solve(partials, nblk, B, T, status, moments, nullptr, nullptr, 0, st);
 }
 
 int dsir_kabsch_moments(dsir_points src, dsir_points tgt, const float *w, int64_t w_batch_stride,
-                        const int64_t *gather, int B, int M, double *moments, void *ws, size_t ws_bytes,
+                        const int64_t *gather, int B, int M, int n_tgt, double *moments, void *ws, size_t ws_bytes,
                         dsir_stream_t stream) {
     if (!moments) return DSIR_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     double *partials; int nblk;
-    int rc = kabsch_common(src, tgt, w, w_batch_stride, gather, B, M, &partials, &nblk, ws, ws_bytes, st);
+    int rc = kabsch_common(src, tgt, w, w_batch_stride, gather, B, M, n_tgt, &partials, &nblk, ws, ws_bytes, st);
     if (rc) return rc;
     return launch_kabsch_reduce(partials, nblk, B, moments, st);
 }
@@ -741,13 +741,19 @@ int dsir_kabsch_from_moments(const double *moments, int B, float *T, int32_t *st
     return launch_kabsch_solve(moments, 1, B, T, status, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
+int dsir_soft_targets(const float *weights, int64_t w_batch_stride, int64_t w_row_stride, const float *tgt, int B, int M, int N,
+                      float *y_soft, float *rowmass, dsir_stream_t stream) {
+    if (!weights || !tgt || !y_soft || !rowmass || B <= 0 || M <= 0 || N <= 0) return DSIR_ERR_BAD_ARG;
+    return launch_soft_targets(weights, w_batch_stride, w_row_stride, tgt, B, M, N, y_soft, rowmass, (cudaStream_t)stream);
+}
+
 int dsir_kabsch_soft(dsir_points src, const float *y_soft, const float *rowmass, int B, int M, float *T,
                      int32_t *status, void *ws, size_t ws_bytes, dsir_stream_t stream) {
     if (!y_soft || !rowmass || !T) return DSIR_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     dsir_points tgt{y_soft, (int64_t)M * 3, 3, 1};
     double *partials; int nblk;
-    int rc = kabsch_common(src, tgt, rowmass, M, nullptr, B, M, &partials, &nblk, ws, ws_bytes, st);
+    int rc = kabsch_common(src, tgt, rowmass, M, nullptr, B, M, 0, &partials, &nblk, ws, ws_bytes, st);
     if (rc) return rc;
     return launch_kabsch_solve(partials, nblk, B, T, status, nullptr, nullptr, nullptr, 1, st);
 }
@@ -806,7 +812,7 @@ int dsir_align_loop(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, floa
         int rc = match_argmin_impl(fs, fr, B, C, J, K, idx, nullptr, match_ws, match_bytes, algo, it > 0, st, prior);  // :558-569
         if (rc) return rc;
         double *partials; int nblk;
-        rc = kabsch_common(src, ref, weights, J, idx, B, J, &partials, &nblk, kab_ws, kab_bytes, st);    // :571,:588
+        rc = kabsch_common(src, ref, weights, J, idx, B, J, K, &partials, &nblk, kab_ws, kab_bytes, st);    // :571,:588
         if (rc) return rc;
         float *T_cum = transforms + (size_t)it * B * 12;
         const float *T_prev = it > 0 ? transforms + (size_t)(it - 1) * B * 12 : nullptr;

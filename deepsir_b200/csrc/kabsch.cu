@@ -25,11 +25,16 @@ __global__ __launch_bounds__(KB_THREADS) void kabsch_moments_kernel(KabschParams
     for (int m = blockIdx.x * KB_THREADS + threadIdx.x; m < P.M; m += gridDim.x * KB_THREADS) {
         float wf = wp ? wp[m] : 1.f;
         size_t tm = gp ? (size_t)gp[m] : (size_t)m;
+        // torch.gather raises on an index outside the target cloud (tools.py:211-221); here it is never dereferenced and
+        // poisons the pair instead: NaN moments -> status 1 / invalid_gradient
+        const bool bad = gp != nullptr && P.n_tgt > 0 && (unsigned long long)gp[m] >= (unsigned long long)P.n_tgt;
+        if (bad) tm = 0;
         const float *s = sp + (size_t)m * P.src.point_stride;
         const float *t = tp + tm * P.tgt.point_stride;
         double w = (double)wf;
         double x0 = s[0], x1 = s[P.src.coord_stride], x2 = s[2 * P.src.coord_stride];
         double y0 = t[0], y1 = t[P.tgt.coord_stride], y2 = t[2 * P.tgt.coord_stride];
+        if (bad) y0 = nan("");
         acc[0] += fabs(w);
         acc[1] += w;
         double wx0 = w * x0, wx1 = w * x1, wx2 = w * x2;
@@ -110,7 +115,12 @@ __device__ void svd3_jacobi(const double H[3][3], double G[3][3], double V[3][3]
     }
 }
 
-// moments -> T (fp32 [3,4]) ; returns status (0 ok, 1 degenerate -> identity)
+// moments -> T (fp32 [3,4]) ; returns status (0 ok, 1 non-finite input -> identity).
+// Rank-deficient covariances (collinear or duplicated correspondences, a single non-zero weight, all-zero weights): the
+// reference still returns V U^T of whatever basis LAPACK completes the null space with and t = c_tgt - R c_src, and flags
+// nothing (model.py:47-58 raises only when the SVD itself fails).  The completion here is deterministic: rank 1 -> the
+// MINIMAL rotation that takes u1 to v1 (the rotation is only determined up to a turn about that axis); rank 0 -> R = I.
+// The centroid translation is kept in both cases.
 __device__ int kabsch_solve(const double *mom, float *T, int signed_norm) {
     const double EPS = 1e-16;  // _EPS of network/model.py:19
     // hard variant normalises by sum|w| (:36); the soft variant by the plain sum of the row masses (:82)
@@ -168,6 +178,37 @@ __device__ int kabsch_solve(const double *mom, float *T, int signed_norm) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) R[i][j] = v1[i] * u1[j] + v2[i] * u2[j] + v3[i] * u3[j];
             status = 0;
+        } else if (sg[i1] > 0.0) {
+            // rank 1: minimal rotation u1 -> v1 (Rodrigues); antiparallel: half turn about an axis orthogonal to u1
+            double u1[3], v1[3], w[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { u1[i] = G[i][i1] / sg[i1]; v1[i] = V[i][i1]; }
+            const double c = u1[0] * v1[0] + u1[1] * v1[1] + u1[2] * v1[2];
+            cross3(u1, v1, w);
+            if (c > -1.0 + 1e-12) {
+                const double k = 1.0 / (1.0 + c);
+                const double K[3][3] = {{0, -w[2], w[1]}, {w[2], 0, -w[0]}, {-w[1], w[0], 0}};
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        double kk = 0;
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) kk += K[i][t] * K[t][j];
+                        R[i][j] = (i == j ? 1.0 : 0.0) + K[i][j] + k * kk;
+                    }
+            } else {
+                double a[3] = {fabs(u1[0]) < 0.6 ? 1.0 : 0.0, fabs(u1[0]) < 0.6 ? 0.0 : 1.0, 0.0}, n[3];
+                cross3(u1, a, n);
+                const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) R[i][j] = 2.0 * n[i] * n[j] / (nn * nn) - (i == j ? 1.0 : 0.0);
+            }
+            status = 0;
+        } else {
+            status = 0;   // rank 0 (zero covariance): R = I, translation between the centroids
         }
     }
     if (status != 0) { cs[0] = cs[1] = cs[2] = 0.0; ct[0] = ct[1] = ct[2] = 0.0; }
@@ -221,6 +262,57 @@ __global__ void kabsch_solve_kernel(const double *__restrict__ partials, int nbl
 #pragma unroll
         for (int i = 0; i < 12; ++i) composed[(size_t)b * 12 + i] = o[i];
     }
+}
+
+// compute_rigid_transform's first two statements (network/model.py:81-84) for a GIVEN weight matrix W [B,M,N]:
+//   rowmass_j = sum_k W_jk,   y_j = (sum_k W_jk tgt_k) / (rowmass_j + eps)
+// One warp per row, 8 rows per block sharing target tiles staged in shared memory; W is read exactly once (HBM-bound).
+constexpr int ST_ROWS = 8, ST_TILE = 1024;
+__global__ __launch_bounds__(ST_ROWS * 32) void soft_targets_kernel(const float *__restrict__ W, long long w_bs, long long w_rs,
+                                                                    const float *__restrict__ tgt, int M, int N,
+                                                                    float *__restrict__ y, float *__restrict__ mass) {
+    __shared__ float st[ST_TILE * 3];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * ST_ROWS + warp;
+    const float *row = W + (size_t)b * w_bs + (size_t)(j < M ? j : 0) * w_rs;
+    const float *tb = tgt + (size_t)b * N * 3;
+    float s = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    for (int k0 = 0; k0 < N; k0 += ST_TILE) {
+        const int nk = min(ST_TILE, N - k0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nk * 3; t += ST_ROWS * 32) st[t] = tb[(size_t)k0 * 3 + t];
+        __syncthreads();
+        if (j < M)
+            for (int k = lane; k < nk; k += 32) {
+                const float w = row[k0 + k];
+                s += w;
+                ax = __fmaf_rn(w, st[3 * k], ax);
+                ay = __fmaf_rn(w, st[3 * k + 1], ay);
+                az = __fmaf_rn(w, st[3 * k + 2], az);
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        az += __shfl_xor_sync(0xffffffffu, az, o);
+    }
+    if (lane == 0 && j < M) {
+        const float inv = 1.f / (s + 1e-16f);
+        mass[(size_t)b * M + j] = s;
+        y[((size_t)b * M + j) * 3 + 0] = ax * inv;
+        y[((size_t)b * M + j) * 3 + 1] = ay * inv;
+        y[((size_t)b * M + j) * 3 + 2] = az * inv;
+    }
+}
+
+int launch_soft_targets(const float *W, long long w_bs, long long w_rs, const float *tgt, int B, int M, int N, float *y, float *mass,
+                        cudaStream_t st) {
+    dim3 grid(cdiv(M, ST_ROWS), B);
+    soft_targets_kernel<<<grid, ST_ROWS * 32, 0, st>>>(W, w_bs, w_rs, tgt, M, N, y, mass);
+    DSIR_LAUNCH_CHECK();
+    return DSIR_OK;
 }
 
 int kabsch_num_blocks(int M) {

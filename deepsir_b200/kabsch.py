@@ -6,13 +6,13 @@ import torch
 from . import _lib as L
 
 
-def _solve(src_p, tgt_p, w, w_bs, gather, B, M, dev, want_moments=False):
+def _solve(src_p, tgt_p, w, w_bs, gather, B, M, dev, want_moments=False, n_tgt=0):
     T = torch.empty(B, 3, 4, dtype=torch.float32, device=dev)
     status = torch.empty(B, dtype=torch.int32, device=dev)
     mom = torch.empty(B, 17, dtype=torch.float64, device=dev) if want_moments else None
     lib = L.lib()
     ws = L.workspace(lib.dsir_kabsch_workspace_bytes(B, M), dev)
-    L.check(lib.dsir_kabsch(src_p, tgt_p, L.ptr(w), w_bs, L.ptr(gather), B, M, T.data_ptr(), status.data_ptr(),
+    L.check(lib.dsir_kabsch(src_p, tgt_p, L.ptr(w), w_bs, L.ptr(gather), B, M, int(n_tgt), T.data_ptr(), status.data_ptr(),
                             L.ptr(mom), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)), "dsir_kabsch")
     return T, status, mom
 
@@ -53,7 +53,8 @@ def kabsch_gather(xyz_src, xyz_ref, indexs, weights):
     w = weights.reshape(B, J)
     if w.stride(1) != 1:
         w = w.contiguous()
-    T, status, _ = _solve(L.points_b3m(xyz_src), L.points_b3m(xyz_ref), w, w.stride(0), indexs.contiguous(), B, J, dev)
+    T, status, _ = _solve(L.points_b3m(xyz_src), L.points_b3m(xyz_ref), w, w.stride(0), indexs.contiguous(), B, J, dev,
+                          n_tgt=xyz_ref.shape[2])
     return T, status
 
 
@@ -70,7 +71,8 @@ def kabsch_moments(src, tgt, weights, gather=None, layout="bm3"):
     lib = L.lib()
     ws = L.workspace(lib.dsir_kabsch_workspace_bytes(B, M), dev)
     g = gather.contiguous() if gather is not None else None
-    L.check(lib.dsir_kabsch_moments(pts(src), pts(tgt), w.data_ptr(), w.stride(0), L.ptr(g), B, M, mom.data_ptr(),
+    n_tgt = (tgt.shape[1] if layout == "bm3" else tgt.shape[2]) if g is not None else 0
+    L.check(lib.dsir_kabsch_moments(pts(src), pts(tgt), w.data_ptr(), w.stride(0), L.ptr(g), B, M, n_tgt, mom.data_ptr(),
                                     ws.data_ptr(), ws.numel(), L.stream_ptr(dev)), "dsir_kabsch_moments")
     return mom
 
@@ -89,12 +91,19 @@ def kabsch_from_moments(moments):
 
 def compute_rigid_transform(src, tgt, weights):
     """network/model.py:68-116 (soft).  src [B,M,3], tgt [B,N,3], weights [B,M,N] -> (T, invalid_gradient).
-    The [B,M,N] weights are an input of this signature, so the row mass and the soft targets come from two
-    library GEMV-shaped torch ops (plumbing); the fused path that never forms [M,N] is match_soft + kabsch_soft."""
+    The [B,M,N] weights are an input of this signature: one pass over them (dsir_soft_targets) gives the row masses and
+    the soft targets; the fused path that never forms [M,N] is match_soft + kabsch_soft."""
     dev = L.require_cuda(src, tgt, weights)
-    ws_ = weights.sum(dim=2)
-    y = (weights @ tgt) / (ws_[:, :, None] + 1e-16)
-    return kabsch_soft(src, y, ws_)
+    B, M, N = weights.shape
+    if weights.dtype != torch.float32:
+        raise L.DeepSIRError("compute_rigid_transform expects float32 weights")
+    w = weights if weights.stride(2) == 1 else weights.contiguous()
+    tg = tgt[:, :, :3].contiguous()
+    y = torch.empty(B, M, 3, dtype=torch.float32, device=dev)
+    mass = torch.empty(B, M, dtype=torch.float32, device=dev)
+    L.check(L.lib().dsir_soft_targets(w.data_ptr(), w.stride(0), w.stride(1), tg.data_ptr(), B, M, N, y.data_ptr(),
+                                      mass.data_ptr(), L.stream_ptr(dev)), "dsir_soft_targets")
+    return kabsch_soft(src, y, mass)
 
 
 def kabsch_soft(src, y_soft, rowmass):

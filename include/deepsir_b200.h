@@ -174,7 +174,11 @@ int dsir_sinkhorn(const float *log_alpha, int B, int J, int K, int n_iters, int 
  * so both [B,M,3] (model.py:586) and [B,3,M] (the loop's layout) work without a transpose copy.
  *   weights w[b,m] = w_base[b * w_bs + m]
  *   gather (nullable) [B,M] int64: tgt point for row m is tgt[b, gather[b,m]] (fuses model.py:571)
- *   T [B,3,4] fp32;  status [B] int32: 0 ok, 1 degenerate (rank<2 / non-finite) -> identity written
+ *   n_tgt: points of the tgt cloud the gather indices refer to; > 0: an index outside [0, n_tgt) is never dereferenced
+ *          and poisons its pair (status 1) - the reference's torch.gather raises (network/tools.py:211-221); 0: unchecked
+ *   T [B,3,4] fp32;  status [B] int32: 0 ok, 1 non-finite input / bad gather index -> identity written.  Rank-deficient
+ *          covariances are NOT an error (the reference does not flag them either): rank 1 -> the minimal rotation that
+ *          aligns the one determined direction, rank 0 -> R = I; the centroid translation is kept.
  *   moments (nullable) [B,17] fp64: additive raw moments {S|w|, Sw, Swx(3), Swy(3), Swxy(9)}
  * ---------------------------------------------------------------------------------------------- */
 typedef struct dsir_points {
@@ -184,14 +188,19 @@ typedef struct dsir_points {
 
 size_t dsir_kabsch_workspace_bytes(int B, int M);
 int dsir_kabsch(dsir_points src, dsir_points tgt, const float *w, int64_t w_batch_stride, const int64_t *gather,
-                int B, int M, float *T, int32_t *status, double *moments, void *ws, size_t ws_bytes,
+                int B, int M, int n_tgt, float *T, int32_t *status, double *moments, void *ws, size_t ws_bytes,
                 dsir_stream_t stream);
 /* first half only (for row-block sharding across GPUs): moments [B,17] of this rank's rows */
 int dsir_kabsch_moments(dsir_points src, dsir_points tgt, const float *w, int64_t w_batch_stride,
-                        const int64_t *gather, int B, int M, double *moments, void *ws, size_t ws_bytes,
+                        const int64_t *gather, int B, int M, int n_tgt, double *moments, void *ws, size_t ws_bytes,
                         dsir_stream_t stream);
 /* second half: centred covariance from (all-reduced) moments, fp64 3x3 SVD, det fix, R,t */
 int dsir_kabsch_from_moments(const double *moments, int B, float *T, int32_t *status, dsir_stream_t stream);
+/* the first statements of compute_rigid_transform (network/model.py:81-84) for a GIVEN weight matrix:
+ * weights [B,M,N] (w[b,j,k] = base[b*w_batch_stride + j*w_row_stride + k]), tgt [B,N,3] contiguous ->
+ * rowmass [B,M] = sum_k w_jk,  y_soft [B,M,3] = (sum_k w_jk tgt_k) / (rowmass + 1e-16).  W is read once. */
+int dsir_soft_targets(const float *weights, int64_t w_batch_stride, int64_t w_row_stride, const float *tgt, int B, int M, int N,
+                      float *y_soft, float *rowmass, dsir_stream_t stream);
 /* soft variant, compute_rigid_transform (network/model.py:68-116) given the fused soft targets:
  * src [B,M,3], y_soft [B,M,3], rowmass [B,M] (sum_k W_jk) */
 int dsir_kabsch_soft(dsir_points src, const float *y_soft, const float *rowmass, int B, int M, float *T,

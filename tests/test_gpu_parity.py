@@ -318,12 +318,27 @@ def test_kabsch_planted_and_layouts():
 
 
 def test_kabsch_degenerate_cases():
+    # rank-1 covariance (collinear points): the reference returns a LAPACK-dependent rotation about the line and the centroid
+    # translation, without flagging; here the completion is the minimal rotation (identity for a pure shift) - never "invalid"
     line = torch.linspace(0, 1, 50)[None, :, None] * torch.tensor([1.0, 2.0, 3.0])
     T, st = D.compute_rigid_transform_2(cu(line), cu(line + 1.0), cu(torch.ones(1, 50, 1)), return_status=True)
-    assert st.item() == 1 and torch.equal(T.cpu(), O.se3_identity(1))
+    assert st.item() == 0
+    assert_pose_close(T, torch.cat([torch.eye(3), torch.ones(3, 1)], 1)[None])
+    Rq = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(2)))[0]
+    Rq = Rq * torch.linalg.det(Rq).sign()
+    T, st = D.compute_rigid_transform_2(cu(line), cu(line @ Rq.t() + 0.5), cu(torch.ones(1, 50, 1)), return_status=True)
+    Tc = T.cpu()[0]
+    assert st.item() == 0 and torch.allclose(Tc[:, :3] @ Tc[:, :3].t(), torch.eye(3), atol=1e-5) and torch.linalg.det(Tc[:, :3]) > 0.999
+    assert torch.allclose(line[0] @ Tc[:, :3].t() + Tc[:, 3], line[0] @ Rq.t() + 0.5, atol=1e-4)   # the line is mapped exactly
+    # rank 0 (all weights zero: centroids 0, covariance 0): identity like the reference, not flagged
     pts = torch.randn(2, 30, 3)
     T, inv = D.compute_rigid_transform_2(cu(pts), cu(pts), cu(torch.zeros(2, 30, 1)))
-    assert bool(inv) and torch.equal(T.cpu(), O.se3_identity(2))
+    assert not bool(inv) and torch.equal(T.cpu(), O.se3_identity(2))
+    # a single non-zero weight: zero covariance, the translation between the two points survives
+    w1 = torch.zeros(2, 30, 1); w1[:, 7] = 2.0
+    T, inv = D.compute_rigid_transform_2(cu(pts), cu(pts + 3.0), cu(w1))
+    assert not bool(inv)
+    assert_pose_close(T, torch.cat([torch.eye(3), torch.full((3, 1), 3.0)], 1).expand(2, -1, -1))
     bad = pts.clone(); bad[0, 3, 1] = float("nan")
     T, st = D.compute_rigid_transform_2(cu(bad), cu(pts), cu(torch.ones(2, 30, 1)), return_status=True)
     assert st.tolist() == [1, 0]
@@ -333,6 +348,20 @@ def test_kabsch_degenerate_cases():
     Rz = torch.diag(torch.tensor([-1.0, -1.0, 1.0]))
     T, _ = D.compute_rigid_transform_2(cu(pts), cu(pts @ Rz.t()), cu(torch.ones(2, 30, 1)))
     assert_pose_close(T, torch.cat([Rz, torch.zeros(3, 1)], 1).expand(2, -1, -1))
+
+
+def test_kabsch_gather_index_out_of_range_poisons_the_pair():
+    """torch.gather raises on an index outside the reference cloud (network/tools.py:211-221); the fused gather never
+    dereferences it and reports the pair through its status instead (invalid_gradient)."""
+    g = torch.Generator().manual_seed(8)
+    xs, xr = torch.randn(2, 3, 400, generator=g), torch.randn(2, 3, 500, generator=g)
+    idx = torch.randint(0, 500, (2, 400), generator=g)
+    w = torch.rand(2, 400, generator=g)
+    T0, st0 = D.kabsch_gather(cu(xs), cu(xr), cu(idx), cu(w))
+    bad = idx.clone(); bad[1, 17] = 500; bad[1, 200] = -3
+    T1, st1 = D.kabsch_gather(cu(xs), cu(xr), cu(bad), cu(w))
+    assert st0.tolist() == [0, 0] and st1.tolist() == [0, 1]
+    assert torch.equal(T1[0], T0[0]) and torch.equal(T1[1].cpu(), O.se3_identity(1)[0])
 
 
 def test_se3_golden(golden):
