@@ -175,15 +175,17 @@ bool take_grid_slot(Workspace &W, int B, int n, GridSlot *s) {
 // spatial structure of one support cloud: brute force (none), uniform grid (knn_grid.cu), bucket tree (knn_tree.cu)
 enum { SP_BRUTE = 0, SP_GRID = 1, SP_TREE = 2 };
 // `Nmax` = the largest cloud that has to be indexed in the same call (support and queries share one structure type)
-int knn_structure(int algo, int Ns, int Nmax, int k) {
+int knn_structure(int algo, int Ns, int Nmax, int k, bool pyramid = false) {
     if (algo == DSIR_KNN_BRUTE) return SP_BRUTE;
     if (algo == DSIR_KNN_GRID) return SP_GRID;
     if (algo == DSIR_KNN_TREE) return k <= KNN_TREE_MAX_K ? SP_TREE : SP_GRID;   // the caller checks the size limit
-    // AUTO: the grid.  Measured on the C2 cloud (profiles/knn_tree_r2.md): the bucket tree's Morton leaves make a warp scan
-    // 25 leaves for its 32 queries (a kd-ordered partition would need 12) and the level-0 self-kNN takes 1.02 ms per 32
-    // clouds against 0.46 ms for the grid, so the tree stays an explicit choice (DSIR_KNN_TREE).
-    (void)Nmax;
-    return Ns < KNN_GRID_MIN_POINTS ? SP_BRUTE : SP_GRID;
+    if (Ns < KNN_GRID_MIN_POINTS) return SP_BRUTE;
+    // AUTO.  Measured on 32 C2 clouds (profiles/knn_tree_r2.md): one k = 16 self query costs 0.53 ms through the bucket tree
+    // (0.13 ms of it the kd-ordered build) against 0.47 ms through the grid, but a whole pyramid - whose 1-NN up-sampling
+    // queries and coarse levels re-use the trees - 0.67 ms against 0.72 ms, and the pair of pyramids of a step 1.11 against
+    // 1.28 ms: pyramids take the tree, single queries the grid.
+    if (pyramid && Nmax <= KNN_TREE_MAX_POINTS && k <= KNN_TREE_MAX_K) return SP_TREE;
+    return SP_GRID;
 }
 
 // tunables (overridable for experiments through DSIR_GRID_CPP / DSIR_GRID_R0)
@@ -292,7 +294,7 @@ static int pyramid_levels(int N, const int *ratios, int L, PyramidLevels *lv) {
 // cloud): n[0], n[1], ..., and the last sub-cloud m[L-1]
 static int pyramid_grid_sizes(const PyramidLevels &lv, int algo, int k, int *sizes, int *sp_out) {
     int ng = 0;
-    const int sp = knn_structure(algo, lv.n[0] >= KNN_TREE_MIN_POINTS ? lv.n[0] : KNN_TREE_MIN_POINTS, lv.n[0], k);
+    const int sp = knn_structure(algo, lv.n[0] >= KNN_TREE_MIN_POINTS ? lv.n[0] : KNN_TREE_MIN_POINTS, lv.n[0], k, true);
     *sp_out = sp;
     if (sp == SP_BRUTE) return 0;
     for (int l = 0; l <= lv.L; ++l) {

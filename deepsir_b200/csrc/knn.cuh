@@ -100,7 +100,7 @@ int launch_knn_grid_query(const KnnGridQueryParams &P, int B, cudaStream_t st);
 namespace dsir {
 
 constexpr int KNN_TREE_MIN_POINTS = 512;     // below this the brute-force kernel is used
-constexpr int KNN_TREE_MAX_POINTS = 24576;   // the build sorts one cloud in the shared memory of one CTA
+constexpr int KNN_TREE_MAX_POINTS = 17408;   // the build sorts one cloud in the shared memory of one CTA (12 bytes per point)
 constexpr int KNN_TREE_MAX_K = 16;           // sorted register list of the query kernel; larger k -> grid path
 
 struct KnnLeaf {   // 512 bytes: one cp.async.bulk per leaf

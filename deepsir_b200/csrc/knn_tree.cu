@@ -1,11 +1,11 @@
-// Exact xyz k-nearest neighbours on a bucket tree of Morton-ordered leaves — the warp-cooperative fast path for level
-// clouds of 512 ... 24576 points (dataloader/data_base.py:165,170 call sites; contract of knn.cu / oracle/knn_oracle.c):
+// Exact xyz k-nearest neighbours on a bucket tree of kd-ordered leaves — the warp-cooperative path for level
+// clouds of up to 17408 points (dataloader/data_base.py:165,170 call sites; contract of knn.cu / oracle/knn_oracle.c):
 //     d2 = fma(dz,dz, fma(dy,dy, dx*dx)) in fp32, results ascending in (d2, support index).
 //
-//   build   one CTA per (cloud, tree): bounding box -> 30-bit Morton keys -> stable LSD radix sort of the permutation in
-//           shared memory (8-bit digits, per-warp histograms ranked with match.any) -> LEAVES of 32 consecutive points,
-//           stored as one 512-byte structure-of-arrays block {-x[32], -y[32], -z[32], index[32]} -> bounding box per leaf
-//           and per SUPERNODE (32 consecutive leaves).  A cloud of 16384 points is 512 leaves / 16 supernodes.
+//   build   one CTA per (cloud, tree): kd-ordered LEAVES of 32 points (level-by-level counting sorts in shared memory
+//           along each segment's widest axis, 8 / 4-way splits at leaf multiples), stored as one 512-byte
+//           structure-of-arrays block {-x[32], -y[32], -z[32], index[32]} -> bounding box per leaf and per SUPERNODE
+//           (32 consecutive leaves).  A cloud of 16384 points is 512 leaves / 16 supernodes.
 //   query   one WARP per query leaf, lane = query.  The 32 queries of a leaf are spatial neighbours, so they share one
 //           candidate set: the warp walks supernodes and leaves nearest-first (lane = child: 32 box tests per instruction
 //           sequence, no stack, no divergence), an elected lane stages each chosen leaf into shared memory with ONE
@@ -29,7 +29,7 @@ namespace {
 constexpr int TREE_BUILD_THREADS = 1024;
 constexpr int TREE_QWARPS = 4;     // query leaves (warps) per CTA
 constexpr int TREE_NST = 2;        // staging ring depth per warp
-constexpr int TREE_QCAP = 16;      // pending-candidate queue entries per lane
+constexpr int TREE_QCAP = 32;      // pair-buffer entries per lane: <= 16 kept + <= 16 new
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NOIDX = 0x7fffffff;
 
@@ -48,16 +48,7 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
-__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-
-__device__ __forceinline__ unsigned part1by2(unsigned v) {   // spread the low 10 bits to every third bit
-    v &= 0x3ffu;
-    v = (v | (v << 16)) & 0x030000FFu;
-    v = (v | (v << 8)) & 0x0300F00Fu;
-    v = (v | (v << 4)) & 0x030C30C3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
+__device__ __forceinline__ void sts_u16(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
 
 // lower bound of d2 between two boxes / a point and a box, in the operation order of d2 (see the header comment)
 __device__ __forceinline__ float gap1(float lo, float hi, float qlo, float qhi) {
@@ -71,22 +62,120 @@ __device__ __forceinline__ float gap2_3(float gx, float gy, float gz) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// build
+// build: kd-ordered leaves
+//   The leaf order decides how many leaves the 32 queries of a warp have to scan: Morton order needs 24 leaves per warp on
+//   the C2 cloud, median splits along the widest axis need 12.5 (tools/knn_leaf_sim.py).  The build therefore sorts level
+//   by level: every segment (a contiguous range of leaves) is counting-sorted along ITS OWN widest axis with an 8-bit key
+//   re-quantised to its own extent, and cut into 8 (first level, when the depth is odd) or 4 children at leaf multiples -
+//   four levels for 512 leaves instead of nine binary ones, with the leaf quality of exact medians (the cut falls inside
+//   one of 256 key bins).  Coordinates are kept as 16-bit quantised copies in shared memory; the quantisation only shapes
+//   the leaves, the search is exact for any order.
 // ---------------------------------------------------------------------------------------------------------------
+// lanes with the same 8-bit key (among the lanes flagged valid)
+__device__ __forceinline__ unsigned peers8(unsigned key, bool valid) {
+    unsigned m = __ballot_sync(FULL, valid);
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const bool on = (key >> bit) & 1u;
+        const unsigned bal = __ballot_sync(FULL, on);
+        m &= on ? bal : ~bal;
+    }
+    return m;
+}
+
+struct BuildSmem {
+    unsigned short *q[3];     // [cap] 16-bit quantised coordinates, indexed by original point index
+    unsigned short *pin, *pout;   // [cap] permutation (ping / pong)
+    unsigned short *hist;     // [32 warps][256]
+    unsigned short *tmp;      // [cap] per position: key | rank among equal keys of the 32-block << 8 | last of its group << 13
+};
+
+// 8-bit key of element e along axis `qa`, relative to [base, base + ext]
+__device__ __forceinline__ unsigned key8(const unsigned short *qa, unsigned e, int base, float mul) {
+    return (unsigned)min(255, __float2int_rz((float)((int)qa[e] - base) * mul));
+}
+
+// one warp sorts positions [p0, p1) of pin into pout along the segment's widest axis (no block-level synchronisation)
+__device__ void warp_sort_segment(const BuildSmem &B, int p0, int p1, const float *unit, unsigned short *wh, int lane) {
+    int lo[3] = {65535, 65535, 65535}, hi[3] = {0, 0, 0};
+    for (int pos = p0 + lane; pos < p1; pos += 32) {
+        const unsigned e = B.pin[pos];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const int v = B.q[a][e]; lo[a] = min(lo[a], v); hi[a] = max(hi[a], v); }
+    }
+    float best = -1.f;
+    int ax = 0, base = 0, ext = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int l = __reduce_min_sync(FULL, lo[a]), h = __reduce_max_sync(FULL, hi[a]);
+        const float w = (float)(h - l) * unit[a];
+        if (w > best) { best = w; ax = a; base = l; ext = h - l; }
+    }
+    const unsigned short *qa = B.q[ax];
+    const float mul = ext > 0 ? 255.99f / (float)ext : 0.f;
+    for (int i = lane; i < 256; i += 32) wh[i] = 0;
+    __syncwarp();
+    for (int pos0 = p0; pos0 < p1; pos0 += 32) {
+        const int pos = pos0 + lane;
+        const bool v = pos < p1;
+        const unsigned e = v ? B.pin[pos] : 0u;
+        const unsigned k = v ? key8(qa, e, base, mul) : 0u;
+        const unsigned m = peers8(k, v);
+        const int rank = __popc(m & ((1u << lane) - 1u)), cnt = __popc(m);
+        if (v && rank == 0) wh[k] = (unsigned short)(wh[k] + cnt);
+        if (v) B.tmp[pos] = (unsigned short)(k | (rank << 8) | ((rank == cnt - 1) << 13));
+        __syncwarp();
+    }
+    {   // exclusive scan of the 256 bins: lane owns bins 8 lane .. 8 lane + 7
+        int loc[8], sum = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { loc[i] = wh[8 * lane + i]; sum += loc[i]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += u;
+        }
+        int run = incl - sum;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { wh[8 * lane + i] = (unsigned short)run; run += loc[i]; }
+    }
+    __syncwarp();
+    for (int pos0 = p0; pos0 < p1; pos0 += 32) {   // scatter: key / rank / group end come from the count pass
+        const int pos = pos0 + lane;
+        const bool v = pos < p1;
+        const unsigned t = v ? B.tmp[pos] : 0u;
+        const unsigned k = t & 255u;
+        const int rank = (t >> 8) & 31;
+        const int off = v ? (int)wh[k] : 0;
+        __syncwarp();
+        if (v && (t >> 13)) wh[k] = (unsigned short)(off + rank + 1);
+        __syncwarp();
+        if (v) B.pout[p0 + off + rank] = B.pin[pos];
+    }
+}
+
 __global__ __launch_bounds__(TREE_BUILD_THREADS) void knn_tree_build_kernel(KnnTreeBuildParams P) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ float s_red[6][32];
     __shared__ float s_box[8];
     __shared__ int s_wtot[32];
+    __shared__ int s_seg[8];                 // CTA-wide sort of one segment: axis, base, ext
+    __shared__ int s_ired[6][32];
+    __shared__ unsigned short s_b0[514], s_b1[514];   // segment boundaries in leaves (current / next level)
 
     const int g = blockIdx.x, b = blockIdx.y;
     const int n = P.n[g];
     const int nleaf = (n + 31) >> 5, nsuper = (nleaf + 31) >> 5, nlpad = nsuper * 32;
     const float4 *pts = P.pts4 + (size_t)b * P.pts_bs;
-    unsigned *key = (unsigned *)sm_raw;                            // [cap]
-    unsigned short *pa = (unsigned short *)(key + P.cap);          // [cap] permutation (ping)
-    unsigned short *pb = pa + P.cap;                               // [cap] permutation (pong)
-    unsigned short *hist = pb + P.cap;                             // [32 warps][256 digits]
+    BuildSmem B;
+    B.q[0] = (unsigned short *)sm_raw;
+    B.q[1] = B.q[0] + P.cap;
+    B.q[2] = B.q[1] + P.cap;
+    B.pin = B.q[2] + P.cap;
+    B.pout = B.pin + P.cap;
+    B.hist = B.pout + P.cap;
+    B.tmp = B.hist + 32 * 256;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- bounding box (NaN coordinates are ignored by fminf / fmaxf) ----
@@ -104,95 +193,147 @@ __global__ __launch_bounds__(TREE_BUILD_THREADS) void knn_tree_build_kernel(KnnT
     }
     __syncthreads();
     if (tid == 0) {
-        float L[3], ext = 0.f;
         for (int a = 0; a < 3; ++a) {
             float l = INFINITY, h = -INFINITY;
             for (int w = 0; w < TREE_BUILD_THREADS / 32; ++w) { l = fminf(l, s_red[a][w]); h = fmaxf(h, s_red[3 + a][w]); }
             if (!(l <= h) || !isfinite(l) || !isfinite(h)) { l = 0.f; h = 0.f; }
-            L[a] = l;
-            ext = fmaxf(ext, h - l);
+            const float ext = h - l;
+            s_box[a] = l;
+            s_box[3 + a] = (ext > 0.f && isfinite(ext)) ? 65535.0f / ext : 0.f;   // quantisation scale of the axis
         }
-        s_box[0] = L[0]; s_box[1] = L[1]; s_box[2] = L[2];
-        s_box[3] = (ext > 0.f && isfinite(ext)) ? 1023.0f / ext : 0.f;   // cubic cells: one scale for the three axes
     }
     __syncthreads();
-    const float ox = s_box[0], oy = s_box[1], oz = s_box[2], scale = s_box[3];
-
-    // ---- Morton keys (the quantisation only shapes the leaves; the search is exact for any order) ----
+    float unit[3];                            // length of one quantisation step per axis (to compare extents across axes)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) unit[a] = s_box[3 + a] > 0.f ? 1.0f / s_box[3 + a] : 0.f;
     for (int i = tid; i < n; i += TREE_BUILD_THREADS) {
         const float4 p = pts[i];
-        const int ix = min(max(__float2int_rz((p.x - ox) * scale), 0), 1023);
-        const int iy = min(max(__float2int_rz((p.y - oy) * scale), 0), 1023);
-        const int iz = min(max(__float2int_rz((p.z - oz) * scale), 0), 1023);
-        key[i] = part1by2((unsigned)ix) | (part1by2((unsigned)iy) << 1) | (part1by2((unsigned)iz) << 2);
+        B.q[0][i] = (unsigned short)min(max(__float2int_rz((p.x - s_box[0]) * s_box[3]), 0), 65535);
+        B.q[1][i] = (unsigned short)min(max(__float2int_rz((p.y - s_box[1]) * s_box[4]), 0), 65535);
+        B.q[2][i] = (unsigned short)min(max(__float2int_rz((p.z - s_box[2]) * s_box[5]), 0), 65535);
+        B.pin[i] = (unsigned short)i;
     }
+    if (tid == 0) { s_b0[0] = 0; s_b0[1] = (unsigned short)nleaf; }
+    __syncthreads();
 
-    // ---- stable LSD radix sort of the permutation, 4 passes of 8 bits.  Warp w owns a contiguous range of 32-blocks;
-    //      inside a block the rank of an element among equal digits comes from match.any ----
-    const int bpw = (nleaf + 31) >> 5;                       // 32-blocks per warp
-    const int blk0 = min(warp * bpw, nleaf), blk1 = min(blk0 + bpw, nleaf);
-    unsigned short *pin = pa, *pout = pb;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = pass * 8;
-        for (int i = tid; i < 32 * 256; i += TREE_BUILD_THREADS) hist[i] = 0;
-        __syncthreads();                                     // also orders key[] / pout writes of the previous step
-        unsigned short *wh = hist + warp * 256;
-        for (int blk = blk0; blk < blk1; ++blk) {
-            const int pos = blk * 32 + lane;
-            const bool v = pos < n;
-            const unsigned e = v ? (pass == 0 ? (unsigned)pos : (unsigned)pin[pos]) : 0u;
-            const unsigned dg = v ? ((key[e] >> shift) & 255u) : 0xffffu;
-            const unsigned m = __match_any_sync(FULL, dg);
-            if (v && lane == __ffs(m) - 1) wh[dg] = (unsigned short)(wh[dg] + __popc(m));
-            __syncwarp();
-        }
-        __syncthreads();
-        // exclusive scan in (digit-major, warp-minor) order: entry e = digit * 32 + warp; thread t owns entries 8t .. 8t+7
-        {
-            const int dg = tid >> 2, w0 = (tid & 3) * 8;
-            int loc[8], sum = 0;
+    // ---- levels: depth T = floor(log2(nleaf)) binary levels, grouped as [8 if T is odd and >= 3 | 2 if T == 1], 4, 4, ... ----
+    int T = 0;
+    while ((2 << T) <= nleaf) ++T;
+    unsigned short *bc = s_b0, *bn = s_b1;
+    int S = 1;
+    while (T > 0) {
+        const int f = (T == 1) ? 2 : ((T & 1) ? 8 : 4);
+        T -= (f == 8) ? 3 : (f == 4 ? 2 : 1);
+        if (S < 32) {
+            // few, large segments: the whole CTA sorts them one after the other (warp w owns a contiguous range of the
+            // segment's 32-blocks; per-warp histograms; exclusive scan in (key-major, warp-minor) order)
+            for (int sgm = 0; sgm < S; ++sgm) {
+                const int p0 = bc[sgm] * 32, p1 = min(bc[sgm + 1] * 32, n);
+                int l3[3] = {65535, 65535, 65535}, h3[3] = {0, 0, 0};
+                for (int pos = p0 + tid; pos < p1; pos += TREE_BUILD_THREADS) {
+                    const unsigned e = B.pin[pos];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { loc[i] = hist[(w0 + i) * 256 + dg]; sum += loc[i]; }
-            int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += u;
-            }
-            if (lane == 31) s_wtot[warp] = incl;
-            __syncthreads();
-            if (warp == 0) {
-                const int u = s_wtot[lane];
-                int inc2 = u;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(FULL, inc2, o);
-                    if (lane >= o) inc2 += t;
+                    for (int a = 0; a < 3; ++a) { const int v = B.q[a][e]; l3[a] = min(l3[a], v); h3[a] = max(h3[a], v); }
                 }
-                s_wtot[lane] = inc2 - u;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const int l = __reduce_min_sync(FULL, l3[a]), h = __reduce_max_sync(FULL, h3[a]);
+                    if (lane == 0) { s_ired[a][warp] = l; s_ired[3 + a][warp] = h; }
+                }
+                for (int i = tid; i < 32 * 256; i += TREE_BUILD_THREADS) B.hist[i] = 0;
+                __syncthreads();
+                if (tid == 0) {
+                    float best = -1.f;
+                    for (int a = 0; a < 3; ++a) {
+                        int l = 65535, h = 0;
+                        for (int w = 0; w < 32; ++w) { l = min(l, s_ired[a][w]); h = max(h, s_ired[3 + a][w]); }
+                        const float wdt = (float)(h - l) * unit[a];
+                        if (wdt > best) { best = wdt; s_seg[0] = a; s_seg[1] = l; s_seg[2] = h - l; }
+                    }
+                }
+                __syncthreads();
+                const unsigned short *qa = B.q[s_seg[0]];
+                const int base = s_seg[1];
+                const float mul = s_seg[2] > 0 ? 255.99f / (float)s_seg[2] : 0.f;
+                const int nblk = (p1 - p0 + 31) >> 5, bpw = (nblk + 31) >> 5;
+                const int blk0 = min(warp * bpw, nblk), blk1 = min(blk0 + bpw, nblk);
+                unsigned short *wh = B.hist + warp * 256;
+                for (int blk = blk0; blk < blk1; ++blk) {
+                    const int pos = p0 + blk * 32 + lane;
+                    const bool v = pos < p1;
+                    const unsigned e = v ? B.pin[pos] : 0u;
+                    const unsigned k = v ? key8(qa, e, base, mul) : 0u;
+                    const unsigned m = peers8(k, v);
+                    const int rank = __popc(m & ((1u << lane) - 1u)), cnt = __popc(m);
+                    if (v && rank == 0) wh[k] = (unsigned short)(wh[k] + cnt);
+                    if (v) B.tmp[pos] = (unsigned short)(k | (rank << 8) | ((rank == cnt - 1) << 13));
+                    __syncwarp();
+                }
+                __syncthreads();
+                {   // entry e = key * 32 + warp; thread t owns entries 8t .. 8t+7
+                    const int dg = tid >> 2, w0 = (tid & 3) * 8;
+                    int loc[8], sum = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { loc[i] = B.hist[(w0 + i) * 256 + dg]; sum += loc[i]; }
+                    int incl = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += u;
+                    }
+                    if (lane == 31) s_wtot[warp] = incl;
+                    __syncthreads();
+                    if (warp == 0) {
+                        const int u = s_wtot[lane];
+                        int inc2 = u;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(FULL, inc2, o);
+                            if (lane >= o) inc2 += t;
+                        }
+                        s_wtot[lane] = inc2 - u;
+                    }
+                    __syncthreads();
+                    int run = s_wtot[warp] + incl - sum;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { B.hist[(w0 + i) * 256 + dg] = (unsigned short)run; run += loc[i]; }
+                }
+                __syncthreads();
+                for (int blk = blk0; blk < blk1; ++blk) {
+                    const int pos = p0 + blk * 32 + lane;
+                    const bool v = pos < p1;
+                    const unsigned t = v ? B.tmp[pos] : 0u;
+                    const unsigned k = t & 255u;
+                    const int rank = (t >> 8) & 31;
+                    const int off = v ? (int)wh[k] : 0;
+                    __syncwarp();
+                    if (v && (t >> 13)) wh[k] = (unsigned short)(off + rank + 1);
+                    __syncwarp();
+                    if (v) B.pout[p0 + off + rank] = B.pin[pos];
+                }
+                __syncthreads();
+            }
+        } else {
+            // many small segments: one warp per segment, no block-level synchronisation inside
+            for (int sgm = warp; sgm < S; sgm += TREE_BUILD_THREADS / 32) {
+                const int p0 = bc[sgm] * 32, p1 = min(bc[sgm + 1] * 32, n);
+                if (p1 > p0) warp_sort_segment(B, p0, p1, unit, B.hist + warp * 256, lane);
             }
             __syncthreads();
-            int run = s_wtot[warp] + incl - sum;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { hist[(w0 + i) * 256 + dg] = (unsigned short)run; run += loc[i]; }
         }
-        __syncthreads();
-        for (int blk = blk0; blk < blk1; ++blk) {
-            const int pos = blk * 32 + lane;
-            const bool v = pos < n;
-            const unsigned e = v ? (pass == 0 ? (unsigned)pos : (unsigned)pin[pos]) : 0u;
-            const unsigned dg = v ? ((key[e] >> shift) & 255u) : 0xffffu;
-            const unsigned m = __match_any_sync(FULL, dg);
-            const int rank = __popc(m & ((1u << lane) - 1u));
-            const int base = v ? (int)wh[dg] : 0;
-            __syncwarp();
-            if (v && lane == __ffs(m) - 1) wh[dg] = (unsigned short)(base + __popc(m));
-            __syncwarp();
-            if (v) pout[base + rank] = (unsigned short)e;
+        // children: segment [a, a + m) -> child c = [a + c m / f, a + (c + 1) m / f)
+        for (int i = tid; i < S * f; i += TREE_BUILD_THREADS) {
+            const int sgm = i / f, c = i % f;
+            const int a0 = bc[sgm], m = bc[sgm + 1] - a0;
+            bn[i] = (unsigned short)(a0 + (c * m) / f);
         }
+        if (tid == 0) bn[S * f] = (unsigned short)nleaf;
+        S *= f;
         __syncthreads();
-        unsigned short *t = pin; pin = pout; pout = t;
+        { unsigned short *t = bc; bc = bn; bn = t; }
+        { unsigned short *t = B.pin; B.pin = B.pout; B.pout = t; }
     }
+    const unsigned short *pin = B.pin;
 
     // ---- leaves + leaf boxes: warp w writes leaf it*32 + w ----
     KnnLeaf *leaves = P.leaves[g] + (size_t)b * nleaf;
@@ -242,12 +383,16 @@ __global__ __launch_bounds__(TREE_BUILD_THREADS) void knn_tree_build_kernel(KnnT
 // ---------------------------------------------------------------------------------------------------------------
 // query
 // ---------------------------------------------------------------------------------------------------------------
-// Selection: every lane keeps its k best (d, idx) pairs as a SORTED LIST IN REGISTERS (16 pairs).  Candidates that pass
-// the lane's threshold are appended to a per-lane queue in shared memory (column layout [slot][lane]: conflict free);
-// when some queue runs full, ALL lanes merge their pending entries at once with sorting networks (Batcher odd-even merge
-// sort of the 16 newest + bitonic merge with the list): branch-free, the same instruction stream for every lane, so a
-// flush costs the same whether one lane or all lanes have work - the opposite of per-candidate heap insertions, whose
-// data-dependent loops ran at ~35 % lane efficiency and took 2/3 of the instructions of the first version of this kernel.
+// Selection.  Every lane keeps (1) the 16 smallest DISTANCES seen so far as a sorted list in registers - only values, so a
+// compare-exchange is two FMNMX - whose last entry is the lane's k-th distance, and (2) the (d, idx) pairs that can still
+// belong to the answer, UNSORTED, in a per-lane buffer in shared memory (column layout [slot][lane]: conflict free).
+// Candidates with d <= k-th distance are appended to the buffer; when some lane has more than 8 new entries, ALL lanes
+// merge their (<= 16) new values into the register list with sorting networks (Batcher 16 + bitonic merge: branch-free,
+// the same instruction stream whether one lane or all have work) and compact their buffers to the entries with
+// d <= new k-th distance; more than k survivors means ties AT the k-th distance, resolved by index in a rare slow loop.
+// After the last leaf the <= 16 surviving pairs are sorted once, lexicographically.  (Earlier versions: per-candidate
+// shared-memory heaps - data-dependent sifts at ~35 % lane efficiency, 2/3 of the kernel's instructions; sorted (d, idx)
+// register lists merged by pair networks - 11 instructions per compare-exchange, 43 % of the instructions.)
 constexpr int TREE_K = 16;   // list length; clouds with k > 16 are served by the grid path
 
 struct Pair { float d; int i; };
@@ -271,26 +416,33 @@ __device__ __forceinline__ void sort16(float (&d)[16], int (&i)[16]) {
     CE(1, 2); CE(3, 4); CE(5, 6); CE(7, 8); CE(9, 10); CE(11, 12); CE(13, 14);
 #undef CE
 }
-// list (ascending) <- the 16 smallest of list U nw (both ascending), ascending
-__device__ __forceinline__ void merge16(float (&ld)[16], int (&li)[16], const float (&nd)[16], const int (&ni)[16]) {
+// the same network on values only (two FMNMX per compare-exchange)
+__device__ __forceinline__ void sort16v(float (&d)[16]) {
+#define CE(a, b) { const float lo_ = fminf(d[a], d[b]); d[b] = fmaxf(d[a], d[b]); d[a] = lo_; }
+    CE(0, 1); CE(2, 3); CE(4, 5); CE(6, 7); CE(8, 9); CE(10, 11); CE(12, 13); CE(14, 15);
+    CE(0, 2); CE(1, 3); CE(4, 6); CE(5, 7); CE(8, 10); CE(9, 11); CE(12, 14); CE(13, 15);
+    CE(1, 2); CE(5, 6); CE(9, 10); CE(13, 14); CE(0, 4); CE(1, 5); CE(2, 6); CE(3, 7);
+    CE(8, 12); CE(9, 13); CE(10, 14); CE(11, 15); CE(2, 4); CE(3, 5); CE(10, 12); CE(11, 13);
+    CE(1, 2); CE(3, 4); CE(5, 6); CE(9, 10); CE(11, 12); CE(13, 14); CE(0, 8); CE(1, 9);
+    CE(2, 10); CE(3, 11); CE(4, 12); CE(5, 13); CE(6, 14); CE(7, 15); CE(4, 8); CE(5, 9);
+    CE(6, 10); CE(7, 11); CE(2, 4); CE(3, 5); CE(6, 8); CE(7, 9); CE(10, 12); CE(11, 13);
+    CE(1, 2); CE(3, 4); CE(5, 6); CE(7, 8); CE(9, 10); CE(11, 12); CE(13, 14);
+#undef CE
+}
+// list (ascending) <- the 16 smallest values of list U nw (both ascending), ascending
+__device__ __forceinline__ void merge16v(float (&l)[16], const float (&nw)[16]) {
 #pragma unroll
-    for (int a = 0; a < 16; ++a) {   // lower half of the bitonic sequence (list, reversed nw)
-        const float bd = nd[15 - a];
-        const int bi = ni[15 - a];
-        const bool sw = ld[a] > bd || (ld[a] == bd && li[a] > bi);
-        ld[a] = sw ? bd : ld[a];
-        li[a] = sw ? bi : li[a];
-    }
+    for (int a = 0; a < 16; ++a) l[a] = fminf(l[a], nw[15 - a]);   // lower half of the bitonic sequence (list, reversed nw)
 #pragma unroll
     for (int k = 8; k >= 1; k >>= 1)
 #pragma unroll
         for (int a = 0; a < 16; ++a)
-            if ((a & k) == 0) ce(ld[a], li[a], ld[a + k], li[a + k]);
+            if ((a & k) == 0) { const float lo_ = fminf(l[a], l[a + k]); l[a + k] = fmaxf(l[a], l[a + k]); l[a] = lo_; }
 }
 
 __host__ __device__ constexpr int tree_warp_smem(bool k1) {
     // stages + mbarriers (padded to 128) + leaf-box cache [6][32] + queue
-    return TREE_NST * 512 + 128 + 768 + (k1 ? 0 : TREE_QCAP * 32 * 8);
+    return TREE_NST * 512 + 128 + 768 + (k1 ? 0 : TREE_QCAP * 32 * 6);   // pair buffer: fp32 distance + 16-bit index
 }
 
 template <bool K1>
@@ -306,7 +458,9 @@ __global__ __launch_bounds__(TREE_QWARPS * 32) void knn_tree_query_kernel(KnnTre
     uint64_t *bar = (uint64_t *)(wb + TREE_NST * 512);
     float *bxc = (float *)(wb + TREE_NST * 512 + 128);        // boxes of the current supernode's leaves [6][32]
     float *qd = (float *)(wb + TREE_NST * 512 + 128 + 768) + lane;   // queue columns of this lane: d, then idx
-    int *qi = (int *)(qd + TREE_QCAP * 32);
+    // indices as 16 bits (tree clouds hold <= 17408 points; 0xffff marks the padding slots of the last leaf): 6 instead of
+    // 8 bytes per entry is two more CTAs per SM
+    unsigned short *qi = (unsigned short *)((float *)(wb + TREE_NST * 512 + 128 + 768) + TREE_QCAP * 32) + lane;
 
     if (lane == 0) {
 #pragma unroll
@@ -334,16 +488,18 @@ __global__ __launch_bounds__(TREE_QWARPS * 32) void knn_tree_query_kernel(KnnTre
     const int k = P.k;
 
     // ---- selection state ----
-    // the k best so far, ascending, in slots [16 - k, 16): the first 16 - k slots hold (-inf, -1) sentinels that sort
-    // before every candidate, so that the k-th best is always ld[15] (no dynamic register index)
-    float ld[TREE_K];
-    int li[TREE_K];
+    // the 16 smallest distances so far, ascending; for k < 16 the first 16 - k slots hold -inf sentinels that sort before
+    // every candidate, so that the k-th distance is always sv[15] (no dynamic register index)
+    float sv[TREE_K];
 #pragma unroll
-    for (int p = 0; p < TREE_K; ++p) { ld[p] = p < TREE_K - k ? -INFINITY : INFINITY; li[p] = p < TREE_K - k ? -1 : NOIDX; }
+    for (int p = 0; p < TREE_K; ++p) sv[p] = p < TREE_K - k ? -INFINITY : INFINITY;
     float bd = INFINITY;                                      // K1: the best pair
     int bi = NOIDX;
     const uint32_t qbase = smem_u32(qd);
-    uint32_t qp = qbase;                                      // queue write cursor of this lane (entry j at qbase + 128 j)
+    uint32_t qp = qbase;                                      // buffer write cursor of this lane (entry j at qbase + 128 j)
+    const uint32_t ibase = smem_u32(qi);
+    uint32_t ip = ibase;                                      // ... and of its index column (entry j at ibase + 64 j)
+    int kept = 0;                                             // entries [0, kept) survived the last compaction
     // the lane's current k-th distance (as of the last flush); -inf for padding / NaN queries: nothing is ever appended
     float thr = qok ? INFINITY : -INFINITY;
     float bound = 0.f;                                        // warp maximum of thr
@@ -352,26 +508,43 @@ __global__ __launch_bounds__(TREE_QWARPS * 32) void knn_tree_query_kernel(KnnTre
     auto flush = [&]() {
         if (K1) return;
         const int cnt = (int)(qp - qbase) >> 7;
-        int mx = cnt;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
         TREE_STAT(3, 1);
-        TREE_STAT(4, (mx + 15) >> 4);
-        TREE_STAT(5, __reduce_add_sync(FULL, cnt));
-        for (int base = 0; base < mx; base += 16) {           // one round unless some queue holds more than 16
+        TREE_STAT(5, __reduce_add_sync(FULL, cnt - kept));
+        {   // the (<= 16) new values -> sorted -> merged into the register list
             float nd[16];
-            int ni[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const bool v = base + j < cnt;
-                nd[j] = v ? qd[(base + j) * 32] : INFINITY;
-                ni[j] = v ? qi[(base + j) * 32] : NOIDX;
-            }
-            sort16(nd, ni);
-            merge16(ld, li, nd, ni);
+            for (int j = 0; j < 16; ++j) nd[j] = kept + j < cnt ? qd[(kept + j) * 32] : INFINITY;
+            sort16v(nd);
+            merge16v(sv, nd);
         }
-        qp = qbase;
-        thr = qok ? ld[TREE_K - 1] : -INFINITY;
+        thr = qok ? sv[TREE_K - 1] : -INFINITY;
+        // compaction: keep the pairs with d <= k-th distance
+        int mx = __reduce_max_sync(FULL, cnt);
+        int w = 0;
+        for (int j = 0; j < mx; ++j) {
+            if (j < cnt) {
+                const float d = qd[j * 32];
+                if (d <= thr) {
+                    const unsigned short id = qi[j * 32];
+                    qd[w * 32] = d; qi[w * 32] = id;
+                    ++w;
+                }
+            }
+        }
+        // more than k survivors: ties at the k-th distance -> drop the tied entries with the largest indices
+        if (__any_sync(FULL, w > k)) {
+            TREE_STAT(4, 1);
+            while (w > k) {
+                int worst = -1, wi = -1;
+                for (int j = 0; j < w; ++j)
+                    if (qd[j * 32] == thr && (int)qi[j * 32] > wi) { wi = qi[j * 32]; worst = j; }
+                --w;
+                qd[worst * 32] = qd[w * 32]; qi[worst * 32] = qi[w * 32];
+            }
+        }
+        kept = w;
+        qp = qbase + (uint32_t)w * 128u;
+        ip = ibase + (uint32_t)w * 64u;
         bound_stale = true;
     };
 
@@ -490,13 +663,14 @@ __global__ __launch_bounds__(TREE_QWARPS * 32) void knn_tree_query_kernel(KnnTre
                         if (K1) {
                             if (d[u] < bd || (d[u] == bd && id[u] < bi)) { bd = d[u]; bi = id[u]; }
                         } else {
-                            if (d[u] <= thr) { sts_f32(qp, d[u]); sts_s32(qp + TREE_QCAP * 128, id[u]); qp += 128; }
+                            if (d[u] <= thr) { sts_f32(qp, d[u]); sts_u16(ip, id[u]); qp += 128; ip += 64; }
                         }
                     }
                 }
-                // every 8 candidates: room for 8 more in every queue?  (at most 16 entries are pending then: one round of
-                // the merge network; on the first leaf that is after 16 candidates, when every lane holds exactly 16)
-                if (!K1 && (__any_sync(FULL, qp > qbase + (TREE_QCAP - 8) * 128) || (nxt < 0 && h == 24))) flush();
+                // every 8 candidates: more than 8 new entries somewhere?  (at most 16 are new then: one round of the merge
+                // network, and kept + new <= 32 always fits the buffer; on the first leaf that is after 16 candidates, when
+                // every lane holds exactly 16)
+                if (!K1 && (__any_sync(FULL, qp > qbase + (uint32_t)(kept + 8) * 128u) || (nxt < 0 && h == 24))) flush();
             }
             if (K1) { thr = qok ? bd : -INFINITY; bound_stale = true; }
         }
@@ -515,14 +689,23 @@ __global__ __launch_bounds__(TREE_QWARPS * 32) void knn_tree_query_kernel(KnnTre
         if (o2) o2[0] = v;
         if (od) od[0] = bd;
     } else {
+        // the <= k surviving pairs, sorted once in lexicographic (d, idx) order
+        float fd[16];
+        int fi[16];
 #pragma unroll
-        for (int s = 0; s < TREE_K; ++s) {
-            const int p = s - (TREE_K - k);
-            if (p >= 0) {
-                const int64_t v = li[s] == NOIDX ? (int64_t)-1 : (int64_t)li[s];
+        for (int j = 0; j < 16; ++j) {
+            fd[j] = j < kept ? qd[j * 32] : INFINITY;
+            const int v16 = j < kept ? (int)qi[j * 32] : 0xffff;
+            fi[j] = v16 == 0xffff ? NOIDX : v16;
+        }
+        sort16(fd, fi);
+#pragma unroll
+        for (int p = 0; p < TREE_K; ++p) {
+            if (p < k) {
+                const int64_t v = fi[p] == NOIDX ? (int64_t)-1 : (int64_t)fi[p];
                 o[p] = v;
                 if (o2) o2[p] = v;
-                if (od) od[p] = ld[s];
+                if (od) od[p] = fd[p];
             }
         }
     }
@@ -562,7 +745,7 @@ int launch_knn_tree_build(const float4 *pts4, long long pts_bs, const KnnTreeVie
     cap = (cap + 1023) / 1024 * 1024;
     if (cap < 1024) cap = 1024;
     P.cap = cap;
-    const size_t smem = (size_t)cap * 8 + 32 * 256 * 2;
+    const size_t smem = (size_t)cap * 12 + 32 * 256 * 2;   // 3 x u16 coordinates + 2 x u16 permutation + u16 scratch per point, histograms
     DSIR_CUDA_TRY(cudaFuncSetAttribute(knn_tree_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ntrees, B);
     knn_tree_build_kernel<<<grid, TREE_BUILD_THREADS, smem, st>>>(P);

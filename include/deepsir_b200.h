@@ -39,7 +39,7 @@ enum { DSIR_METRIC_L2 = 0, DSIR_METRIC_EUCLIDEAN = 1, DSIR_METRIC_ACOS_DOT = 2, 
        DSIR_METRIC_SQDIFF_SQRT = 5 /* feat_dist 'euclidean': sqrt(sum (s-r)^2 + 1e-16) */ };
 /* algorithm selectors (0 = let the library choose) */
 enum { DSIR_KNN_AUTO = 0, DSIR_KNN_BRUTE = 1, DSIR_KNN_GRID = 2 /* uniform grid, any size */,
-       DSIR_KNN_TREE = 3 /* bucket tree of Morton leaves, clouds of <= 24576 points */ };
+       DSIR_KNN_TREE = 3 /* bucket tree of kd-ordered leaves: clouds of <= 17408 points, k <= 16 (else the grid) */ };
 enum { DSIR_MATCH_AUTO = 0, DSIR_MATCH_FP32 = 1 /* CUDA-core exact */, DSIR_MATCH_TC = 2 /* tcgen05 filter + fp32 refine */ };
 
 int dsir_version(void);
