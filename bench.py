@@ -589,12 +589,12 @@ def main():
                                        "CUDA events on its stream); frac_of_sustained uses bf16_tflops_sustained",
                         "ms_per_launch": filter_ms, "match_call_ms": match_ms,
                         "match_call_frac": flops / (match_ms / 1e3) / 1e12 / tc_peak},
-           "roofline_knn": {"bound": "hbm", "kernel": "knn pyramid (grid build + queries, both clouds of a step)",
+           "roofline_knn": {"bound": "hbm", "kernel": "knn pyramid (kd-ordered bucket-tree build + warp-cooperative queries, both clouds of a step)",
                             "achieved": knn_bytes / (knn_ms / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                             "frac": knn_bytes / (knn_ms / 1e3) / 1e9 / pk["hbm"], "ms_per_step": knn_ms,
                             "note": "HBM-bound by the scan/graph rule, but instruction bound in practice: ncu on the level-0 "
-                                    "query kernel shows issue slots 76 % busy, DRAM 1.8 % (profiles/ncu_digest_knn_r1f.txt); "
-                                    "brute-force equivalent: 5.73 GFLOP per pair"}}
+                                    "query kernel shows issue slots 54 % busy, DRAM < 2 % (profiles/ncu_digest_knn_tree_r2d.txt, "
+                                    "profiles/knn_tree_r2.md); brute-force equivalent: 5.73 GFLOP per pair"}}
     if rowblock is not None:
         out["rowblock"] = rowblock
     if not args.no_cpu_baseline and world == 1:      # the CPU port is timed beside the N=1 run only
