@@ -27,7 +27,15 @@ namespace dsir {
 namespace {
 
 constexpr int TREE_BUILD_THREADS = 1024;
-constexpr int TREE_QWARPS = 4;     // query leaves (warps) per CTA
+#ifndef DSIR_TREE_QWARPS
+#define DSIR_TREE_QWARPS 4
+#endif
+#ifndef DSIR_TREE_CHK
+#define DSIR_TREE_CHK 4
+#endif
+constexpr int TREE_QWARPS = DSIR_TREE_QWARPS;     // query leaves (warps) per CTA
+constexpr int TREE_CHK = DSIR_TREE_CHK;           // candidates between two looks at the buffers (4 or 8)
+constexpr int TREE_TRIG = 16 - TREE_CHK;          // flush when a lane has more new entries than this (<= 16 new at the flush)
 constexpr int TREE_NST = 2;        // staging ring depth per warp
 constexpr int TREE_QCAP = 32;      // pair-buffer entries per lane: <= 16 kept + <= 16 new
 constexpr unsigned FULL = 0xffffffffu;
@@ -642,9 +650,9 @@ __global__ __launch_bounds__(TREE_QWARPS * 32) void knn_tree_query_kernel(KnnTre
             TREE_STAT(2, __popc(__ballot_sync(FULL, need)));
             const float *S = stage + st * 128;
 #pragma unroll 1
-            for (int h = 0; h < 32; h += 8) {
+            for (int h = 0; h < 32; h += TREE_CHK) {
 #pragma unroll
-                for (int c = 0; c < 8; c += 4) {
+                for (int c = 0; c < TREE_CHK; c += 4) {
                     const float *Sc = S + h + c;
                     const ulonglong2 X = *(const ulonglong2 *)(Sc), Y = *(const ulonglong2 *)(Sc + 32), Z = *(const ulonglong2 *)(Sc + 64);
                     const int4 I = *(const int4 *)(Sc + 96);
@@ -667,10 +675,10 @@ __global__ __launch_bounds__(TREE_QWARPS * 32) void knn_tree_query_kernel(KnnTre
                         }
                     }
                 }
-                // every 8 candidates: more than 8 new entries somewhere?  (at most 16 are new then: one round of the merge
+                // every TREE_CHK candidates: more than TREE_TRIG new entries somewhere?  (at most 16 are new then: one round of the merge
                 // network, and kept + new <= 32 always fits the buffer; on the first leaf that is after 16 candidates, when
                 // every lane holds exactly 16)
-                if (!K1 && (__any_sync(FULL, qp > qbase + (uint32_t)(kept + 8) * 128u) || (nxt < 0 && h == 24))) flush();
+                if (!K1 && (__any_sync(FULL, qp > qbase + (uint32_t)(kept + TREE_TRIG) * 128u) || (nxt < 0 && h == 32 - TREE_CHK))) flush();
             }
             if (K1) { thr = qok ? bd : -INFINITY; bound_stale = true; }
         }
