@@ -92,6 +92,9 @@ _SIGS = {
     "dsir_match_soft_sweep": (_c.c_int, [Feat, Feat, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                          _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "dsir_match_soft_topk_workspace_bytes": (_c.c_size_t, [_c.c_int] * 5),
+    "dsir_match_soft_topk_fused": (_c.c_int, [_c.c_int] * 5),
+    "dsir_match_soft_topk_exhaustive_rows": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                                        _c.c_void_p, _c.c_void_p]),
     "dsir_match_soft": (_c.c_int, [Feat, Feat, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                    _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,
                                    _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),

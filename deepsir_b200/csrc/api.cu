@@ -560,18 +560,27 @@ size_t dsir_match_soft_workspace_bytes(int B, int C, int J, int K) {
     return fp32;
 }
 
-// extra workspace of the top-k pass: a row chunk of the distance matrix (<= 256 MB), chunk norms, reference norms, lse
-static size_t soft_topk_chunk_rows(int B, int J, int K) {
-    long long rows = (256ll << 20) / ((long long)B * K * 4);
+// Top-k soft weights.  Fused route (match_tc.cu, launch_match_tc_topk): two tensor-core sweeps + exact re-scoring of the
+// listed columns, nothing of size J x K.  Materialising route (small problems, C > 64, a column bias - the order is then not
+// the distance order): row chunks of the exact fp32 distance matrix (<= 256 MB, or whatever the workspace holds) + one warp
+// per row.  Both give the same bits.
+static size_t soft_topk_chunk_rows(int B, int J, int K, size_t budget = (size_t)256 << 20) {
+    long long rows = (long long)(budget / ((size_t)B * K * 4 + (size_t)B * 4));
     if (rows < 1) rows = 1;
     if (rows > J) rows = J;
     return (size_t)rows;
 }
+static size_t soft_topk_chunk_fixed(int B, int J, int K) { return ws_block((size_t)B * K * 4) + ws_block((size_t)B * J * 4) + 1024; }
 size_t dsir_match_soft_topk_workspace_bytes(int B, int C, int J, int K, int topk) {
     size_t base = dsir_match_soft_workspace_bytes(B, C, J, K);
     if (topk <= 0 || B <= 0 || J <= 0 || K <= 0) return base;
+    if (match_tc_topk_supported(B, C, J, K, topk)) {
+        const size_t fused = ws_block((size_t)B * J * 4) + match_tc_topk_workspace_bytes(B, C, J, K, topk) + 512;
+        const size_t one_row = soft_topk_chunk_fixed(B, J, K) + ws_block((size_t)B * K * 4) + ws_block((size_t)B * 4);
+        return base + (fused > one_row ? fused : one_row);
+    }
     const size_t Jc = soft_topk_chunk_rows(B, J, K);
-    return base + ws_block((size_t)B * Jc * K * 4) + ws_block((size_t)B * Jc * 4) + ws_block((size_t)B * K * 4) + ws_block((size_t)B * J * 4) + 256;
+    return base + soft_topk_chunk_fixed(B, J, K) + ws_block((size_t)B * Jc * K * 4) + ws_block((size_t)B * Jc * 4);
 }
 
 static int match_soft_core(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,
@@ -608,19 +617,34 @@ int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, cons
     if (topk > 32 || topk > K) return topk > K ? DSIR_ERR_BAD_ARG : DSIR_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (topk == 0) return match_soft_core(fs, fr, B, C, J, K, beta, alpha, col_bias, xyz_ref, y_soft, lse, ws, ws_bytes, st);
-    // ---- top-k: the fused pass gives lse (and y); the k largest weights of a row come from row chunks of the exact fp32
-    //      distance matrix (DENSE kernel), one warp per row ----
     const size_t base = dsir_match_soft_workspace_bytes(B, C, J, K);
     if (!ws || ws_bytes < dsir_match_soft_topk_workspace_bytes(B, C, J, K, topk)) return DSIR_ERR_WORKSPACE;
+    int rc;
+    if (match_tc_topk_supported(B, C, J, K, topk) && col_bias == nullptr) {
+        // ---- fused: lse (and y) from the online-softmax pass, the k best columns from two filter sweeps + exact re-scoring
+        Workspace W((char *)ws + base, ws_bytes - base);
+        float *lse_tmp = W.take<float>((size_t)B * J);
+        if (!W.ok()) return DSIR_ERR_WORKSPACE;
+        float *lse_use = lse ? lse : lse_tmp;
+        if ((rc = match_soft_core(fs, fr, B, C, J, K, beta, alpha, col_bias, xyz_ref, y_soft, lse_use, ws, base, st))) return rc;
+        MatchParams T{};
+        T.fs = fs; T.fr = fr; T.B = B; T.C = C; T.J = J; T.K = K; T.beta = beta; T.alpha = alpha; T.lse = lse_use;
+        const size_t used = base + ws_block((size_t)B * J * 4);
+        return launch_match_tc_topk(T, topk, topk_idx, topk_w, (char *)ws + used, ws_bytes - used, st);
+    }
+    // ---- materialising: the k largest weights of a row come from row chunks of the exact fp32 distance matrix (DENSE
+    //      kernel), one warp per row ----
     Workspace W((char *)ws + base, ws_bytes - base);
-    const int Jc = (int)soft_topk_chunk_rows(B, J, K);
-    float *chunk = W.take<float>((size_t)B * Jc * K);
-    float *ns_c = W.take<float>((size_t)B * Jc);
     float *nr = W.take<float>((size_t)B * K);
     float *lse_tmp = W.take<float>((size_t)B * J);
     if (!W.ok()) return DSIR_ERR_WORKSPACE;
+    const size_t left = ws_bytes - base - soft_topk_chunk_fixed(B, J, K);
+    int Jc = (int)soft_topk_chunk_rows(B, J, K, left < ((size_t)256 << 20) ? left : ((size_t)256 << 20));
+    while (Jc > 1 && ws_block((size_t)B * Jc * K * 4) + ws_block((size_t)B * Jc * 4) > left) --Jc;
+    float *chunk = W.take<float>((size_t)B * Jc * K);
+    float *ns_c = W.take<float>((size_t)B * Jc);
+    if (!W.ok()) return DSIR_ERR_WORKSPACE;
     float *lse_use = lse ? lse : lse_tmp;
-    int rc;
     if ((rc = match_soft_core(fs, fr, B, C, J, K, beta, alpha, col_bias, xyz_ref, y_soft, lse_use, ws, base, st))) return rc;
     if ((rc = launch_sqnorm(fr, B, C, K, nr, st))) return rc;
     for (int j0 = 0; j0 < J; j0 += Jc) {
@@ -634,6 +658,19 @@ int dsir_match_soft(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, cons
         if ((rc = launch_row_topk(chunk, B, jc, K, beta, alpha, col_bias, lse_use, J, j0, topk, topk_idx, topk_w, (long long)J * topk, st))) return rc;
     }
     return DSIR_OK;
+}
+
+int dsir_match_soft_topk_fused(int B, int C, int J, int K, int topk) {
+    return (B > 0 && J > 0 && K > 0 && match_tc_topk_supported(B, C, J, K, topk)) ? 1 : 0;
+}
+
+int dsir_match_soft_topk_exhaustive_rows(const void *ws, size_t ws_bytes, int B, int C, int J, int K, int topk, int32_t *host_out,
+                                         dsir_stream_t stream) {
+    if (!ws || !host_out || B <= 0 || J <= 0 || K <= 0) return DSIR_ERR_BAD_ARG;
+    if (!match_tc_topk_supported(B, C, J, K, topk)) return DSIR_ERR_UNSUPPORTED;
+    if (ws_bytes < dsir_match_soft_topk_workspace_bytes(B, C, J, K, topk)) return DSIR_ERR_WORKSPACE;
+    const size_t used = dsir_match_soft_workspace_bytes(B, C, J, K) + ws_block((size_t)B * J * 4);
+    return match_tc_topk_exhaustive_rows((const char *)ws + used, B, C, J, K, topk, host_out, (cudaStream_t)stream);
 }
 
 int dsir_match_soft_sweep(dsir_feat fs, dsir_feat fr, int B, int C, int J, int K, const float *beta, const float *alpha,

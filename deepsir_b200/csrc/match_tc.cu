@@ -35,6 +35,7 @@
 #include <cstdlib>
 
 #include "match_tc.cuh"
+#include <vector>
 #include "tc_common.cuh"
 
 namespace dsir {
@@ -149,10 +150,17 @@ __device__ __forceinline__ void release_acc(uint64_t *empty_bar, int lane) {
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar);
 }
-template <bool LAST>
+// MODE (template of the kernel): 0 = row argmin (candidate lists), 1 = value only (minima per column granule, top-k
+// sweep 1), 2 = collect (top-k sweep 2: every column at or below the row's FIXED threshold is appended to the row's list)
+struct TopkRow {
+    int n;        // columns seen at or below the threshold (the row has ONE owner thread: top-k plans never split K)
+    int *list;    // the row's column list, `cap` entries
+    int cap;
+};
+template <bool LAST, int MODE = 0>
 __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint32_t taddr, float margin, float &thr,
                                          float (&cv)[TC_T], int (&ci)[TC_T], bool sample, float &best,
-                                         uint64_t *empty_bar = nullptr, int lane = 0) {
+                                         uint64_t *empty_bar = nullptr, int lane = 0, TopkRow *tk = nullptr) {
 #define F(i) __uint_as_float(v[i])
     const float a0 = fmin3(F(0), F(1), F(2)), a1 = fmin3(F(3), F(4), F(5)), a2 = fmin3(F(6), F(7), F(8));
     const float a3 = fmin3(F(9), F(10), F(11)), a4 = fmin3(F(12), F(13), F(14)), a5 = fmin3(F(15), F(16), F(17));
@@ -167,6 +175,20 @@ __device__ __forceinline__ void filter32(const uint32_t (&v)[32], int col0, uint
     }
     const bool slow = __any_sync(0xffffffffu, mm <= thr);   // inclusive, like the refine step's `v <= gmin + margin`
     if (LAST && !slow) release_acc(empty_bar, lane);
+    if constexpr (MODE == 2) {
+        // collect: tens of hits per row and sweep - no TMEM re-read, the 32 values are tested where they are (static indices)
+        if (slow) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+                if (F(e) <= thr) {
+                    if (tk->n < tk->cap) tk->list[tk->n] = col0 + e;
+                    ++tk->n;
+                }
+            if (tk->n > tk->cap) thr = -INFINITY;   // the list is full: the row goes to the exhaustive pass, stop looking
+            if (LAST) release_acc(empty_bar, lane);
+        }
+        return;
+    }
     if (slow) {
         unsigned qm = 0;       // which aligned column quads hold a value below the threshold
 #pragma unroll
@@ -222,12 +244,20 @@ struct TcParams {
     const int64_t *prior;
     const __half *a16, *b16;  // tensor-core copies [B][J][64], [B][K][64]
     const float *nr;          // [B,K] exact squared norms
+    // top-k sweeps (MODE 1 / 2 of the kernel, see launch_match_tc_topk)
+    float *umin;              // MODE 1 out: [B][G][Jpad] minima of x per column granule (G granules of `gran` columns)
+    int gran32;               // MODE 1: granule = 32 columns (one epilogue step) instead of the 128-column unit
+    int G;                    // granules per row
+    const float *thr_in;      // MODE 2 in: [B][Jpad] fixed threshold per row
+    int *tk_cnt;              // MODE 2: [B][Jpad] entries appended
+    int *tk_list;             // MODE 2: [B][Jpad][tk_cap] column indices
+    int tk_cap;
     int dbg_flags;            // experiments only (DSIR_TC_DEBUG): bit 0 = never take the slow path (wrong results)
     unsigned int *trace;      // DSIR_TC_DEBUG bit 1: block 0 logs clock stamps of its first 256 units (see match_tc_filter_trace)
     unsigned long long *dbg;  // [grid][4]: start ns, end ns, cycles, units (diagnostic, always written)
 };
 
-template <int NKS>  // 16-channel k-steps of the feature part (NKS = ceil(C / 16), C <= 64)
+template <int NKS, int MODE = 0>  // 16-channel k-steps of the feature part (NKS = ceil(C / 16), C <= 64)
 __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                         const __grid_constant__ CUtensorMap mapB,
                                                                         const __grid_constant__ CUtensorMap mapAaug,
@@ -361,11 +391,19 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
             // through the slow path at every step; their lists are never read, so they never look at anything.
             const bool dead = j >= P.J || (TC_TRACE && (P.dbg_flags & 1));
             float thr = dead ? -INFINITY : INFINITY;
+            TopkRow tk{0, nullptr, 0};
+            if constexpr (MODE == 2) {
+                const size_t row = (size_t)b * P.Jpad + j;
+                if (!dead) thr = P.thr_in[row];
+                tk.list = P.tk_list + row * P.tk_cap; tk.cap = P.tk_cap;
+            }
+            float *umin_row = nullptr;
+            if constexpr (MODE == 1) umin_row = P.umin + (size_t)b * P.G * P.Jpad + j;
             const float nsj = j < P.J ? P.ns[(size_t)b * P.J + j] : 0.f;
             const float xmb = P.xm[b];
             const bool aug = xmb < 0.f;
             const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C) + fmaxf(xmb, 0.f);
-            if (P.prior != nullptr && !dead) {
+            if (MODE == 0 && P.prior != nullptr && !dead) {
                 // x of the prior match from the same fp16 operands the tensor core sees.  The two fp32 accumulations (80
                 // products each, different order) differ by less than the accumulation term of eps plus a quarter of it,
                 // i.e. by less than margin = 2.04 eps: x' + margin bounds the accumulator value of that column, hence the
@@ -392,7 +430,8 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
             }
             for (int t = 0; t < us.total(); ++t) {
                 const int u = us.unit(t);
-                const bool sample = t < us.ns;
+                const bool sample = MODE == 1 || t < us.ns;
+                if constexpr (MODE == 1) best = INFINITY;
                 const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) +
                                        (uint32_t)((pa.stage * TC_RBS + r) * 128 + h * (TC_BN / TC_HALVES));
                 mbar_wait(&tmem_full[pa.stage * TC_RBS + r], pa.phase);
@@ -406,26 +445,36 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
                     tmem_wait32(va);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 1] = (unsigned int)clock64();
                     tmem_ld32(tbase + (g + 1) * 32, vb);
-                    filter32<false>(va, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci, sample, best);
+                    filter32<false, MODE>(va, col0 + g * 32, tbase + g * 32, margin, thr, cv, ci, sample, best, nullptr, 0, &tk);
+                    if constexpr (MODE == 1)
+                        if (P.gran32) { if (!dead) umin_row[(size_t)(u * TC_STEPS + g) * P.Jpad] = best; best = INFINITY; }
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 2] = (unsigned int)clock64();
                     tmem_wait32(vb);
                     if (g + 2 < TC_STEPS) tmem_ld32(tbase + (g + 2) * 32, va);
                     if (tracing && useq < 256 && g == 0) P.trace[1024 + useq * 8 + 3] = (unsigned int)clock64();
                     if (g + 2 < TC_STEPS)
-                        filter32<false>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best);
+                        filter32<false, MODE>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best, nullptr,
+                                              0, &tk);
                     else   // last step: the accumulator is handed back from inside (right after the vote)
-                        filter32<true>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best,
-                                       &tmem_empty[pa.stage * TC_RBS + r], lane);
+                        filter32<true, MODE>(vb, col0 + (g + 1) * 32, tbase + (g + 1) * 32, margin, thr, cv, ci, sample, best,
+                                             &tmem_empty[pa.stage * TC_RBS + r], lane, &tk);
+                    if constexpr (MODE == 1)
+                        if (P.gran32) { if (!dead) umin_row[(size_t)(u * TC_STEPS + g + 1) * P.Jpad] = best; best = INFINITY; }
                 }
+                if constexpr (MODE == 1)
+                    if (!P.gran32 && !dead) umin_row[(size_t)u * P.Jpad] = best;
                 if (tracing && useq < 256) P.trace[1024 + useq * 8 + 4] = (unsigned int)clock64();
-                if (t == us.ns - 1 && !dead) thr = best + margin;   // primed: every row has seen a value <= best
+                if (MODE == 0 && t == us.ns - 1 && !dead) thr = best + margin;   // primed: every row has seen a value <= best
                 if (tracing && useq < 256) P.trace[1024 + useq * 8 + 5] = (unsigned int)clock64();
                 ++useq;
                 pa.advance(TC_ACC_STAGES);
             }
-            const size_t slot = ((((size_t)b * P.Jpad + (size_t)j) * P.S + sp) * TC_LISTS + h) * TC_T;
-            *reinterpret_cast<float4 *>(P.cand_val + slot) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-            *reinterpret_cast<int4 *>(P.cand_idx + slot) = make_int4(ci[0], ci[1], ci[2], ci[3]);
+            if constexpr (MODE == 2) P.tk_cnt[(size_t)b * P.Jpad + j] = tk.n;
+            if constexpr (MODE == 0) {
+                const size_t slot = ((((size_t)b * P.Jpad + (size_t)j) * P.S + sp) * TC_LISTS + h) * TC_T;
+                *reinterpret_cast<float4 *>(P.cand_val + slot) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                *reinterpret_cast<int4 *>(P.cand_idx + slot) = make_int4(ci[0], ci[1], ci[2], ci[3]);
+            }
         }
     }
     tc_fence_before();
@@ -457,6 +506,12 @@ __global__ __launch_bounds__(TC_THREADS, 1) void match_tc_filter_kernel(const __
 // come out of the norm kernel (atomics); the first block of the reference-side prep kernel writes the decision.
 // ---------------------------------------------------------------------------------------------------------
 constexpr float TC_NOAUG_SPREAD = 6.1035e-5f;
+
+__global__ void tc_init_kernel(int *count, float *rmax, float *amax, float *rmin, int B) {
+    if (threadIdx.x < 2) count[threadIdx.x] = 0;
+    if (rmax != nullptr)
+        for (int b = threadIdx.x; b < B; b += blockDim.x) { rmax[b] = 0.f; amax[b] = 0.f; rmin[b] = __int_as_float(0x7f7f7f7f); }
+}
 
 // prep: [B,C,N] fp32 (any strides) -> fp16 tensor-core copy [B][N][64] = mul * sigma * f (point-major, channels C..63
 // zero), and for the reference side the folded-norm channels [B][Npad][16] = {hi, lo, lolo, 0..} of sigma^2 |r|^2
@@ -719,9 +774,22 @@ struct TcPlan {
     int NKS, RB, U, S, Jpad, Kpad;
     size_t off_a16, off_b16, off_baug, off_aaug, off_rmax, off_amax, off_scale, off_xm, off_rmin, off_cval, off_cidx, off_count,
         off_rows, off_erows, off_keys, off_dbg, off_trace, total;
+    int gran = 0, G = 0, cap = 0;                              // top-k sweeps (launch_match_tc_topk)
+    size_t off_umin = 0, off_thr = 0, off_tkcnt = 0, off_tklist = 0, off_frt = 0;
 };
 
-TcPlan make_plan(int B, int C, int J, int K) {
+// top-k sweeps: column granule of the sweep-1 minima.  The k-th smallest of G granule minima bounds the k-th smallest
+// element from above; with G >= 1.25 k the expected number of columns at or below it stays near 2 k (iid columns:
+// (1-p)^gran = 1 - k/G), within the 4 k list.  0 = the fused path does not apply (too few columns).
+int topk_granule(int K, int topk) {
+    if (topk <= 0) return 0;
+    if (4ll * ((K + 127) / 128) >= 5ll * topk) return 128;
+    if (4ll * ((K + 31) / 32) >= 5ll * topk) return 32;
+    return 0;
+}
+int topk_cap(int topk) { return topk * 4 < 32 ? 32 : topk * 4; }
+
+TcPlan make_plan(int B, int C, int J, int K, int topk = 0) {
     TcPlan p;
     p.NKS = (C + 15) / 16;
     p.RB = (J + TC_BM - 1) / TC_BM;
@@ -736,6 +804,7 @@ TcPlan make_plan(int B, int C, int J, int K) {
         if (S > p.U) S = p.U;
         if (S < 1) S = 1;
     }
+    if (topk > 0) S = 1;   // top-k sweeps: one owner thread per row (list position in a register, no atomics)
     p.S = S;   // (splitting further to fill the last wave was measured slower: every split re-primes and re-discovers its minima)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += ws_block(bytes); return o; };
@@ -756,6 +825,16 @@ TcPlan make_plan(int B, int C, int J, int K) {
     p.off_keys = take((size_t)B * J * 8);
     p.off_dbg = take((size_t)256 * 4 * 8);
     p.off_trace = take((size_t)4096 * 4);
+    p.gran = topk_granule(K, topk);
+    if (p.gran) {
+        p.G = p.Kpad / p.gran;
+        p.cap = topk_cap(topk);
+        p.off_umin = take((size_t)B * p.G * p.Jpad * 4);
+        p.off_thr = take((size_t)B * p.Jpad * 4);
+        p.off_tkcnt = take((size_t)B * p.Jpad * 4);
+        p.off_tklist = take((size_t)B * p.Jpad * p.cap * 4);
+        p.off_frt = take((size_t)B * K * ((C + 3) / 4 * 4) * 4);
+    }
     p.total = off + 1024;
     return p;
 }
@@ -783,24 +862,27 @@ size_t match_tc_workspace_bytes(int B, int C, int J, int K) {
     return make_plan(B, C, J, K).total;
 }
 
-int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_t st) {
-    const TcPlan pl = make_plan(P.B, P.C, P.J, P.K);
-    char *base = (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-    if (ws == nullptr || (size_t)(base - (char *)ws) + pl.total - 1024 > ws_bytes) return DSIR_ERR_WORKSPACE;
+namespace {
+
+// norms, maxima, fp16 operand copies and tensor maps of one (features, workspace) pair; fills the common part of TcParams
+struct TcReady {
+    CUtensorMap mapA, mapB, mapAaug, mapBaug;
+    TcParams T;
+    int grid, sms;
+};
+
+int tc_prepare(const MatchParams &P, const TcPlan &pl, char *base, TcReady &R, cudaStream_t st) {
     __half *a16 = (__half *)(base + pl.off_a16), *b16 = (__half *)(base + pl.off_b16);
     __half *baug = (__half *)(base + pl.off_baug), *aaug = (__half *)(base + pl.off_aaug);
     float *rmax = (float *)(base + pl.off_rmax), *amax = (float *)(base + pl.off_amax), *scale = (float *)(base + pl.off_scale);
     float *xm = (float *)(base + pl.off_xm), *rmin = (float *)(base + pl.off_rmin);
-    float *cval = (float *)(base + pl.off_cval);
-    int *cidx = (int *)(base + pl.off_cidx), *count = (int *)(base + pl.off_count), *rows = (int *)(base + pl.off_rows);
-
-    DSIR_CUDA_TRY(cudaMemsetAsync(count, 0, 8, st));
+    int *count = (int *)(base + pl.off_count);
+    // one tiny launch instead of three memsets: row counters, and (first call on these features) the per-batch extrema
+    tc_init_kernel<<<1, 256, 0, st>>>(count, P.reuse_prep ? nullptr : rmax, amax, rmin, P.B);
+    DSIR_LAUNCH_CHECK();
     int rc;
     if (!P.reuse_prep) {
-        // rmax and amax are adjacent 256-byte blocks: one memset clears both
-        DSIR_CUDA_TRY(cudaMemsetAsync(rmax, 0, pl.off_scale - pl.off_rmax, st));
         // exact squared norms (fma chains, shared with the fp32 kernel) + per-batch maxima for sigma and the margin
-        DSIR_CUDA_TRY(cudaMemsetAsync(rmin, 0x7f, (size_t)P.B * 4, st));
         if ((rc = launch_sqnorm(P.fr, P.B, P.C, P.K, const_cast<float *>(P.nr), (int *)rmax, (int *)amax, (int *)rmin, st))) return rc;
         if ((rc = launch_sqnorm(P.fs, P.B, P.C, P.J, const_cast<float *>(P.ns), (int *)amax, nullptr, st))) return rc;
         tc_prep_kernel<<<dim3(cdiv(P.J, 32), P.B), 256, 0, st>>>(P.fs, P.C, P.J, P.J, amax, nullptr, 1.0f, a16, nullptr, aaug, scale);
@@ -809,36 +891,35 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
                                                                 rmin, rmax, xm);
         DSIR_LAUNCH_CHECK();
     }
-    CUtensorMap mapA, mapB, mapAaug, mapBaug;
-    if (!make_f16_tmap(&mapA, a16, P.B, P.J, TC_CH, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_f16_tmap(&mapB, b16, P.B, P.K, TC_CH, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_f16_tmap(&mapAaug, aaug, 1, 128, TC_AUG, TC_AUG, CU_TENSOR_MAP_SWIZZLE_32B) ||
-        !make_f16_tmap(&mapBaug, baug, P.B, pl.Kpad, TC_AUG, TC_AUG, CU_TENSOR_MAP_SWIZZLE_32B))
+    if (!make_f16_tmap(&R.mapA, a16, P.B, P.J, TC_CH, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_f16_tmap(&R.mapB, b16, P.B, P.K, TC_CH, TC_CH, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_f16_tmap(&R.mapAaug, aaug, 1, 128, TC_AUG, TC_AUG, CU_TENSOR_MAP_SWIZZLE_32B) ||
+        !make_f16_tmap(&R.mapBaug, baug, P.B, pl.Kpad, TC_AUG, TC_AUG, CU_TENSOR_MAP_SWIZZLE_32B))
         return DSIR_ERR_UNSUPPORTED;
-
-    TcParams T{};
+    TcParams &T = R.T;
+    T = TcParams{};
     T.B = P.B; T.J = P.J; T.K = P.K; T.C = P.C; T.RB = pl.RB; T.U = pl.U; T.S = pl.S;
-    T.Jpad = pl.Jpad; T.Kpad = pl.Kpad; T.ns = P.ns; T.rmax = rmax; T.scale = scale; T.xm = xm; T.cand_val = cval; T.cand_idx = cidx;
+    T.Jpad = pl.Jpad; T.Kpad = pl.Kpad; T.ns = P.ns; T.rmax = rmax; T.scale = scale; T.xm = xm;
+    T.cand_val = (float *)(base + pl.off_cval); T.cand_idx = (int *)(base + pl.off_cidx);
     T.dbg = (unsigned long long *)(base + pl.off_dbg);
     T.trace = (unsigned int *)(base + pl.off_trace);
-    T.dbg_flags = 0;
-    T.prime_div = 8;
-#ifdef DSIR_TC_TRACE
-    { const char *e = getenv("DSIR_TC_DEBUG"); T.dbg_flags = e ? atoi(e) : 0; }
-    { const char *e = getenv("DSIR_TC_PRIME"); T.prime_div = e ? atoi(e) : 8; }
-#endif
-    T.prior = P.prior_idx; T.a16 = a16; T.b16 = b16; T.nr = P.nr;
-    if (T.prior) T.prime_div = 0;
+    T.a16 = a16; T.b16 = b16; T.nr = P.nr;
     const int items = P.B * pl.RB * pl.S;
-    int dev = 0, sms = 148;
+    int dev = 0;
+    R.sms = 148;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = items < sms ? items : (sms > 256 ? 256 : sms);
+    cudaDeviceGetAttribute(&R.sms, cudaDevAttrMultiProcessorCount, dev);
+    R.grid = items < R.sms ? items : (R.sms > 256 ? 256 : R.sms);
+    return DSIR_OK;
+}
+
+template <int MODE>
+int tc_launch_filter(const TcPlan &pl, const TcReady &R, cudaStream_t st) {
     const size_t smem = filter_smem_bytes();
 #define DSIR_TC_LAUNCH(NKS)                                                                                                   \
     do {                                                                                                                      \
-        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_filter_kernel<NKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        match_tc_filter_kernel<NKS><<<grid, TC_THREADS, smem, st>>>(mapA, mapB, mapAaug, mapBaug, T);                         \
+        DSIR_CUDA_TRY(cudaFuncSetAttribute(match_tc_filter_kernel<NKS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        match_tc_filter_kernel<NKS, MODE><<<R.grid, TC_THREADS, smem, st>>>(R.mapA, R.mapB, R.mapAaug, R.mapBaug, R.T);          \
     } while (0)
     switch (pl.NKS) {
         case 1: DSIR_TC_LAUNCH(1); break;
@@ -848,6 +929,32 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     }
 #undef DSIR_TC_LAUNCH
     DSIR_LAUNCH_CHECK();
+    return DSIR_OK;
+}
+
+}  // namespace
+
+int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const TcPlan pl = make_plan(P.B, P.C, P.J, P.K);
+    char *base = (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    if (ws == nullptr || (size_t)(base - (char *)ws) + pl.total - 1024 > ws_bytes) return DSIR_ERR_WORKSPACE;
+    TcReady Rdy;
+    int rc;
+    if ((rc = tc_prepare(P, pl, base, Rdy, st))) return rc;
+    TcParams &T = Rdy.T;
+    T.dbg_flags = 0;
+    T.prime_div = 8;
+#ifdef DSIR_TC_TRACE
+    { const char *e = getenv("DSIR_TC_DEBUG"); T.dbg_flags = e ? atoi(e) : 0; }
+    { const char *e = getenv("DSIR_TC_PRIME"); T.prime_div = e ? atoi(e) : 8; }
+#endif
+    T.prior = P.prior_idx;
+    if (T.prior) T.prime_div = 0;
+    if ((rc = tc_launch_filter<0>(pl, Rdy, st))) return rc;
+    const int sms = Rdy.sms;
+    float *rmax = (float *)(base + pl.off_rmax), *scale = (float *)(base + pl.off_scale), *xm = (float *)(base + pl.off_xm);
+    float *cval = T.cand_val;
+    int *cidx = T.cand_idx, *count = (int *)(base + pl.off_count), *rows = (int *)(base + pl.off_rows);
 
     RefineParams R{};
     R.B = P.B; R.J = P.J; R.K = P.K; R.C = P.C; R.S = pl.S; R.Jpad = pl.Jpad;
@@ -864,6 +971,311 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     DSIR_LAUNCH_CHECK();
     match_tc_rescue_finalize_kernel<<<sms, 256, 0, st>>>(R, R.rescue_keys);
     DSIR_LAUNCH_CHECK();
+    return DSIR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Top-k soft correspondences without a score matrix (north_star: "row-wise online softmax / top-k ... never materialised").
+// With a_jk = -beta (d_jk - alpha) and beta > 0 the k largest weights of a row are its k smallest distances:
+//   sweep 1 (MODE 1)  the tensor-core pass, value only: x-minima of every column granule (128 or 32 columns) of every row;
+//   threshold         tau_j = k-th smallest granule minimum of the row: k different columns have x_hat <= tau_j, so the exact
+//                     k-th smallest x is <= tau_j + eps and every column of the exact top-k set has x_hat <= tau_j + 2 eps;
+//   sweep 2 (MODE 2)  the same pass again, appending every column with x_hat <= tau_j + margin (+ a round-off allowance for
+//                     the map d -> a) to the row's list (4 k entries);
+//   exact             one warp per row re-scores the listed columns with the fp32 op order of match_fp32.cu and takes the k
+//                     largest a (ties to the lower index), w = exp(a - lse).  Rows whose list overflowed or holds fewer than
+//                     k columns (ties en masse, beta <= 0, NaN rows) are scanned exhaustively by the same warp.
+// Outputs are those of the materialising path (DENSE chunk + row_topk_kernel), bit for bit.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ float warp_sort32(float v, int lane) {   // ascending over the lanes (bitonic network)
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, v, stride);
+            const bool up = (lane & size) == 0, lower = (lane & stride) == 0;
+            v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
+        }
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_merge32(float v, int lane) {  // bitonic sequence -> ascending
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) {
+        const float o = __shfl_xor_sync(0xffffffffu, v, stride);
+        v = (lane & stride) == 0 ? fminf(v, o) : fmaxf(v, o);
+    }
+    return v;
+}
+
+// one warp per row: the 32 smallest granule minima live one per lane (ascending); thr = k-th + margin + allowance
+__global__ __launch_bounds__(256) void topk_thr_kernel(TcParams P, int topk, const float *__restrict__ beta,
+                                                       const float *__restrict__ alpha, float *__restrict__ thr_out,
+                                                       int *__restrict__ cnt_out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= (long long)P.B * P.J) return;
+    const int b = (int)(row / P.J), j = (int)(row % P.J);
+    const float *u = P.umin + (size_t)b * P.G * P.Jpad + j;
+    float best = INFINITY;                                  // lane l: the (l+1)-th smallest so far
+    for (int g0 = 0; g0 < P.G; g0 += 32) {
+        float v = g0 + lane < P.G ? u[(size_t)(g0 + lane) * P.Jpad] : INFINITY;
+        v = v == v ? v : INFINITY;                          // NaN columns never count
+        v = warp_sort32(v, lane);
+        const float rev = __shfl_sync(0xffffffffu, v, 31 - lane);
+        best = warp_merge32(fminf(best, rev), lane);        // ascending vs descending: the element-wise minimum is the 32 smallest
+    }
+    const float tau = __shfl_sync(0xffffffffu, best, topk - 1);
+    if (lane == 0) {
+        const float nsj = P.ns[(size_t)b * P.J + j], sg = P.scale[b], rm = P.rmax[b];
+        const float margin = tc_margin(nsj, rm, sg, P.C) + fmaxf(P.xm[b], 0.f);
+        // columns whose distances differ by a few ulps of (|alpha| + d) can tie in a = -beta (d - alpha): keep them all
+        const float allow = sg * sg * 4.8e-7f * (fabsf(alpha[b]) + nsj + rm + 2.f * sqrtf(nsj * rm));
+        float t = tau + margin + allow;
+        if (!(beta[b] > 0.f)) t = INFINITY;                 // not a distance order: everything to the exhaustive pass
+        thr_out[(size_t)b * P.Jpad + j] = t;
+        cnt_out[(size_t)b * P.Jpad + j] = 0;
+    }
+}
+
+// [B,C,N] (any strides) -> point-major fp32 copy [B][N][C4] (C4 = C rounded up to 4, zero filled): a listed column's
+// channels become 16-byte loads of one or two lines instead of C scattered sectors
+__global__ __launch_bounds__(256) void feat_point_major_kernel(dsir_feat f, int C, int N, int C4, float *__restrict__ out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float *src = f.ptr + (size_t)b * f.batch_stride;
+    for (int c = ty; c < 32; c += 8) {
+        const int n = n0 + tx;
+        tile[c][tx] = (c0 + c < C && n < N) ? src[(size_t)(c0 + c) * f.chan_stride + (size_t)n * f.point_stride] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int n = n0 + i, c = c0 + tx;
+        if (n < N && c < C4) out[((size_t)b * N + n) * C4 + c] = tile[tx][i];
+    }
+}
+
+// <s_j, r_k> over the point-major copy: the fma chain over ascending channels of match_fp32.cu (the zero-filled tail
+// channels add exact zeros)
+__device__ __forceinline__ float dot_point_major(const float *srow, const float4 *__restrict__ rp, int C4) {
+    float dot = 0.f;
+    for (int c4 = 0; c4 < C4 / 4; ++c4) {
+        const float4 r = rp[c4];
+        const float4 sv = *reinterpret_cast<const float4 *>(srow + 4 * c4);
+        dot = __fmaf_rn(sv.x, r.x, dot); dot = __fmaf_rn(sv.y, r.y, dot);
+        dot = __fmaf_rn(sv.z, r.z, dot); dot = __fmaf_rn(sv.w, r.w, dot);
+    }
+    return dot;
+}
+
+// rows whose list holds between k and cap columns (nearly all): every lane re-scores at most LPL listed columns (fp32 op
+// order of match_fp32.cu: fma chain over the channels, ((-2 dot) + |s|^2) + |r|^2), keeps them sorted, and k rounds of a
+// warp arg-max over the lane heads emit the row's top-k (a descending, ties to the lower index).
+template <int LPL>
+__global__ __launch_bounds__(256) void topk_listed_kernel(RefineParams P, const int *__restrict__ cnt, const int *__restrict__ list,
+                                                          int cap, int topk, const float *__restrict__ frt, int C4,
+                                                          const float *__restrict__ beta, const float *__restrict__ alpha,
+                                                          const float *__restrict__ lse, int64_t *__restrict__ out_idx,
+                                                          float *__restrict__ out_w) {
+    __shared__ __align__(16) float srow[8][TC_CH];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= (long long)P.B * P.J) return;
+    const int b = (int)(row / P.J), j = (int)(row % P.J);
+    const size_t prow = (size_t)b * P.Jpad + j;
+    const int n = cnt[prow];
+    if (n > cap || n < topk) return;                       // topk_exact_kernel scans these exhaustively
+    const float *sp = P.fs.ptr + (size_t)b * P.fs.batch_stride + (size_t)j * P.fs.point_stride;
+    for (int c = lane; c < C4; c += 32) srow[w][c] = c < P.C ? sp[(size_t)c * P.fs.chan_stride] : 0.f;
+    __syncwarp();
+    const int *lst = list + prow * cap;
+    const float nb = -beta[b], al = alpha[b];
+    const float nsj = P.ns[(size_t)b * P.J + j];
+    float av[LPL];
+    int ai[LPL];
+#pragma unroll
+    for (int q = 0; q < LPL; ++q) {
+        const int p = lane + 32 * q;
+        av[q] = -INFINITY; ai[q] = 0x7fffffff;
+        if (p < n) {
+            const int k = lst[p];
+            const float4 *rp = reinterpret_cast<const float4 *>(frt + ((size_t)b * P.K + k) * C4);
+            const float dot = dot_point_major(srow[w], rp, C4);
+            const float a = nb * (l2_from_dot(dot, nsj, P.nr[(size_t)b * P.K + k]) - al);
+            if (a == a) { av[q] = a + 0.f; ai[q] = k; }    // NaN scores are never selected (like the materialising route); -0 -> +0: one bit pattern per value
+        }
+    }
+    // order-preserving bits: the arg-max over the lane heads is one REDUX for the value and one for the (lower) index
+    unsigned int hv[LPL];
+#pragma unroll
+    for (int q = 0; q < LPL; ++q) hv[q] = float_order_bits(av[q]);
+    // sort the lane's LPL entries, descending (a, -index)
+#pragma unroll
+    for (int x = 0; x < LPL; ++x)
+#pragma unroll
+        for (int y = 0; y + 1 < LPL - x; ++y) {
+            const bool sw = hv[y + 1] > hv[y] || (hv[y + 1] == hv[y] && ai[y + 1] < ai[y]);
+            const unsigned int tv = sw ? hv[y] : hv[y + 1]; const int ti = sw ? ai[y] : ai[y + 1];
+            hv[y] = sw ? hv[y + 1] : hv[y]; ai[y] = sw ? ai[y + 1] : ai[y];
+            hv[y + 1] = tv; ai[y + 1] = ti;
+        }
+    const float l = lse[(size_t)b * P.J + j];
+    int64_t *oi = out_idx + ((size_t)b * P.J + j) * topk;
+    float *ow = out_w + ((size_t)b * P.J + j) * topk;
+    unsigned int myv = 0;
+    int myi = 0x7fffffff;
+    constexpr unsigned int PAD = 0x007fffffu;              // float_order_bits(-inf)
+    for (int t = 0; t < topk; ++t) {
+        const unsigned int m = __reduce_max_sync(0xffffffffu, hv[0]);
+        const int i = __reduce_min_sync(0xffffffffu, hv[0] == m ? ai[0] : 0x7fffffff);
+        if (hv[0] == m && ai[0] == i) {                    // the winner pops its head (padding entries may pop together: harmless)
+#pragma unroll
+            for (int q = 0; q < LPL - 1; ++q) { hv[q] = hv[q + 1]; ai[q] = ai[q + 1]; }
+            hv[LPL - 1] = PAD; ai[LPL - 1] = 0x7fffffff;
+        }
+        if (lane == t) { myv = m; myi = i; }               // lane t keeps result t: one coalesced store per row
+    }
+    if (lane < topk) {
+        oi[lane] = myi == 0x7fffffff ? (int64_t)-1 : (int64_t)myi;
+        ow[lane] = myi == 0x7fffffff ? 0.f : expf(float_from_order_bits(myv) - l);
+    }
+}
+
+template <int KMAX>
+__global__ __launch_bounds__(256) void topk_exact_kernel(RefineParams P, const int *__restrict__ cnt, const int *__restrict__ list,
+                                                         int cap, int topk, const float *__restrict__ frt, int C4,
+                                                         const float *__restrict__ beta, const float *__restrict__ alpha,
+                                                         const float *__restrict__ lse, int64_t *__restrict__ out_idx,
+                                                         float *__restrict__ out_w) {
+    __shared__ __align__(16) float srow[8][TC_CH];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= (long long)P.B * P.J) return;
+    const int b = (int)(row / P.J), j = (int)(row % P.J);
+    const size_t prow = (size_t)b * P.Jpad + j;
+    const int n = cnt[prow];
+    const bool exhaustive = n > cap || n < topk;
+    if (!exhaustive && cap <= 128) return;                 // topk_listed_kernel has done this row
+    const int count = exhaustive ? P.K : n;
+    const int *lst = list + prow * cap;
+    const float nb = -beta[b], al = alpha[b];
+    const float nsj = P.ns[(size_t)b * P.J + j];
+    const float *sp = P.fs.ptr + (size_t)b * P.fs.batch_stride + (size_t)j * P.fs.point_stride;
+    for (int c = lane; c < C4; c += 32) srow[w][c] = c < P.C ? sp[(size_t)c * P.fs.chan_stride] : 0.f;
+    __syncwarp();
+    float bv[KMAX];
+    int bi[KMAX];
+#pragma unroll
+    for (int p = 0; p < KMAX; ++p) { bv[p] = -INFINITY; bi[p] = 0x7fffffff; }
+    for (int p = lane; p < count; p += 32) {
+        const int k = exhaustive ? p : lst[p];
+        const float dot = dot_point_major(srow[w], reinterpret_cast<const float4 *>(frt + ((size_t)b * P.K + k) * C4), C4);
+        const float a = nb * (l2_from_dot(dot, nsj, P.nr[(size_t)b * P.K + k]) - al);
+        if (a > bv[KMAX - 1] || (a == bv[KMAX - 1] && k < bi[KMAX - 1])) {   // sorted insertion, descending (value, -index)
+#pragma unroll
+            for (int q = KMAX - 1; q >= 0; --q) {
+                const int qm = q > 0 ? q - 1 : 0;
+                const bool shift = (q > 0) && (a > bv[qm] || (a == bv[qm] && k < bi[qm]));
+                const bool here = !shift && (a > bv[q] || (a == bv[q] && k < bi[q]));
+                bv[q] = shift ? bv[qm] : (here ? a : bv[q]);
+                bi[q] = shift ? bi[qm] : (here ? k : bi[q]);
+            }
+        }
+    }
+    const float l = lse[(size_t)b * P.J + j];
+    int64_t *oi = out_idx + ((size_t)b * P.J + j) * topk;
+    float *ow = out_w + ((size_t)b * P.J + j) * topk;
+    for (int t = 0; t < topk; ++t) {      // warp arg-max over the lane heads
+        float v = bv[0];
+        int i = bi[0], src = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, i, o), s2 = __shfl_xor_sync(0xffffffffu, src, o);
+            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; src = s2; }
+        }
+        if (lane == src) {
+#pragma unroll
+            for (int q = 0; q < KMAX - 1; ++q) { bv[q] = bv[q + 1]; bi[q] = bi[q + 1]; }
+            bv[KMAX - 1] = -INFINITY; bi[KMAX - 1] = 0x7fffffff;
+        }
+        if (lane == 0) {
+            oi[t] = i == 0x7fffffff ? (int64_t)-1 : (int64_t)i;
+            ow[t] = i == 0x7fffffff ? 0.f : expf(v - l);
+        }
+    }
+}
+
+}  // namespace
+
+bool match_tc_topk_supported(int B, int C, int J, int K, int topk) {
+    if (topk < 1 || topk > 32 || C < 1 || C > TC_CH) return false;
+    if ((long long)B * J >= (1ll << 31) || (long long)B * K >= (1ll << 31)) return false;
+    if ((double)B * J * K < 4.0e6) return false;      // tiny problems: the materialising path is a handful of launches
+    return topk_granule(K, topk) != 0 && tc_encode_fn() != nullptr;
+}
+
+size_t match_tc_topk_workspace_bytes(int B, int C, int J, int K, int topk) {
+    return make_plan(B, C, J, K, topk).total + ws_block((size_t)B * J * 4) + ws_block((size_t)B * K * 4);
+}
+
+// P: fs, fr, B, C, J, K, beta, alpha, lse (given, [B,J]); out_idx / out_w [B,J,topk]
+int launch_match_tc_topk(const MatchParams &P0, int topk, int64_t *out_idx, float *out_w, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!match_tc_topk_supported(P0.B, P0.C, P0.J, P0.K, topk)) return DSIR_ERR_UNSUPPORTED;
+    const TcPlan pl = make_plan(P0.B, P0.C, P0.J, P0.K, topk);
+    char *base = (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    const size_t need = pl.total - 1024 + ws_block((size_t)P0.B * P0.J * 4) + ws_block((size_t)P0.B * P0.K * 4);
+    if (ws == nullptr || (size_t)(base - (char *)ws) + need > ws_bytes) return DSIR_ERR_WORKSPACE;
+    MatchParams P = P0;
+    float *ns = (float *)(base + pl.total - 1024);
+    float *nr = (float *)((char *)ns + ws_block((size_t)P.B * P.J * 4));
+    P.ns = ns; P.nr = nr; P.reuse_prep = 0; P.prior_idx = nullptr;
+    TcReady Rdy;
+    int rc;
+    if ((rc = tc_prepare(P, pl, base, Rdy, st))) return rc;
+    TcParams &T = Rdy.T;
+    T.prime_div = 0;
+    T.umin = (float *)(base + pl.off_umin); T.gran32 = pl.gran == 32 ? 1 : 0; T.G = pl.G;
+    float *thr = (float *)(base + pl.off_thr);
+    T.thr_in = thr; T.tk_cnt = (int *)(base + pl.off_tkcnt); T.tk_list = (int *)(base + pl.off_tklist); T.tk_cap = pl.cap;
+    if ((rc = tc_launch_filter<1>(pl, Rdy, st))) return rc;
+    const long long nrows = (long long)P.B * P.J;
+    const unsigned wgrid = (unsigned)((nrows + 7) / 8);
+    topk_thr_kernel<<<wgrid, 256, 0, st>>>(T, topk, P.beta, P.alpha, thr, T.tk_cnt);
+    DSIR_LAUNCH_CHECK();
+    if ((rc = tc_launch_filter<2>(pl, Rdy, st))) return rc;
+    RefineParams R{};
+    R.B = P.B; R.J = P.J; R.K = P.K; R.C = P.C; R.S = pl.S; R.Jpad = pl.Jpad;
+    R.fs = P.fs; R.fr = P.fr; R.ns = P.ns; R.nr = P.nr;
+    const int C4 = (P.C + 3) / 4 * 4;
+    float *frt = (float *)(base + pl.off_frt);
+    feat_point_major_kernel<<<dim3(cdiv(P.K, 32), cdiv(C4, 32), P.B), 256, 0, st>>>(P.fr, P.C, P.K, C4, frt);
+    DSIR_LAUNCH_CHECK();
+    if (pl.cap <= 32) topk_listed_kernel<1><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w);
+    else if (pl.cap <= 64) topk_listed_kernel<2><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w);
+    else topk_listed_kernel<4><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w);
+    DSIR_LAUNCH_CHECK();
+    if (topk <= 8) topk_exact_kernel<8><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w);
+    else topk_exact_kernel<32><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w);
+    DSIR_LAUNCH_CHECK();
+    return DSIR_OK;
+}
+
+// diagnostic: rows of the last top-k launch on this workspace that took the exhaustive pass (synchronises the stream)
+int match_tc_topk_exhaustive_rows(const void *ws, int B, int C, int J, int K, int topk, int *out, cudaStream_t st) {
+    const TcPlan pl = make_plan(B, C, J, K, topk);
+    if (!pl.gran) return DSIR_ERR_UNSUPPORTED;
+    const char *base = (const char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    std::vector<int> h((size_t)B * pl.Jpad);
+    DSIR_CUDA_TRY(cudaMemcpyAsync(h.data(), base + pl.off_tkcnt, h.size() * 4, cudaMemcpyDeviceToHost, st));
+    DSIR_CUDA_TRY(cudaStreamSynchronize(st));
+    int n = 0;
+    for (int b = 0; b < B; ++b)
+        for (int j = 0; j < J; ++j) { const int c = h[(size_t)b * pl.Jpad + j]; n += (c > pl.cap || c < topk) ? 1 : 0; }
+    *out = n;
     return DSIR_OK;
 }
 

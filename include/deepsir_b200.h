@@ -126,9 +126,18 @@ int dsir_match_argmin_filter_trace(const void *ws, size_t ws_bytes, int B, int C
  *   y_j = sum_k w_jk xyz_ref[b,k,:] / (sum_k w_jk + 1e-16)      soft target, network/model.py:81-84
  * outputs: y_soft [B,J,3] (or NULL), lse [B,J] (or NULL); topk > 0 additionally returns the topk largest
  * weights per row, descending, ties to the lower index: topk_idx [B,J,topk] int64, topk_w [B,J,topk] (topk <= 32;
- * workspace from dsir_match_soft_topk_workspace_bytes). */
+ * workspace from dsir_match_soft_topk_workspace_bytes).  Without a column bias, C <= 64 and K >= 40 topk (roughly) the
+ * top-k comes from two more tensor-core sweeps (granule minima -> per-row threshold -> <= 4 topk listed columns, re-scored
+ * exactly): nothing of size J x K exists.  Otherwise row chunks of the exact fp32 distance matrix are materialised inside
+ * the workspace (<= 256 MB).  Same bits either way. */
 size_t dsir_match_soft_workspace_bytes(int B, int C, int J, int K);
 size_t dsir_match_soft_topk_workspace_bytes(int B, int C, int J, int K, int topk);
+/* 1 when dsir_match_soft(topk) with col_bias == NULL takes the fused tensor-core route for this shape, else 0 */
+int dsir_match_soft_topk_fused(int B, int C, int J, int K, int topk);
+/* diagnostic (synchronises `stream`): rows of the LAST fused top-k call on this workspace whose column list overflowed or
+ * came up short and were therefore scanned exhaustively (mass ties, beta <= 0, NaN rows).  host_out is HOST memory. */
+int dsir_match_soft_topk_exhaustive_rows(const void *ws, size_t ws_bytes, int B, int C, int J, int K, int topk,
+                                         int32_t *host_out, dsir_stream_t stream);
 /* one sweep of an iteration that calls the fused soft match repeatedly with the SAME features and workspace and only the
  * column bias changing (the Sinkhorn half-steps of matchnet.py:211-271 in dual form): with reuse_prep != 0 the norms and
  * the tensor-core operand copies left in `ws` by the previous sweep are used as they are. */

@@ -730,7 +730,8 @@ def test_match_soft_tensor_core_path(shape):
     assert torch.allclose(lse_b.cpu(), ref, rtol=SOFT_RTOL, atol=1e-5)
 
 
-@pytest.mark.parametrize("shape,topk", [((2, 32, 700, 900), 4), ((1, 64, 300, 2500), 16), ((2, 32, 2100, 1000), 8)])
+@pytest.mark.parametrize("shape,topk", [((2, 32, 700, 900), 4), ((1, 64, 300, 2500), 16), ((2, 32, 2100, 1000), 8),
+                                        ((2, 32, 900, 5000), 32), ((1, 48, 1500, 2777), 20)])
 def test_match_soft_topk(shape, topk):
     """Top-k soft correspondences: the k largest weights of every row, descending, ties to the lower index; equal to the
     top-k of the reference's materialised softmax (matchnet.py:195-208,259)."""
@@ -758,6 +759,78 @@ def test_match_soft_topk(shape, topk):
     pos3 = (ti == 3).float().argmax(dim=2)
     pos5 = (ti == 5).float().argmax(dim=2)
     assert (pos3[has3] < pos5[has3]).all()
+
+
+def _soft_topk_raw(fs, fr, beta, alpha, topk, bias=None):
+    """dsir_match_soft(topk) through ctypes with a workspace the test keeps: (idx, w, lse, exhaustive rows or None)."""
+    from deepsir_b200 import _lib as L
+    lib = L.lib()
+    B, C, J = fs.shape
+    K = fr.shape[2]
+    (f1, _a), (f2, _b) = L.feat_cn(fs), L.feat_cn(fr)
+    lse = torch.empty(B, J, device=DEV)
+    ti = torch.empty(B, J, topk, dtype=torch.int64, device=DEV)
+    tw = torch.empty(B, J, topk, device=DEV)
+    ws = L.workspace(lib.dsir_match_soft_topk_workspace_bytes(B, C, J, K, topk), fs.device)
+    L.check(lib.dsir_match_soft(f1, f2, B, C, J, K, beta.data_ptr(), alpha.data_ptr(), L.ptr(bias), None, None, lse.data_ptr(),
+                                topk, ti.data_ptr(), tw.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(fs.device)), "soft")
+    ex = None
+    if bias is None and lib.dsir_match_soft_topk_fused(B, C, J, K, topk):
+        import ctypes
+        out = ctypes.c_int32(-1)
+        L.check(lib.dsir_match_soft_topk_exhaustive_rows(ws.data_ptr(), ws.numel(), B, C, J, K, topk, ctypes.byref(out),
+                                                         L.stream_ptr(fs.device)), "exhaustive_rows")
+        ex = out.value
+    return ti.cpu(), tw.cpu(), lse.cpu(), ex
+
+
+@pytest.mark.parametrize("shape,topk,fused", [
+    ((2, 32, 900, 5000), 32, True),      # C3 width: 40 units >= 1.25 * 32 -> 128-column granules
+    ((1, 64, 300, 16384), 5, True),      # C2 width, norm K-step skipped (unit features, K % 128 == 0)
+    ((2, 32, 2100, 1000), 8, True),      # 8 units < 10 -> 32-column granules
+    ((1, 16, 3000, 2777), 32, True),     # ragged K (folded norm, zero-filled tail), 32-column granules
+    ((3, 20, 1300, 1153), 1, True),      # k = 1
+    ((2, 32, 4000, 600), 32, False),     # 19 granules of 32 < 40: materialising route
+])
+def test_match_soft_topk_fused_equals_materialised(shape, topk, fused):
+    """The two-sweep tensor-core top-k (no J x K object) returns the bits of the materialising route (exact fp32 distance
+    chunks + one warp per row), which a zero column bias selects; few rows need the exhaustive pass."""
+    from deepsir_b200 import _lib as L
+    B, C, J, K = shape
+    assert bool(L.lib().dsir_match_soft_topk_fused(B, C, J, K, topk)) == fused
+    b = synth.make_batch(B, max(J, K), C, "3dmatch", config=3, first_pair=91)
+    fs, fr = cu(b["feat_src"][:, :, :J].contiguous()), cu(b["feat_ref"][:, :, :K].contiguous())
+    fr[:, :, 7] = fr[:, :, 2]                                    # exact duplicate: tie -> lower index first
+    fr[:, :, K - 1] = fr[:, :, 2]
+    beta, alpha = cu(torch.tensor([10.0, 6.0, 30.0][:B])), cu(torch.tensor([0.5, 0.3, 0.0][:B]))
+    ti, tw, lse, ex = _soft_topk_raw(fs, fr, beta, alpha, topk)
+    ti0, tw0, lse0, _ = _soft_topk_raw(fs, fr, beta, alpha, topk, bias=torch.zeros(B, K, device=DEV))
+    assert torch.equal(lse, lse0)
+    assert torch.equal(ti, ti0) and torch.equal(tw, tw0)
+    if fused:
+        assert ex is not None and ex <= 0.01 * B * J, ex
+
+
+def test_match_soft_topk_fused_degenerate_rows():
+    """Mass ties (every reference point equal), beta = 0 (no distance order), a NaN source row and a NaN reference column:
+    the fused route sends such rows through its exhaustive pass and still returns the materialising route's bits."""
+    B, C, J, K, topk = 3, 32, 600, 4096, 16
+    g = torch.Generator().manual_seed(5)
+    fs = torch.nn.functional.normalize(torch.randn(B, C, J, generator=g), dim=1)
+    fr = torch.nn.functional.normalize(torch.randn(B, C, K, generator=g), dim=1)
+    fr[0] = fr[0, :, :1]                                           # batch 0: all K reference points identical
+    fs[2, :, 11] = float("nan")
+    fr[2, :, 100] = float("nan")
+    beta, alpha = cu(torch.tensor([8.0, 0.0, 12.0])), cu(torch.tensor([0.2, 0.5, 0.4]))
+    fs, fr = cu(fs), cu(fr)
+    ti, tw, lse, ex = _soft_topk_raw(fs, fr, beta, alpha, topk)
+    ti0, tw0, lse0, _ = _soft_topk_raw(fs, fr, beta, alpha, topk, bias=torch.zeros(B, K, device=DEV))
+    assert torch.equal(ti, ti0)
+    assert torch.equal(torch.nan_to_num(tw, nan=-1.0), torch.nan_to_num(tw0, nan=-1.0))
+    assert torch.equal(ti[0], torch.arange(topk).expand(J, topk))          # all tied: the first k columns
+    assert torch.equal(ti[1], torch.arange(topk).expand(J, topk))          # beta = 0: every weight equal
+    assert not (ti[2] == 100).any()
+    assert ex >= 2 * J                                                       # batches 0 and 1 went through the exhaustive pass
 
 
 @pytest.mark.parametrize("shape,beta", [((64, 16, 200, 180), 10.0), ((1, 32, 130, 20001), 25.0), ((2, 64, 1111, 1000), 100.0),

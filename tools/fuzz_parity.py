@@ -248,6 +248,36 @@ def fuzz_topk(rng, seed):
     return f"topk n{n} k{k}", msg
 
 
+def fuzz_softtopk(rng, seed):
+    """Fused two-sweep top-k of the soft weights against the materialising route (selected by a zero column bias): same bits."""
+    g = torch.Generator().manual_seed(seed)
+    B, C = rng.randint(1, 3), rng.choice([3, 16, 32, 33, 64])
+    J, K = max(1, size(rng, 3000)), rng.choice([rng.randint(64, 900), rng.randint(900, 6000), 128 * rng.randint(8, 40)])
+    topk = rng.choice([1, 2, 5, 8, 9, 16, 31, 32])
+    topk = min(topk, K)
+    fs, fr = torch.randn(B, C, J, generator=g), torch.randn(B, C, K, generator=g)
+    style = rng.choice(["unit", "raw", "lattice", "dups", "scaled"])
+    if style in ("unit", "dups"):
+        fs, fr = torch.nn.functional.normalize(fs, dim=1), torch.nn.functional.normalize(fr, dim=1)
+    if style == "lattice":
+        fs, fr = torch.round(fs * 2) / 2, torch.round(fr * 2) / 2          # heavy exact ties
+    if style == "dups":
+        fr[:, :, torch.randint(0, K, (K // 2,), generator=g)] = fr[:, :, :1]
+    if style == "scaled":
+        fs, fr = fs * 10.0 ** rng.uniform(-3, 2), fr * 10.0 ** rng.uniform(-3, 2)
+    beta = torch.tensor([rng.choice([0.0, 0.5, 5.0, 50.0]) for _ in range(B)])
+    alpha = torch.tensor([rng.uniform(-1.0, 3.0) for _ in range(B)])
+    out = D.match_soft(cu(fs), cu(fr), None, cu(beta), cu(alpha), topk=topk)
+    ref = D.match_soft(cu(fs), cu(fr), None, cu(beta), cu(alpha), col_bias=cu(torch.zeros(B, K)), topk=topk)
+    msg = []
+    if not torch.equal(out[3], ref[3]):
+        msg.append(f"{(out[3] != ref[3]).sum().item()} top-k indices differ")
+    if not torch.equal(torch.nan_to_num(out[4], nan=-1.0), torch.nan_to_num(ref[4], nan=-1.0)):
+        msg.append("top-k weights differ")
+    fused = D.lib().dsir_match_soft_topk_fused(B, C, J, K, topk)
+    return f"softtopk B{B} C{C} J{J} K{K} k{topk} {style} fused{fused}", msg
+
+
 def fuzz_consumers(rng, seed):
     """KNN consumers of the RandLA encoder (gather_neighbour, relative_pos_encoding, random_sample, nearest_interpolation)."""
     g = torch.Generator().manual_seed(seed)
@@ -297,12 +327,12 @@ def main():
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--seed", type=int, default=0)
     assert D.lib().dsir_device_check() == 0
-    ap.add_argument("--only", default="", help="comma-separated fuzzer names (argmin,knn,soft,kabsch,pyramid,loop,sinkhorn,logot,topk,consumers,metrics)")
+    ap.add_argument("--only", default="", help="comma-separated fuzzer names (argmin,knn,soft,kabsch,pyramid,loop,sinkhorn,logot,topk,softtopk,consumers,metrics)")
     ap.add_argument("--scale", type=int, default=1, help="multiply the size range (fewer, larger trials)")
     args = ap.parse_args()
     global SCALE
     SCALE = args.scale
-    fuzzers = [fuzz_argmin, fuzz_knn, fuzz_soft, fuzz_kabsch, fuzz_pyramid, fuzz_loop, fuzz_sinkhorn, fuzz_logot, fuzz_topk, fuzz_consumers, fuzz_metrics]
+    fuzzers = [fuzz_argmin, fuzz_knn, fuzz_soft, fuzz_kabsch, fuzz_pyramid, fuzz_loop, fuzz_sinkhorn, fuzz_logot, fuzz_topk, fuzz_softtopk, fuzz_consumers, fuzz_metrics]
     if args.only:
         fuzzers = [f for f in fuzzers if f.__name__[5:] in args.only.split(",")]
     counts = {f.__name__: 0 for f in fuzzers}

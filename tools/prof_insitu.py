@@ -17,7 +17,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--n", type=int, default=16384)
 ap.add_argument("--iters", type=int, default=5)
-ap.add_argument("--what", default="all")
+ap.add_argument("--what", default="all", help="all | match | knn | topk (config-3-shaped soft match + top-k)")
+ap.add_argument("--topk", type=int, default=32)
 a = ap.parse_args()
 dev = "cuda:0"
 b = {k: v.to(dev) for k, v in synth.make_batch(a.batch, a.n, 64, "kitti", config=2).items()}
@@ -25,7 +26,16 @@ xs = b["points_src"][:, :, :3].permute(0, 2, 1).contiguous()
 xr = b["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
 
 
+if a.what == "topk":
+    g = torch.Generator().manual_seed(1)
+    tfs = torch.nn.functional.normalize(torch.randn(a.batch, 32, 5000, generator=g), dim=1).to(dev)
+    tfr = torch.nn.functional.normalize(torch.randn(a.batch, 32, 5000, generator=g), dim=1).to(dev)
+    tbeta, talpha = torch.full((a.batch,), 10.0, device=dev), torch.full((a.batch,), 0.5, device=dev)
+
+
 def step():
+    if a.what == "topk":
+        D.match_soft(tfs, tfr, None, tbeta, talpha, topk=a.topk)
     if a.what in ("all", "knn"):
         D.nn_search_cloud(b["points_src"], 16, (4, 4, 4, 4))
         D.nn_search_cloud(b["points_ref"], 16, (4, 4, 4, 4))
