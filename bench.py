@@ -338,6 +338,7 @@ def main():
     dev_index = local * (n_vis // world) if (world > 1 and n_vis >= 2 * world and local < world) else local
     torch.cuda.set_device(dev_index)
     dev = torch.device("cuda", dev_index)
+    torch.cuda.set_stream(torch.cuda.Stream(dev, priority=-1))     # the main stream of this process (see step_resident)
     local = dev_index
     if True:
         # one process per GPU: keep the rank (and the pinned host buffers it is about to allocate: first touch) on the CPUs /
@@ -369,6 +370,14 @@ def main():
     match_events, knn_events = [], []
 
     knn_stream = torch.cuda.Stream(dev)
+    knn_stream.wait_stream(torch.cuda.current_stream(dev))          # the inputs above were produced on the main stream
+    knn_pending = {"ev": None}
+
+    def join_knn():
+        """The main stream waits for the KNN pyramids still in flight on the forked stream."""
+        if knn_pending["ev"] is not None:
+            torch.cuda.current_stream(dev).wait_event(knn_pending["ev"])
+            knn_pending["ev"] = None
 
     def step_resident(record=False, d=None):
         d = d or devt
@@ -388,11 +397,17 @@ def main():
         # The KNN pyramids of a batch do not depend on its match / Kabsch (in the reference they run in the DataLoader
         # workers while the GPU is busy with the previous batch): they go to a forked stream and are joined at the end of
         # the step, so that their latency-bound kernels fill the gaps around the persistent match kernel.
-        knn_stream.wait_stream(cur)
+        # Nor do they depend on the PREVIOUS batch's match: the forked stream runs pyramid after pyramid in its own order and
+        # the main stream joins the pyramids of step i at the end of step i+1 (one step of lag; `join_knn` before every end
+        # event), so the pack / tree-build prologue of one step runs under the tail of the previous one.  The main stream
+        # has the higher priority: the persistent match kernel takes its SMs first, the KNN CTAs fill in around it.
         with torch.cuda.stream(knn_stream):
             g = D.nn_search_pair(d["points_src"], d["points_ref"], KNN_K, RATIOS)
+            e = torch.cuda.Event()
+            e.record(knn_stream)
         out = D.align_loop(d["feat_src"], d["feat_ref"], xs0, xr0, d["weights"], 1)
-        cur.wait_stream(knn_stream)
+        join_knn()
+        knn_pending["ev"] = e
         return out, g
 
     def barrier():
@@ -415,6 +430,7 @@ def main():
         a.record()
         for _ in range(args.steps):
             fn()
+        join_knn()               # every pyramid of the block has finished before the end event
         b_.record()
         barrier()
         return a.elapsed_time(b_)
@@ -442,8 +458,11 @@ def main():
                   feat_ref=synth.random_features(B, FEAT_D, N_PTS, 9001 + rank).to(dev))
     for _ in range(2):
         step_resident(d=d_rand)
+    join_knn()
     ms_rand = timed_block(lambda: step_resident(d=d_rand))
     _, n_rescued = D.match_argmin(d_rand["feat_src"], d_rand["feat_ref"], algo=D.MATCH_TC, return_rescued=True)
+    join_knn()
+    torch.cuda.synchronize()
     del d_rand
     # the same step with the reference's default of 5 registration iterations (arguments.py:69), reported beside the headline
     def step_r5():
@@ -561,7 +580,9 @@ def main():
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "registration_iters": 1,
                       "l2": "inputs larger than L2 (268 MB of features per step vs 126 MB L2), no explicit flush",
-                      "sharding": "by pair, no collective"},
+                      "sharding": "by pair, no collective",
+                      "streams": "match + Kabsch on a high-priority stream, the KNN pyramids of a step on a forked stream joined one "
+                                 "step later (every pyramid of a timed block finishes before its end event)"},
            "clocks": clocks,
            "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "h2d_gbs": h2d * args.steps / (ms_e2e / 1e3) / 1e9, "blocks": len(e2e_blocks),

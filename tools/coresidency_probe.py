@@ -42,6 +42,22 @@ def main():
         cur.wait_stream(knn_stream)
         return out, g
 
+    lag = {"ev": None}
+
+    def step_lag(knn_stream):
+        """KNN of step i runs on its own stream without waiting for the match of step i-1; the main stream joins the KNN of the
+        PREVIOUS step (one step of lag), so consecutive steps overlap: prologue of one under the tail of the other."""
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(knn_stream):
+            g = knn()
+            e = torch.cuda.Event()
+            e.record(knn_stream)
+        out = match()
+        if lag["ev"] is not None:
+            cur.wait_event(lag["ev"])
+        lag["ev"] = e
+        return out, g
+
     def timed(fn, steps=20, blocks=9):
         for _ in range(5):
             fn()
@@ -65,6 +81,7 @@ def main():
         with torch.cuda.stream(main_stream):
             for order in ("knn_first", "match_first"):
                 print("  main prio %2d  %-12s %.3f ms" % (main_prio, order, timed(lambda: step(order, side[0]))))
+            print("  main prio %2d  %-12s %.3f ms" % (main_prio, "lag1", timed(lambda: step_lag(side[0]))))
 
 
 if __name__ == "__main__":
