@@ -69,6 +69,7 @@ constexpr int TC_WARP_TMA = TC_EPI_WARPS, TC_WARP_MMA0 = TC_EPI_WARPS + 1;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_MMA_WARPS) * 32;
 constexpr int TC_LISTS = TC_HALVES;           // candidate lists per (row, split)
 constexpr int TC_MAX_SPLIT = 8 / TC_HALVES;
+constexpr double TC_ITEM_OVERHEAD = 24.0;     // fixed cost of a work item in units of one 512x128 unit (fitted: tools/sweep_split.py)
 constexpr int TC_CH = 64;                     // fp16 channels per point in the tensor-core copy (one 128-byte swizzle row)
 constexpr int TC_AUG = 16;                    // folded-norm channels (one K=16 MMA)
 constexpr float TC_PAD_NORM = 60000.0f;       // folded norm of padded reference rows: larger than any real x_jk (<= 3)
@@ -796,14 +797,25 @@ TcPlan make_plan(int B, int C, int J, int K, int topk = 0) {
     p.U = (K + TC_BN - 1) / TC_BN;
     p.Jpad = p.RB * TC_BM;
     p.Kpad = p.U * TC_BN;
+    // K-splits: S work items per (batch element, 512-row block).  The persistent grid runs the items in rounds of one per
+    // SM; a round costs what ONE item costs: its share of the units, the priming pass over an eighth of them, and a fixed
+    // part (A tiles, cold threshold, list write-back - TC_ITEM_OVERHEAD units, fitted to tools/sweep_split.py).  Take the S
+    // with the cheapest total; more splits only when they pay (every split re-primes and re-discovers its minima).
     long long items = (long long)B * p.RB;
     int S = 1;
-    if (items < 2 * 148) {
-        S = (int)((2 * 148 + items - 1) / items);
-        if (S > TC_MAX_SPLIT) S = TC_MAX_SPLIT;
-        if (S > p.U) S = p.U;
-        if (S < 1) S = 1;
+    {
+        const int sms = 148;
+        double best = 0.0;
+        for (int s = 1; s <= TC_MAX_SPLIT && s <= p.U; ++s) {
+            const long long rounds = (items * s + sms - 1) / sms;
+            const int nu = (p.U + s - 1) / s;
+            const double cost = (double)rounds * (nu + (nu >= 16 ? nu / 8 : 0) + TC_ITEM_OVERHEAD);
+            if (s == 1 || cost < best * 0.97) { best = cost; S = s; }   // a further split must win by 3 %
+        }
     }
+#ifdef DSIR_TC_TRACE
+    { const char *e = getenv("DSIR_TC_SPLIT"); if (e && atoi(e) > 0) S = atoi(e) < p.U ? atoi(e) : p.U; if (S > TC_MAX_SPLIT) S = TC_MAX_SPLIT; }
+#endif
     if (topk > 0) S = 1;   // top-k sweeps: one owner thread per row (list position in a register, no atomics)
     p.S = S;   // (splitting further to fill the last wave was measured slower: every split re-primes and re-discovers its minima)
     size_t off = 0;
