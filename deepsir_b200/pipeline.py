@@ -3,7 +3,9 @@
 The reference moves a collated batch to the device (`dict_all_to_device`, test.py:391), runs the forward pass and reads
 the pose back, strictly in sequence.  Here the upload of batch i+1 (copy stream) overlaps the kernels of batch i
 (compute stream) and the small result download, so a stream of batches runs at max(PCIe time, kernel time) per batch
-instead of their sum.  Everything on the device goes through libdeepsir_b200.so; torch only provides streams, events
+instead of their sum.  The KNN pyramids of a batch depend on nothing but its points (in the reference they are built in
+the DataLoader workers): they run on a third stream, next to the match / Kabsch loop of the same and of the previous
+batch, and are joined on the host when the batch is handed out.  Everything on the device goes through libdeepsir_b200.so; torch only provides streams, events
 and memory.
 """
 from __future__ import annotations
@@ -35,6 +37,7 @@ class RegistrationPipeline:
             raise L.DeepSIRError("RegistrationPipeline runs on a CUDA device only")
         self.k, self.ratios, self.iters, self.depth, self.keep_graph = num_knn, tuple(sub_sampling_ratio), iters, depth, keep_graph
         self.copy_stream = torch.cuda.Stream(self.dev)
+        self.knn_stream = torch.cuda.Stream(self.dev)
         # pinned result buffers: a ring of depth + 2 sets, allocated once per shape (cudaHostAlloc is far too slow for the
         # steady-state loop).  A yielded set is overwritten depth + 2 batches later: copy what must outlive that.
         self._ring, self._ring_shape, self._ring_pos = [], None, 0
@@ -58,11 +61,17 @@ class RegistrationPipeline:
         for k, v in d.items():
             if not host[k].is_cuda:
                 v.record_stream(compute)   # the compute stream reads them: keep the allocator from recycling early
+                if k.startswith("points"):
+                    v.record_stream(self.knn_stream)
         return d, up
 
     def _compute(self, d, up, compute):
         compute.wait_event(up)
-        g_src, g_ref = nn_search_pair(d["points_src"], d["points_ref"], self.k, self.ratios)
+        self.knn_stream.wait_event(up)
+        with torch.cuda.stream(self.knn_stream):
+            g_src, g_ref = nn_search_pair(d["points_src"], d["points_ref"], self.k, self.ratios)
+            knn_done = torch.cuda.Event()
+            knn_done.record(self.knn_stream)
         xs = d["points_src"][:, :, :3].permute(0, 2, 1).contiguous()   # the loop's [B,3,N] layout (model.py:541-549)
         xr = d["points_ref"][:, :, :3].permute(0, 2, 1).contiguous()
         tr, pred, _, status = align_loop(d["feat_src"], d["feat_ref"], xs, xr, d["weights"], self.iters)
@@ -75,11 +84,12 @@ class RegistrationPipeline:
             out["graph_src"], out["graph_ref"] = g_src, g_ref
         done = torch.cuda.Event()
         done.record(compute)
-        return out, done
+        return out, (done, knn_done)
 
     def run(self, batches):
         compute = torch.cuda.current_stream(self.dev)
         self.copy_stream.wait_stream(compute)        # uploads start after whatever the caller enqueued before
+        self.knn_stream.wait_stream(compute)         # (device-resident inputs were produced there)
         uploaded, inflight = deque(), deque()
         it = iter(batches)
 
@@ -99,10 +109,12 @@ class RegistrationPipeline:
             del d
             feed()                                   # the next upload is enqueued while this batch computes
             if len(inflight) >= self.depth:
-                out, done = inflight.popleft()
-                done.synchronize()
+                out, events = inflight.popleft()
+                for e in events:
+                    e.synchronize()
                 yield out
         while inflight:
-            out, done = inflight.popleft()
-            done.synchronize()
+            out, events = inflight.popleft()
+            for e in events:
+                e.synchronize()
             yield out
