@@ -44,6 +44,9 @@ e = d(epi[sl])
 names = ["full seen -> 32 cols in regs", "step 1 (tree, vote, slow path)", "wait second 32 cols", "step 2", "fence + arrive"]
 print(f"epilogue warp 0: issued -> full seen {np.mean(e[:, 0] - d(mma[sl, 0, 1])):6.0f}")
 for k, n in enumerate(names):
-    print(f"   {n:34s} {np.mean(e[:, k + 1] - e[:, k]):6.0f}")
+    dd = e[:, k + 1] - e[:, k]
+    print(f"   {n:34s} mean {np.mean(dd):6.0f}  median {np.median(dd):6.0f}  p10 {np.percentile(dd, 10):6.0f}  p90 {np.percentile(dd, 90):6.0f}")
+uu = np.diff(d(mma[sl, 0, 0]))
+print(f"   unit period: median {np.median(uu):.0f}  p10 {np.percentile(uu, 10):.0f}  p90 {np.percentile(uu, 90):.0f}")
 print(f"   drain total {np.mean(e[:, 5] - e[:, 0]):6.0f};  released -> issuer sees it free (2 units later) "
       f"{np.mean(d(mma[sl, 0, 0])[2:] - e[:-2, 5]):6.0f}")
