@@ -776,7 +776,7 @@ struct TcPlan {
     size_t off_a16, off_b16, off_baug, off_aaug, off_rmax, off_amax, off_scale, off_xm, off_rmin, off_cval, off_cidx, off_count,
         off_rows, off_erows, off_keys, off_dbg, off_trace, total;
     int gran = 0, G = 0, cap = 0;                              // top-k sweeps (launch_match_tc_topk)
-    size_t off_umin = 0, off_thr = 0, off_tkcnt = 0, off_tklist = 0, off_frt = 0;
+    size_t off_umin = 0, off_thr = 0, off_tkcnt = 0, off_tklist = 0, off_frt = 0, off_exrows = 0;
 };
 
 // top-k sweeps: column granule of the sweep-1 minima.  The k-th smallest of G granule minima bounds the k-th smallest
@@ -846,6 +846,7 @@ TcPlan make_plan(int B, int C, int J, int K, int topk = 0) {
         p.off_tkcnt = take((size_t)B * p.Jpad * 4);
         p.off_tklist = take((size_t)B * p.Jpad * p.cap * 4);
         p.off_frt = take((size_t)B * K * ((C + 3) / 4 * 4) * 4);
+        p.off_exrows = take((size_t)B * J * 4 + 256);     // [0] = count, rows from +64 ints on
     }
     p.total = off + 1024;
     return p;
@@ -1025,7 +1026,8 @@ __device__ __forceinline__ float warp_merge32(float v, int lane) {  // bitonic s
 // one warp per row: the 32 smallest granule minima live one per lane (ascending); thr = k-th + margin + allowance
 __global__ __launch_bounds__(256) void topk_thr_kernel(TcParams P, int topk, const float *__restrict__ beta,
                                                        const float *__restrict__ alpha, float *__restrict__ thr_out,
-                                                       int *__restrict__ cnt_out) {
+                                                       int *__restrict__ cnt_out, int *__restrict__ ex_count) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ex_count = 0;
     const int lane = threadIdx.x & 31;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= (long long)P.B * P.J) return;
@@ -1074,6 +1076,7 @@ __global__ __launch_bounds__(256) void feat_point_major_kernel(dsir_feat f, int 
 // channels add exact zeros)
 __device__ __forceinline__ float dot_point_major(const float *srow, const float4 *__restrict__ rp, int C4) {
     float dot = 0.f;
+#pragma unroll 8      // eight 16-byte loads in flight; the fma chain stays in channel order
     for (int c4 = 0; c4 < C4 / 4; ++c4) {
         const float4 r = rp[c4];
         const float4 sv = *reinterpret_cast<const float4 *>(srow + 4 * c4);
@@ -1091,7 +1094,7 @@ __global__ __launch_bounds__(256) void topk_listed_kernel(RefineParams P, const 
                                                           int cap, int topk, const float *__restrict__ frt, int C4,
                                                           const float *__restrict__ beta, const float *__restrict__ alpha,
                                                           const float *__restrict__ lse, int64_t *__restrict__ out_idx,
-                                                          float *__restrict__ out_w) {
+                                                          float *__restrict__ out_w, int *__restrict__ ex) {
     __shared__ __align__(16) float srow[8][TC_CH];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1099,7 +1102,10 @@ __global__ __launch_bounds__(256) void topk_listed_kernel(RefineParams P, const 
     const int b = (int)(row / P.J), j = (int)(row % P.J);
     const size_t prow = (size_t)b * P.Jpad + j;
     const int n = cnt[prow];
-    if (n > cap || n < topk) return;                       // topk_exact_kernel scans these exhaustively
+    if (n > cap || n < topk) {                             // topk_exact_kernel scans these exhaustively
+        if (lane == 0) ex[64 + atomicAdd(ex, 1)] = (int)row;
+        return;
+    }
     const float *sp = P.fs.ptr + (size_t)b * P.fs.batch_stride + (size_t)j * P.fs.point_stride;
     for (int c = lane; c < C4; c += 32) srow[w][c] = c < P.C ? sp[(size_t)c * P.fs.chan_stride] : 0.f;
     __syncwarp();
@@ -1156,67 +1162,85 @@ __global__ __launch_bounds__(256) void topk_listed_kernel(RefineParams P, const 
     }
 }
 
+// the rows topk_listed_kernel set aside (list overflowed or short: mass ties, beta <= 0, NaN rows): one CTA per row, the
+// grid strides over the list.  Every warp scans an eighth of the columns (per-lane sorted lists of KMAX, the only bound that
+// holds for any distribution of the winners over the lanes), emits its own top-k by warp arg-max rounds, warp 0 merges the
+// eight sorted lists.  Same order as everywhere: a descending, ties to the lower index; NaN scores never enter.
 template <int KMAX>
-__global__ __launch_bounds__(256) void topk_exact_kernel(RefineParams P, const int *__restrict__ cnt, const int *__restrict__ list,
-                                                         int cap, int topk, const float *__restrict__ frt, int C4,
+__global__ __launch_bounds__(256) void topk_exact_kernel(RefineParams P, int topk, const float *__restrict__ frt, int C4,
                                                          const float *__restrict__ beta, const float *__restrict__ alpha,
                                                          const float *__restrict__ lse, int64_t *__restrict__ out_idx,
-                                                         float *__restrict__ out_w) {
-    __shared__ __align__(16) float srow[8][TC_CH];
+                                                         float *__restrict__ out_w, const int *__restrict__ ex) {
+    __shared__ __align__(16) float srow[TC_CH];
+    __shared__ float sm_a[8][32];
+    __shared__ int sm_i[8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= (long long)P.B * P.J) return;
-    const int b = (int)(row / P.J), j = (int)(row % P.J);
-    const size_t prow = (size_t)b * P.Jpad + j;
-    const int n = cnt[prow];
-    const bool exhaustive = n > cap || n < topk;
-    if (!exhaustive && cap <= 128) return;                 // topk_listed_kernel has done this row
-    const int count = exhaustive ? P.K : n;
-    const int *lst = list + prow * cap;
-    const float nb = -beta[b], al = alpha[b];
-    const float nsj = P.ns[(size_t)b * P.J + j];
-    const float *sp = P.fs.ptr + (size_t)b * P.fs.batch_stride + (size_t)j * P.fs.point_stride;
-    for (int c = lane; c < C4; c += 32) srow[w][c] = c < P.C ? sp[(size_t)c * P.fs.chan_stride] : 0.f;
-    __syncwarp();
-    float bv[KMAX];
-    int bi[KMAX];
+    const int n_ex = ex[0];
+    for (int it = blockIdx.x; it < n_ex; it += gridDim.x) {
+        const int row = ex[64 + it];
+        const int b = row / P.J, j = row % P.J;
+        __syncthreads();                                   // the previous row is finished with the shared arrays
+        const float *sp = P.fs.ptr + (size_t)b * P.fs.batch_stride + (size_t)j * P.fs.point_stride;
+        for (int c = threadIdx.x; c < C4; c += blockDim.x) srow[c] = c < P.C ? sp[(size_t)c * P.fs.chan_stride] : 0.f;
+        __syncthreads();
+        const float nb = -beta[b], al = alpha[b];
+        const float nsj = P.ns[(size_t)b * P.J + j];
+        float bv[KMAX];
+        int bi[KMAX];
 #pragma unroll
-    for (int p = 0; p < KMAX; ++p) { bv[p] = -INFINITY; bi[p] = 0x7fffffff; }
-    for (int p = lane; p < count; p += 32) {
-        const int k = exhaustive ? p : lst[p];
-        const float dot = dot_point_major(srow[w], reinterpret_cast<const float4 *>(frt + ((size_t)b * P.K + k) * C4), C4);
-        const float a = nb * (l2_from_dot(dot, nsj, P.nr[(size_t)b * P.K + k]) - al);
-        if (a > bv[KMAX - 1] || (a == bv[KMAX - 1] && k < bi[KMAX - 1])) {   // sorted insertion, descending (value, -index)
+        for (int p = 0; p < KMAX; ++p) { bv[p] = -INFINITY; bi[p] = 0x7fffffff; }
+        for (int k = threadIdx.x; k < P.K; k += 256) {
+            const float dot = dot_point_major(srow, reinterpret_cast<const float4 *>(frt + ((size_t)b * P.K + k) * C4), C4);
+            const float a = nb * (l2_from_dot(dot, nsj, P.nr[(size_t)b * P.K + k]) - al);
+            if (a > bv[KMAX - 1] || (a == bv[KMAX - 1] && k < bi[KMAX - 1])) {   // sorted insertion, descending (value, -index)
 #pragma unroll
-            for (int q = KMAX - 1; q >= 0; --q) {
-                const int qm = q > 0 ? q - 1 : 0;
-                const bool shift = (q > 0) && (a > bv[qm] || (a == bv[qm] && k < bi[qm]));
-                const bool here = !shift && (a > bv[q] || (a == bv[q] && k < bi[q]));
-                bv[q] = shift ? bv[qm] : (here ? a : bv[q]);
-                bi[q] = shift ? bi[qm] : (here ? k : bi[q]);
+                for (int q = KMAX - 1; q >= 0; --q) {
+                    const int qm = q > 0 ? q - 1 : 0;
+                    const bool shift = (q > 0) && (a > bv[qm] || (a == bv[qm] && k < bi[qm]));
+                    const bool here = !shift && (a > bv[q] || (a == bv[q] && k < bi[q]));
+                    bv[q] = shift ? bv[qm] : (here ? a : bv[q]);
+                    bi[q] = shift ? bi[qm] : (here ? k : bi[q]);
+                }
             }
         }
-    }
-    const float l = lse[(size_t)b * P.J + j];
-    int64_t *oi = out_idx + ((size_t)b * P.J + j) * topk;
-    float *ow = out_w + ((size_t)b * P.J + j) * topk;
-    for (int t = 0; t < topk; ++t) {      // warp arg-max over the lane heads
-        float v = bv[0];
-        int i = bi[0], src = lane;
+        for (int t = 0; t < topk; ++t) {      // this warp's t-th best: warp arg-max over the lane heads
+            float v = bv[0];
+            int i = bi[0], src = lane;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
-            const int i2 = __shfl_xor_sync(0xffffffffu, i, o), s2 = __shfl_xor_sync(0xffffffffu, src, o);
-            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; src = s2; }
-        }
-        if (lane == src) {
+            for (int o = 16; o > 0; o >>= 1) {
+                const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+                const int i2 = __shfl_xor_sync(0xffffffffu, i, o), s2 = __shfl_xor_sync(0xffffffffu, src, o);
+                if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; src = s2; }
+            }
+            if (lane == src) {
 #pragma unroll
-            for (int q = 0; q < KMAX - 1; ++q) { bv[q] = bv[q + 1]; bi[q] = bi[q + 1]; }
-            bv[KMAX - 1] = -INFINITY; bi[KMAX - 1] = 0x7fffffff;
+                for (int q = 0; q < KMAX - 1; ++q) { bv[q] = bv[q + 1]; bi[q] = bi[q + 1]; }
+                bv[KMAX - 1] = -INFINITY; bi[KMAX - 1] = 0x7fffffff;
+            }
+            if (lane == 0) { sm_a[w][t] = v; sm_i[w][t] = i; }
         }
-        if (lane == 0) {
-            oi[t] = i == 0x7fffffff ? (int64_t)-1 : (int64_t)i;
-            ow[t] = i == 0x7fffffff ? 0.f : expf(v - l);
+        __syncthreads();
+        if (w == 0) {                          // merge the eight sorted lists: lane l < 8 walks list l
+            const float l = lse[(size_t)b * P.J + j];
+            int64_t *oi = out_idx + ((size_t)b * P.J + j) * topk;
+            float *ow = out_w + ((size_t)b * P.J + j) * topk;
+            int pos = 0;
+            for (int t = 0; t < topk; ++t) {
+                const bool have = lane < 8 && pos < topk;
+                float v = have ? sm_a[lane][pos] : -INFINITY;
+                int i = have ? sm_i[lane][pos] : 0x7fffffff, src = lane;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+                    const int i2 = __shfl_xor_sync(0xffffffffu, i, o), s2 = __shfl_xor_sync(0xffffffffu, src, o);
+                    if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; src = s2; }
+                }
+                if (lane == src) ++pos;        // (lanes 0..7 agree on the winner: the xor tree over 4, 2, 1 stays inside them)
+                if (lane == 0) {
+                    oi[t] = i == 0x7fffffff ? (int64_t)-1 : (int64_t)i;
+                    ow[t] = i == 0x7fffffff ? 0.f : expf(v - l);
+                }
+            }
         }
     }
 }
@@ -1252,11 +1276,12 @@ int launch_match_tc_topk(const MatchParams &P0, int topk, int64_t *out_idx, floa
     T.prime_div = 0;
     T.umin = (float *)(base + pl.off_umin); T.gran32 = pl.gran == 32 ? 1 : 0; T.G = pl.G;
     float *thr = (float *)(base + pl.off_thr);
+    int *ex = (int *)(base + pl.off_exrows);
     T.thr_in = thr; T.tk_cnt = (int *)(base + pl.off_tkcnt); T.tk_list = (int *)(base + pl.off_tklist); T.tk_cap = pl.cap;
     if ((rc = tc_launch_filter<1>(pl, Rdy, st))) return rc;
     const long long nrows = (long long)P.B * P.J;
     const unsigned wgrid = (unsigned)((nrows + 7) / 8);
-    topk_thr_kernel<<<wgrid, 256, 0, st>>>(T, topk, P.beta, P.alpha, thr, T.tk_cnt);
+    topk_thr_kernel<<<wgrid, 256, 0, st>>>(T, topk, P.beta, P.alpha, thr, T.tk_cnt, ex);
     DSIR_LAUNCH_CHECK();
     if ((rc = tc_launch_filter<2>(pl, Rdy, st))) return rc;
     RefineParams R{};
@@ -1266,12 +1291,12 @@ int launch_match_tc_topk(const MatchParams &P0, int topk, int64_t *out_idx, floa
     float *frt = (float *)(base + pl.off_frt);
     feat_point_major_kernel<<<dim3(cdiv(P.K, 32), cdiv(C4, 32), P.B), 256, 0, st>>>(P.fr, P.C, P.K, C4, frt);
     DSIR_LAUNCH_CHECK();
-    if (pl.cap <= 32) topk_listed_kernel<1><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w);
-    else if (pl.cap <= 64) topk_listed_kernel<2><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w);
-    else topk_listed_kernel<4><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w);
+    if (pl.cap <= 32) topk_listed_kernel<1><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w, ex);
+    else if (pl.cap <= 64) topk_listed_kernel<2><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w, ex);
+    else topk_listed_kernel<4><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w, ex);
     DSIR_LAUNCH_CHECK();
-    if (topk <= 8) topk_exact_kernel<8><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w);
-    else topk_exact_kernel<32><<<wgrid, 256, 0, st>>>(R, T.tk_cnt, T.tk_list, pl.cap, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w);
+    if (topk <= 8) topk_exact_kernel<8><<<Rdy.sms * 2, 256, 0, st>>>(R, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w, ex);
+    else topk_exact_kernel<32><<<Rdy.sms, 256, 0, st>>>(R, topk, frt, C4, P.beta, P.alpha, P.lse, out_idx, out_w, ex);
     DSIR_LAUNCH_CHECK();
     return DSIR_OK;
 }
@@ -1281,13 +1306,8 @@ int match_tc_topk_exhaustive_rows(const void *ws, int B, int C, int J, int K, in
     const TcPlan pl = make_plan(B, C, J, K, topk);
     if (!pl.gran) return DSIR_ERR_UNSUPPORTED;
     const char *base = (const char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-    std::vector<int> h((size_t)B * pl.Jpad);
-    DSIR_CUDA_TRY(cudaMemcpyAsync(h.data(), base + pl.off_tkcnt, h.size() * 4, cudaMemcpyDeviceToHost, st));
+    DSIR_CUDA_TRY(cudaMemcpyAsync(out, base + pl.off_exrows, 4, cudaMemcpyDeviceToHost, st));
     DSIR_CUDA_TRY(cudaStreamSynchronize(st));
-    int n = 0;
-    for (int b = 0; b < B; ++b)
-        for (int j = 0; j < J; ++j) { const int c = h[(size_t)b * pl.Jpad + j]; n += (c > pl.cap || c < topk) ? 1 : 0; }
-    *out = n;
     return DSIR_OK;
 }
 
