@@ -662,21 +662,29 @@ __global__ __launch_bounds__(256) void match_tc_refine_kernel(RefineParams P) {
     }
 }
 
-// exact re-scoring of the listed rows: one warp per row, one lane per candidate slot (<= 32), every qualifying lane
-// walks its own fma chain; the (value, index) lexicographic minimum wins, exactly like match_fp32_kernel.
+// exact re-scoring of the listed rows: one lane per candidate slot (S x 4 <= 32 slots per row, hence 32 / LPR rows per warp:
+// eight at S = 1), every qualifying lane walks its own fma chain; the (value, index) lexicographic minimum of a row's lanes
+// wins, exactly like match_fp32_kernel.
+template <int LPR>   // lanes per row: the candidate slots of a row (S x 4) rounded up to a power of two; 32 / LPR rows per warp
 __global__ __launch_bounds__(256) void match_tc_exact_kernel(RefineParams P) {
-    const int lane = threadIdx.x & 31;
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;
     const int count = *P.exact_count;
     const int nlist = P.S * TC_LISTS, ncand = nlist * TC_T;
-    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += gridDim.x * (blockDim.x >> 5)) {
-        const int row = P.exact_rows[i];
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int i0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; i0 < count; i0 += warps * RPW) {
+        const int i = i0 + sub;
+        const bool live = i < count;
+        const int row = live ? P.exact_rows[i] : 0;
         const int b = row / P.J, j = row % P.J;
         const size_t cbase = ((size_t)b * P.Jpad + j) * ncand;
         float v = INFINITY;
         int k = -1;
-        if (lane < ncand) { v = P.cand_val[cbase + lane]; k = P.cand_idx[cbase + lane]; }
+        if (live && sl < ncand) { v = P.cand_val[cbase + sl]; k = P.cand_idx[cbase + sl]; }
         const bool valid = k >= 0 && k < P.K && v < 1e38f;
-        const float gmin = warp_min(valid ? v : INFINITY);
+        float gmin = valid ? v : INFINITY;
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
         const float nsj = P.ns[(size_t)b * P.J + j];
         const float margin = tc_margin(nsj, P.rmax[b], P.scale[b], P.C) + fmaxf(P.xm[b], 0.f);
         const bool take = valid && v <= gmin + margin;
@@ -689,12 +697,12 @@ __global__ __launch_bounds__(256) void match_tc_exact_kernel(RefineParams P) {
             kk = k;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = LPR / 2; o > 0; o >>= 1) {
             const float d2 = __shfl_xor_sync(0xffffffffu, d, o);
             const int k2 = __shfl_xor_sync(0xffffffffu, kk, o);
             if (d2 < d || (d2 == d && k2 < kk)) { d = d2; kk = k2; }
         }
-        if (lane == 0) {
+        if (live && sl == 0) {
             const bool rescue = !(d < INFINITY);   // every qualifying distance was NaN/inf: let the exhaustive path decide
             P.idx[row] = rescue ? 0 : (int64_t)kk;
             if (P.min_d) P.min_d[row] = d;
@@ -978,9 +986,15 @@ int launch_match_tc(const MatchParams &P, void *ws, size_t ws_bytes, cudaStream_
     const long long nrows = (long long)P.B * P.J;
     match_tc_refine_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(R);
     DSIR_LAUNCH_CHECK();
-    match_tc_exact_kernel<<<sms * 8, 256, 0, st>>>(R);
+    {   // one lane per candidate slot: S x 4 slots per row -> 8, 4, 2 or 1 rows per warp
+        const int ncand = pl.S * TC_LISTS * TC_T;
+        if (ncand <= 4) match_tc_exact_kernel<4><<<sms * 8, 256, 0, st>>>(R);
+        else if (ncand <= 8) match_tc_exact_kernel<8><<<sms * 8, 256, 0, st>>>(R);
+        else if (ncand <= 16) match_tc_exact_kernel<16><<<sms * 8, 256, 0, st>>>(R);
+        else match_tc_exact_kernel<32><<<sms * 8, 256, 0, st>>>(R);
+    }
     DSIR_LAUNCH_CHECK();
-    match_tc_rescue_kernel<<<sms * 4, 256, 0, st>>>(R, R.rescue_keys);
+    match_tc_rescue_kernel<<<sms * 16, 256, 0, st>>>(R, R.rescue_keys);   // (row, 256-column chunk) units: one per CTA for a few rows
     DSIR_LAUNCH_CHECK();
     match_tc_rescue_finalize_kernel<<<sms, 256, 0, st>>>(R, R.rescue_keys);
     DSIR_LAUNCH_CHECK();
