@@ -196,6 +196,14 @@ def fuzz_loop(rng, seed):
     tr_o, pred_o, xyz_o = O.align_loop(b["feat_src"], b["feat_ref"], xs, xr, b["weights"], iters)
     tr, pred, xyz, st = D.align_loop(cu(b["feat_src"]), cu(b["feat_ref"]), cu(xs), cu(xr), cu(b["weights"]), iters)
     msg = []
+    p0, p0o = pred[0].cpu(), pred_o[0]
+    if not torch.equal(p0, p0o):
+        # iteration 0 sees identical inputs: a row may differ only where the fp64 top-2 gap is below fp32 round-off (the
+        # reference's own sgemm order decides such rows); one flipped correspondence moves every later pose, so the trial
+        # is then judged on iteration 0 alone (seed 12345041468: fp32 distances equal, fp64 gap 3.0e-7)
+        _, gap = O.match_top2_fp64(b["feat_src"], b["feat_ref"])
+        if bool((gap[p0 != p0o] < 2e-6).all()):
+            return f"loop {kind} B{B} C{C} N{n} iters{iters} (tie-ambiguous row at iteration 0)", msg
     if not torch.equal(torch.stack(pred).cpu(), torch.stack(pred_o)):
         msg.append(f"{(torch.stack(pred).cpu() != torch.stack(pred_o)).sum().item()} correspondences differ")
     for i in range(iters):
