@@ -49,6 +49,13 @@ def test_workspace_queries_are_pure(built):
     assert L.dsir_match_argmin_workspace_bytes(1, 64, 1000, 1000, 1) >= 8000
     assert L.dsir_kabsch_workspace_bytes(4, 16384) >= 4 * 17 * 8
     assert L.dsir_align_loop_workspace_bytes(2, 64, 512, 512, 0) > 0
+    # top-k soft match: never less than the plain soft pass, and the route query is a pure function of the shape
+    base = L.dsir_match_soft_workspace_bytes(4, 32, 5000, 5000)
+    assert L.dsir_match_soft_topk_workspace_bytes(4, 32, 5000, 5000, 0) == base
+    assert L.dsir_match_soft_topk_workspace_bytes(4, 32, 5000, 5000, 16) > base
+    assert L.dsir_match_soft_topk_fused(4, 32, 5000, 5000, 16) in (0, 1)       # 1 only where a driver (TMA descriptors) exists
+    assert L.dsir_match_soft_topk_fused(4, 32, 5000, 200, 32) == 0             # 7 granules of 32 columns < 1.25 x 32
+    assert L.dsir_match_soft_topk_fused(4, 65, 5000, 5000, 16) == 0            # C > 64: fp32 CUDA-core route
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-box behaviour")
