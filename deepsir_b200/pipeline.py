@@ -82,6 +82,13 @@ class RegistrationPipeline:
         out["status"].copy_(status, non_blocking=True)
         if self.keep_graph:
             out["graph_src"], out["graph_ref"] = g_src, g_ref
+            # produced on the KNN stream, consumed by the caller on the compute stream: tell the caching allocator, so that a
+            # tensor dropped while the caller's kernels still read it is not recycled under them
+            for g in (g_src, g_ref):
+                for lst in g.values():
+                    for t in (lst if isinstance(lst, (list, tuple)) else [lst]):
+                        if torch.is_tensor(t):
+                            t.record_stream(compute)
         done = torch.cuda.Event()
         done.record(compute)
         return out, (done, knn_done)
