@@ -58,11 +58,6 @@ constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 static_assert(SF_RBS * SF_ACC * 128 == 512 && SF_HALVES == 1 && SF_RBS % SF_MMA_WARPS == 0, "TMEM / warp budget");
 
 // explicit shared-space loads (the generic pointer arithmetic on the dynamic smem base would compile to generic LD)
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ float2 lds64(uint32_t addr) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
