@@ -529,15 +529,13 @@ __global__ __launch_bounds__(TREE_QWARPS * 32) void knn_tree_query_kernel(KnnTre
         // compaction: keep the pairs with d <= k-th distance
         int mx = __reduce_max_sync(FULL, cnt);
         int w = 0;
-        for (int j = 0; j < mx; ++j) {
-            if (j < cnt) {
-                const float d = qd[j * 32];
-                if (d <= thr) {
-                    const unsigned short id = qi[j * 32];
-                    qd[w * 32] = d; qi[w * 32] = id;
-                    ++w;
-                }
-            }
+#pragma unroll 4
+        for (int j = 0; j < mx; ++j) {       // branch-free: predicated loads / stores (slots beyond cnt are inside the buffer)
+            const float d = qd[j * 32];
+            const unsigned short id = qi[j * 32];
+            const bool keep = j < cnt && d <= thr;
+            if (keep) { qd[w * 32] = d; qi[w * 32] = id; }
+            w += keep ? 1 : 0;
         }
         // more than k survivors: ties at the k-th distance -> drop the tied entries with the largest indices
         if (__any_sync(FULL, w > k)) {
